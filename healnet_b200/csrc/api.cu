@@ -1,0 +1,878 @@
+// api.cu — the C ABI of libhealnet_b200.so (include/healnet_b200.h): handle management, weight
+// registration / repacking, and the stream-ordered orchestration of one HealNet.forward
+// (reference healnet/models/healnet.py:190-250) as a fixed sequence of the sm_100a kernels in
+// rowops.cu / gemm.cu / xattn.cu. No host synchronisation, no allocation inside hn_forward.
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <new>
+#include <vector>
+
+#include "../../include/healnet_b200.h"
+#include "common.cuh"
+#include "pack.cuh"
+
+namespace hn {
+namespace {
+thread_local std::string g_error;
+}
+void set_error(const std::string& msg) { g_error = msg; }
+const char* get_error() { return g_error.c_str(); }
+
+namespace {
+
+constexpr int HP = 64;  // head pitch: every head occupies 64 columns of Q / K / V / O (zero padded)
+constexpr float LOG2E = 1.4426950408889634074f;
+
+// bump allocator over a caller-provided (or handle-owned) device buffer; 256-byte aligned pieces
+struct Arena {
+  char* base = nullptr;
+  size_t off = 0;
+  template <typename T>
+  T* take(size_t count) {
+    off = (off + 255) & ~size_t(255);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += count * sizeof(T);
+    return p;
+  }
+};
+
+struct AttnPacked {     // one PreNorm(Attention) module
+  bool small = false;   // reassociated small-context path (cross-attention with C <= 63)
+  int zw = 0;           // small path: width of a z row (32 or 64)
+  int C = 0;            // context width (cross) or D (self)
+  // generic / self
+  // all fp16 weight rows are split [hi (seg cols) | lo (seg cols)], seg = round_up(K, 64)
+  __half* Wq = nullptr;     // cross generic: [H*64][2 segD] scaled;  self: [3*lH*64][2 segD] (Q scaled | K | V)
+  __half* Wkv = nullptr;    // cross generic: [2*H*64][2 segC], context-LN gamma folded
+  float* bkv = nullptr;     // cross generic: [2*H*64], context-LN beta folded (K part zero: it cancels in softmax)
+  // small (used when the token axis is long; short axes take the generic precise path whatever C is)
+  __half* WqS = nullptr;    // [H*zw][2 segD]  Wk^T Wq reassociated, gamma and scale folded
+  float* Wv = nullptr;      // [I][zw]  gamma folded
+  float* bv = nullptr;      // [I]      beta folded
+  __half* Wo = nullptr;     // [D][2 * H*64] head-padded columns
+};
+struct FFPacked {
+  __half* W1 = nullptr;  // [8D][2 segD] rows interleaved (a_j, g_j)
+  float* b1 = nullptr;   // [8D] interleaved
+  __half* W2 = nullptr;  // [D][2 seg4D]
+};
+struct SlotKey {
+  std::vector<const void*> ptrs;
+  bool operator<(const SlotKey& o) const { return ptrs < o.ptrs; }
+};
+
+}  // namespace
+}  // namespace hn
+
+using namespace hn;
+
+struct hn_handle {
+  hn_desc d;
+  int M = 0, I = 0, lI = 0;
+  int segD = 0, seg4D = 0;        // hi/lo segment widths of D-wide / 4D-wide split operands (multiples of 64)
+  int C[HN_MAX_MODALITIES];       // context width per modality
+  // registered fp32 parameters: index (layer + 1) * slots_per_layer + slot
+  int slots_per_layer = 0;
+  std::vector<std::vector<const float*>> w;
+  // packed store
+  void* packed = nullptr;
+  size_t packed_bytes = 0;
+  bool packed_valid = false;
+  std::vector<AttnPacked> attn;   // [layer][M + 1] (index M = latent self-attention)
+  std::vector<FFPacked> ff;       // [layer][M + 1]
+  int launches = 0;
+  // optional per-launch timing of the cross-attention kernels (bench.py roofline): CUDA event pairs on the
+  // forward's own stream, one pair per (layer, modality), read back after the caller synchronises
+  bool profile = false;
+  std::vector<cudaEvent_t> ev;          // 2 per slot
+  std::vector<int> ev_mod;              // modality of each recorded slot in the last forward
+  std::vector<double> ev_flops;         // tensor-core FLOPs the launch executed (padded tiles included)
+  std::vector<double> ev_exps;          // softmax exponentials the launch evaluated
+};
+
+namespace {
+
+int slot_index(const hn_handle* h, int layer, int slot) { return (layer + 1) * h->slots_per_layer + slot; }
+
+int ctx_ld(int C) { return round_up(C, 8); }
+int seg_of(int K) { return round_up(K, 64); }
+// token axes up to this length run the precise (split hi/lo) attention + K/V projection
+constexpr long PRECISE_MAX_TOKENS = 2048;
+
+// sizes (or carves, when arena.base != null) the packed store; dedupes tied layers by pointer identity
+int plan_packed(hn_handle* h, Arena& ar) {
+  const hn_desc& d = h->d;
+  const int M = h->M, D = d.l_d;
+  std::map<SlotKey, AttnPacked> attn_seen;
+  std::map<SlotKey, FFPacked> ff_seen;
+  h->attn.assign(static_cast<size_t>(d.depth) * (M + 1), AttnPacked());
+  h->ff.assign(static_cast<size_t>(d.depth) * (M + 1), FFPacked());
+  for (int l = 0; l < d.depth; ++l) {
+    for (int m = 0; m <= M; ++m) {
+      const bool self = (m == M);
+      if (self && d.self_per_cross_attn == 0) continue;
+      const std::vector<const float*>& wa = h->w[slot_index(h, l, 2 * m)];
+      const std::vector<const float*>& wf = h->w[slot_index(h, l, 2 * m + 1)];
+      HN_REQUIRE(!wa.empty() && !wf.empty(), "hn_pack_weights: a layer slot has no registered weights");
+      SlotKey ka{std::vector<const void*>(wa.begin(), wa.end())};
+      ka.ptrs.push_back(reinterpret_cast<const void*>(static_cast<intptr_t>(self ? -1 : h->C[m])));
+      auto ita = attn_seen.find(ka);
+      if (ita != attn_seen.end()) {
+        h->attn[l * (M + 1) + m] = ita->second;
+      } else {
+        AttnPacked p;
+        if (self) {
+          p.C = D;
+          p.Wq = ar.take<__half>(static_cast<size_t>(3) * d.l_heads * HP * 2 * h->segD);
+          p.Wo = ar.take<__half>(static_cast<size_t>(D) * 2 * d.l_heads * HP);
+        } else {
+          p.C = h->C[m];
+          p.small = p.C <= 63;
+          if (p.small) {
+            p.zw = p.C <= 31 ? 32 : 64;
+            p.WqS = ar.take<__half>(static_cast<size_t>(d.x_heads) * p.zw * 2 * h->segD);
+            p.Wv = ar.take<float>(static_cast<size_t>(h->I) * p.zw);
+            p.bv = ar.take<float>(h->I);
+          }
+          p.Wq = ar.take<__half>(static_cast<size_t>(d.x_heads) * HP * 2 * h->segD);
+          p.Wkv = ar.take<__half>(static_cast<size_t>(2) * d.x_heads * HP * 2 * seg_of(p.C));
+          p.bkv = ar.take<float>(static_cast<size_t>(2) * d.x_heads * HP);
+          p.Wo = ar.take<__half>(static_cast<size_t>(D) * 2 * d.x_heads * HP);
+        }
+        attn_seen[ka] = p;
+        h->attn[l * (M + 1) + m] = p;
+      }
+      SlotKey kf{std::vector<const void*>(wf.begin(), wf.end())};
+      auto itf = ff_seen.find(kf);
+      if (itf != ff_seen.end()) {
+        h->ff[l * (M + 1) + m] = itf->second;
+      } else {
+        FFPacked p;
+        p.W1 = ar.take<__half>(static_cast<size_t>(8) * D * 2 * h->segD);
+        p.b1 = ar.take<float>(static_cast<size_t>(8) * D);
+        p.W2 = ar.take<__half>(static_cast<size_t>(D) * 2 * h->seg4D);
+        ff_seen[kf] = p;
+        h->ff[l * (M + 1) + m] = p;
+      }
+    }
+  }
+  return 0;
+}
+
+struct ModPlan {
+  bool present = false;
+  bool small = false;
+  int zw = 0;       // small: z row width
+  int ldz = 0;      // generic: z row pitch
+  bool precise = false;  // generic: short token axis -> split z / K / V / Q and the precise attention kernel
+  int segC = 0;
+  int C = 0, c_raw = 0, n_axes = 0;
+  int axes[HN_MAX_AXES];
+  long N = 0;
+  int nsplit = 1;
+  bool masked = false;
+  float* tab = nullptr;
+  __half* z = nullptr;
+};
+
+struct Workspace {
+  ModPlan mod[HN_MAX_MODALITIES];
+  float* x = nullptr;        // [b*L][D] fp32 residual stream
+  __half* xn = nullptr;      // [b*L][2 segD]       split
+  __half* q = nullptr;       // [b*L][2 qw]         split (small-C Q': hi only)
+  __half* o = nullptr;       // [b*L][2 ow]         split
+  __half* hid = nullptr;     // [b*L][2 seg4D]      split
+  __half* kv = nullptr;      // [b*Nmax][2*H*64] (x2 when precise)   (generic cross-attention only)
+  bool self_precise = false;
+  float* part_acc = nullptr;
+  float* part_ml = nullptr;
+  uint64_t* mask_bits = nullptr;
+  int self_nsplit = 1;
+  size_t bytes = 0;
+};
+
+// Lays the forward workspace out over `base` (null: sizing pass). present[m] tells which modalities are given.
+int plan_workspace(const hn_handle* h, int batch, const int* axis_sizes, const bool* present, long mask_tokens,
+                   char* base, Workspace& ws) {
+  const hn_desc& d = h->d;
+  const int M = h->M, L = d.l_c, D = d.l_d;
+  Arena ar;
+  ar.base = base;
+  const long rows = static_cast<long>(batch) * L;
+  ws.x = ar.take<float>(rows * D);
+  ws.xn = ar.take<__half>(rows * 2 * h->segD);
+  int qw = d.self_per_cross_attn ? 3 * d.l_heads * HP : 0;
+  int ow = d.self_per_cross_attn ? d.l_heads * HP : 0;
+  size_t part_acc_elems = 0, part_ml_elems = 0, kv_elems = 0, mask_words = 0;
+  const int n_ltiles = (L + 127) / 128;
+  ws.self_precise = L <= PRECISE_MAX_TOKENS;
+  if (d.self_per_cross_attn) {
+    ws.self_nsplit = attention_pick_nsplit(batch, L, d.l_heads, L);
+    part_acc_elems = static_cast<size_t>(batch) * ws.self_nsplit * d.l_heads * n_ltiles * 128 * 64;
+    part_ml_elems = static_cast<size_t>(batch) * ws.self_nsplit * d.l_heads * n_ltiles * 128 * 2;
+  }
+  for (int m = 0; m < M; ++m) {
+    ModPlan& mp = ws.mod[m];
+    mp = ModPlan();
+    mp.present = present ? present[m] : true;
+    if (!mp.present) continue;
+    mp.n_axes = d.num_spatial_axes[m];
+    mp.c_raw = d.channel_dims[m];
+    mp.C = h->C[m];
+    mp.N = 1;
+    for (int a = 0; a < mp.n_axes; ++a) {
+      mp.axes[a] = axis_sizes[m * HN_MAX_AXES + a];
+      HN_REQUIRE(mp.axes[a] >= 1, "hn_forward: axis sizes must be >= 1");
+      mp.N *= mp.axes[a];
+    }
+    HN_REQUIRE(mp.N < (1L << 31), "hn_forward: token axis too long");
+    mp.small = mp.C <= 63 && mp.N > PRECISE_MAX_TOKENS;
+    mp.masked = (mask_tokens > 0 && mask_tokens == mp.N);
+    int axsum = 0;
+    for (int a = 0; a < mp.n_axes; ++a) axsum += mp.axes[a];
+    mp.tab = ar.take<float>(static_cast<size_t>(axsum) * (2 * d.num_freq_bands + 1));
+    const int vd = mp.small ? (mp.C <= 31 ? 32 : 64) : 64;
+    if (mp.small) {
+      mp.zw = vd;
+      mp.z = ar.take<__half>(static_cast<size_t>(batch) * mp.N * mp.zw);
+      qw = qw > d.x_heads * mp.zw ? qw : d.x_heads * mp.zw;
+    } else {
+      mp.precise = mp.N <= PRECISE_MAX_TOKENS;
+      mp.segC = seg_of(mp.C);
+      mp.ldz = mp.precise ? 2 * mp.segC : ctx_ld(mp.C);
+      mp.z = ar.take<__half>(static_cast<size_t>(batch) * mp.N * mp.ldz);
+      const size_t kv = static_cast<size_t>(batch) * mp.N * 2 * d.x_heads * HP * (mp.precise ? 2 : 1);
+      kv_elems = kv > kv_elems ? kv : kv_elems;
+      qw = qw > d.x_heads * HP ? qw : d.x_heads * HP;
+    }
+    ow = ow > d.x_heads * HP ? ow : d.x_heads * HP;
+    mp.nsplit = attention_pick_nsplit(batch, L, d.x_heads, mp.N);
+    const size_t pa = static_cast<size_t>(batch) * mp.nsplit * d.x_heads * n_ltiles * 128 * vd;
+    const size_t pm = static_cast<size_t>(batch) * mp.nsplit * d.x_heads * n_ltiles * 128 * 2;
+    part_acc_elems = pa > part_acc_elems ? pa : part_acc_elems;
+    part_ml_elems = pm > part_ml_elems ? pm : part_ml_elems;
+    if (mp.masked) mask_words = static_cast<size_t>(batch) * ((mp.N + 63) / 64);
+  }
+  ws.q = ar.take<__half>(rows * 2 * (qw > 8 ? qw : 8));
+  ws.o = ar.take<__half>(rows * 2 * (ow > 8 ? ow : 8));
+  ws.hid = ar.take<__half>(rows * 2 * h->seg4D);
+  ws.kv = ar.take<__half>(kv_elems);
+  ws.part_acc = ar.take<float>(part_acc_elems);
+  ws.part_ml = ar.take<float>(part_ml_elems);
+  ws.mask_bits = ar.take<uint64_t>(mask_words);
+  ws.bytes = ar.off + 256;
+  return 0;
+}
+
+#define HN_TRY(expr)          \
+  do {                        \
+    int _rc = (expr);         \
+    if (_rc != 0) return _rc; \
+    ++h->launches;            \
+  } while (0)
+
+int profile_begin(hn_handle* h, int modality, const AttnArgs& a, cudaStream_t st) {
+  if (!h->profile) return 0;
+  const size_t slot = h->ev_mod.size();
+  while (h->ev.size() < 2 * (slot + 1)) {
+    cudaEvent_t e;
+    HN_CHECK_CUDA(cudaEventCreate(&e));
+    h->ev.push_back(e);
+  }
+  const double rows = static_cast<double>((a.L + 127) / 128) * 128.0, toks = static_cast<double>((a.N + 63) / 64) * 64.0;
+  const double kd = a.shared_kv ? a.kd : 64.0;
+  const double passes = a.precise ? 5.0 : 2.0;  // S: 3 + PV: 2 products in precise mode, else 1 + 1
+  h->ev_mod.push_back(modality);
+  h->ev_flops.push_back(static_cast<double>(a.batch) * a.H * rows * toks * 2.0 * kd * passes);
+  h->ev_exps.push_back(static_cast<double>(a.batch) * a.H * rows * toks);
+  HN_CHECK_CUDA(cudaEventRecord(h->ev[2 * slot], st));
+  return 0;
+}
+void profile_end(hn_handle* h, cudaStream_t st) {
+  if (!h->profile) return;
+  cudaEventRecord(h->ev[2 * (h->ev_mod.size() - 1) + 1], st);
+}
+
+// x += FeedForward(LN(x))   (healnet.py:237/245, 339-351)
+int run_ff(hn_handle* h, const std::vector<const float*>& wf, const FFPacked& fp, Workspace& ws, long rows,
+           cudaStream_t st) {
+  const hn_desc& d = h->d;
+  const int D = d.l_d;
+  const int sD = h->segD, s4 = h->seg4D;
+  HN_TRY(launch_layernorm_f16(ws.x, D, wf[0], wf[1], ws.xn, 2 * sD, sD, sD, rows, D, st));
+  GemmArgs g1{ws.xn, fp.W1, static_cast<int>(rows), 8 * D, D, 2 * sD, 2 * sD, EPI_GATE_F16,
+              d.snn ? ACT_SELU : ACT_GELU, fp.b1, ws.hid, 2 * s4, 3, sD, sD, s4};
+  HN_TRY(launch_gemm(g1, st));
+  GemmArgs g2{ws.hid, fp.W2, static_cast<int>(rows), D, 4 * D, 2 * s4, 2 * s4, EPI_RES, 0, wf[5], ws.x, D, 3, s4, s4, 0};
+  HN_TRY(launch_gemm(g2, st));
+  return 0;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+const char* hn_last_error(void) { return hn::get_error(); }
+
+int hn_create(const hn_desc* desc, hn_handle** out) {
+  HN_REQUIRE(desc != nullptr && out != nullptr, "hn_create: null argument");
+  const hn_desc& d = *desc;
+  HN_REQUIRE(d.n_modalities >= 1 && d.n_modalities <= HN_MAX_MODALITIES, "hn_create: 1..16 modalities supported");
+  HN_REQUIRE(d.depth >= 1, "hn_create: depth must be >= 1");
+  HN_REQUIRE(d.l_c >= 1 && d.l_d >= 1, "hn_create: latent array must be non-empty");
+  HN_REQUIRE(d.x_heads >= 1 && d.l_heads >= 1, "hn_create: head counts must be >= 1");
+  HN_REQUIRE(d.cross_dim_head >= 1 && d.cross_dim_head <= HP, "hn_create: cross_dim_head must be in 1..64");
+  HN_REQUIRE(d.latent_dim_head >= 1 && d.latent_dim_head <= HP, "hn_create: latent_dim_head must be in 1..64");
+  HN_REQUIRE(d.self_per_cross_attn == 0 || d.self_per_cross_attn == 1,
+             "hn_create: self_per_cross_attn must be 0 or 1 (the reference fails for >= 2, healnet.py:242)");
+  HN_REQUIRE(d.num_freq_bands >= 1 || !d.fourier_encode_data, "hn_create: num_freq_bands must be >= 1");
+  HN_REQUIRE(!d.final_classifier_head || d.out_dims >= 1, "hn_create: out_dims must be >= 1");
+  hn_handle* h = new (std::nothrow) hn_handle();
+  HN_REQUIRE(h != nullptr, "hn_create: out of host memory");
+  h->d = d;
+  h->M = d.n_modalities;
+  h->I = d.x_heads * d.cross_dim_head;
+  h->lI = d.l_heads * d.latent_dim_head;
+  h->segD = round_up(d.l_d, 64);
+  h->seg4D = round_up(4 * d.l_d, 64);
+  for (int m = 0; m < h->M; ++m) {
+    if (!(d.num_spatial_axes[m] >= 1 && d.num_spatial_axes[m] <= HN_MAX_AXES && d.channel_dims[m] >= 1)) {
+      delete h;
+      set_error("hn_create: each modality needs 1..4 spatial axes and >= 1 channel");
+      return -1;
+    }
+    h->C[m] = d.channel_dims[m] + (d.fourier_encode_data ? d.num_spatial_axes[m] * (2 * d.num_freq_bands + 1) : 0);
+  }
+  h->slots_per_layer = 2 * h->M + 2;
+  h->w.assign(static_cast<size_t>(d.depth + 1) * h->slots_per_layer, std::vector<const float*>());
+  *out = h;
+  return 0;
+}
+
+int hn_destroy(hn_handle* h) {
+  if (h == nullptr) return 0;
+  if (h->packed != nullptr) cudaFree(h->packed);
+  for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+  delete h;
+  return 0;
+}
+
+int hn_set_weights(hn_handle* h, int layer, int slot, const void* const* dev_ptrs, int n) {
+  HN_REQUIRE(h != nullptr && dev_ptrs != nullptr, "hn_set_weights: null argument");
+  HN_REQUIRE(layer >= -1 && layer < h->d.depth, "hn_set_weights: layer out of range");
+  int expect;
+  if (layer == -1) {
+    HN_REQUIRE(slot == 0 || slot == 1, "hn_set_weights: layer -1 has slots 0 (latents) and 1 (to_logits)");
+    expect = slot == 0 ? 1 : 4;
+  } else {
+    HN_REQUIRE(slot >= 0 && slot < 2 * h->M + 2, "hn_set_weights: slot out of range");
+    expect = (slot % 2 == 1) ? 6 : (slot < 2 * h->M ? 8 : 6);
+  }
+  HN_REQUIRE(n == expect, "hn_set_weights: wrong number of tensors for this slot");
+  std::vector<const float*> v(n);
+  for (int i = 0; i < n; ++i) {
+    HN_REQUIRE(dev_ptrs[i] != nullptr, "hn_set_weights: null tensor pointer");
+    v[i] = static_cast<const float*>(dev_ptrs[i]);
+  }
+  std::vector<const float*>& dst = h->w[slot_index(h, layer, slot)];
+  if (dst != v) {
+    dst = v;
+    h->packed_valid = false;
+  }
+  return 0;
+}
+
+int hn_pack_weights(hn_handle* h, void* cuda_stream) {
+  HN_REQUIRE(h != nullptr, "hn_pack_weights: null handle");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  const hn_desc& d = h->d;
+  const int M = h->M, D = d.l_d, sD = h->segD;
+  Arena sizing;
+  int rc = plan_packed(h, sizing);
+  if (rc != 0) return rc;
+  const size_t need = sizing.off + 256;
+  if (h->packed == nullptr || h->packed_bytes < need) {
+    if (h->packed != nullptr) {
+      HN_CHECK_CUDA(cudaStreamSynchronize(st));
+      cudaFree(h->packed);
+      h->packed = nullptr;
+    }
+    HN_CHECK_CUDA(cudaMalloc(&h->packed, need));
+    h->packed_bytes = need;
+  }
+  Arena ar;
+  ar.base = static_cast<char*>(h->packed);
+  rc = plan_packed(h, ar);
+  if (rc != 0) return rc;
+  std::map<const void*, bool> done;
+  for (int l = 0; l < d.depth; ++l) {
+    for (int m = 0; m <= M; ++m) {
+      const bool self = (m == M);
+      if (self && d.self_per_cross_attn == 0) continue;
+      const std::vector<const float*>& wa = h->w[slot_index(h, l, 2 * m)];
+      const std::vector<const float*>& wf = h->w[slot_index(h, l, 2 * m + 1)];
+      const AttnPacked& ap = h->attn[l * (M + 1) + m];
+      const FFPacked& fp = h->ff[l * (M + 1) + m];
+      if (!done[ap.Wq]) {
+        done[ap.Wq] = true;
+        if (self) {
+          // {norm.w, norm.b, to_q.w [lI][D], to_kv.w [2lI][D], to_out.w [D][lI], to_out.b}
+          const int lh = d.l_heads, ldh = d.latent_dim_head;
+          const float scale = 2.f / std::sqrt(static_cast<float>(ldh)) * LOG2E;
+          rc = pack_headpad_rows(ap.Wq, 2 * sD, 0, wa[2], D, 0, lh, ldh, D, scale, nullptr, sD, sD, st);
+          if (rc == 0) rc = pack_headpad_rows(ap.Wq, 2 * sD, lh * HP, wa[3], D, 0, lh, ldh, D, 1.f, nullptr, sD, sD, st);
+          if (rc == 0)
+            rc = pack_headpad_rows(ap.Wq, 2 * sD, 2 * lh * HP, wa[3], D, h->lI, lh, ldh, D, 1.f, nullptr, sD, sD, st);
+          if (rc == 0) rc = pack_headpad_cols(ap.Wo, 2 * lh * HP, wa[4], h->lI, D, lh, ldh, lh * HP, lh * HP, st);
+        } else {
+          // {norm.w, norm.b, norm_context.w, norm_context.b, to_q.w [I][D], to_kv.w [2I][C], to_out.w [D][I], to_out.b}
+          const int H = d.x_heads, dh = d.cross_dim_head, C = ap.C;
+          const float scale = 2.f / std::sqrt(static_cast<float>(dh)) * LOG2E;
+          if (ap.small) {
+            rc = pack_smallc_q(ap.WqS, 2 * sD, wa[4], wa[5], wa[2], H, D, C, dh, scale, ap.zw, sD, sD, st);
+            if (rc == 0) rc = pack_smallc_v(ap.Wv, ap.bv, wa[5], wa[2], wa[3], h->I, C, ap.zw, st);
+          }
+          if (rc == 0) {
+            const int sC = seg_of(C);
+            rc = pack_headpad_rows(ap.Wq, 2 * sD, 0, wa[4], D, 0, H, dh, D, scale, nullptr, sD, sD, st);
+            if (rc == 0) rc = pack_headpad_rows(ap.Wkv, 2 * sC, 0, wa[5], C, 0, H, dh, C, 1.f, wa[2], sC, sC, st);
+            if (rc == 0)
+              rc = pack_headpad_rows(ap.Wkv, 2 * sC, H * HP, wa[5], C, h->I, H, dh, C, 1.f, wa[2], sC, sC, st);
+            if (rc == 0) HN_CHECK_CUDA(cudaMemsetAsync(ap.bkv, 0, sizeof(float) * H * HP, st));
+            if (rc == 0) rc = fold_beta_headpad(ap.bkv, H * HP, wa[5], C, h->I, H, dh, C, wa[3], st);
+          }
+          if (rc == 0) rc = pack_headpad_cols(ap.Wo, 2 * H * HP, wa[6], h->I, D, H, dh, H * HP, H * HP, st);
+        }
+        if (rc != 0) return rc;
+      }
+      if (!done[fp.W1]) {
+        done[fp.W1] = true;
+        // {norm.w, norm.b, net.0.w [8D][D], net.0.b [8D], net.2.w [D][4D], net.2.b [D]}
+        rc = pack_ff1(fp.W1, 2 * sD, fp.b1, wf[2], wf[3], D, 4 * D, sD, sD, st);
+        if (rc == 0) rc = pack_plain(fp.W2, 2 * h->seg4D, wf[4], 4 * D, D, 4 * D, h->seg4D, h->seg4D, st);
+        if (rc != 0) return rc;
+      }
+    }
+  }
+  h->packed_valid = true;
+  return 0;
+}
+
+size_t hn_workspace_bytes(const hn_handle* h, int batch, const int* axis_sizes) {
+  if (h == nullptr || batch < 1 || axis_sizes == nullptr) {
+    set_error("hn_workspace_bytes: bad argument");
+    return 0;
+  }
+  Workspace ws;
+  // size for the worst case: every modality present and masked
+  long mask_tokens = 0;
+  for (int m = 0; m < h->M; ++m) {
+    long n = 1;
+    for (int a = 0; a < h->d.num_spatial_axes[m]; ++a) n *= axis_sizes[m * HN_MAX_AXES + a];
+    mask_tokens = n > mask_tokens ? n : mask_tokens;
+  }
+  if (plan_workspace(h, batch, axis_sizes, nullptr, 0, nullptr, ws) != 0) return 0;
+  return ws.bytes + static_cast<size_t>(batch) * ((mask_tokens + 63) / 64) * 8 + 256;
+}
+
+int hn_last_launch_count(const hn_handle* h) { return h ? h->launches : 0; }
+
+int hn_profile_enable(hn_handle* h, int on) {
+  HN_REQUIRE(h != nullptr, "hn_profile_enable: null handle");
+  h->profile = on != 0;
+  return 0;
+}
+
+int hn_profile_read(hn_handle* h, int modality, float* ms, int* launches, double* flops, double* exps) {
+  HN_REQUIRE(h != nullptr && ms && launches && flops && exps, "hn_profile_read: null argument");
+  *ms = 0.f;
+  *launches = 0;
+  *flops = 0.0;
+  *exps = 0.0;
+  for (size_t i = 0; i < h->ev_mod.size(); ++i) {
+    if (h->ev_mod[i] != modality) continue;
+    float t = 0.f;
+    HN_CHECK_CUDA(cudaEventElapsedTime(&t, h->ev[2 * i], h->ev[2 * i + 1]));
+    *ms += t;
+    *launches += 1;
+    *flops += h->ev_flops[i];
+    *exps += h->ev_exps[i];
+  }
+  return 0;
+}
+
+int hn_forward(hn_handle* h, int batch, const void* const* modality_ptrs, const int* axis_sizes,
+               const int* skip_latent_block, const uint8_t* mask, long mask_tokens, float* latents_out,
+               float* logits_out, void* workspace, size_t workspace_bytes, void* cuda_stream) {
+  HN_REQUIRE(h != nullptr && modality_ptrs != nullptr && axis_sizes != nullptr, "hn_forward: null argument");
+  HN_REQUIRE(batch >= 1, "hn_forward: batch must be >= 1");
+  HN_REQUIRE(h->packed_valid, "hn_forward: call hn_pack_weights after registering / changing weights");
+  HN_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+             "hn_forward: workspace must be a 256-byte aligned device buffer");
+  HN_REQUIRE(latents_out != nullptr || logits_out != nullptr, "hn_forward: no output requested");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  const hn_desc& d = h->d;
+  const int M = h->M, L = d.l_c, D = d.l_d;
+  const long rows = static_cast<long>(batch) * L;
+  HN_REQUIRE(rows < (1L << 31), "hn_forward: batch * l_c too large");
+  if (logits_out != nullptr) HN_REQUIRE(d.final_classifier_head, "hn_forward: model has no classifier head");
+  const std::vector<const float*>& wl = h->w[slot_index(h, -1, 0)];
+  HN_REQUIRE(wl.size() == 1, "hn_forward: latents not registered");
+  if (logits_out != nullptr) HN_REQUIRE(h->w[slot_index(h, -1, 1)].size() == 4, "hn_forward: to_logits not registered");
+
+  bool present[HN_MAX_MODALITIES];
+  for (int m = 0; m < M; ++m) present[m] = modality_ptrs[m] != nullptr;
+  if (mask == nullptr) mask_tokens = 0;
+  Workspace ws;
+  int rc = plan_workspace(h, batch, axis_sizes, present, mask_tokens, static_cast<char*>(workspace), ws);
+  if (rc != 0) return rc;
+  HN_REQUIRE(ws.bytes <= workspace_bytes, "hn_forward: workspace too small (see hn_workspace_bytes)");
+  h->launches = 0;
+  h->ev_mod.clear();
+  h->ev_flops.clear();
+  h->ev_exps.clear();
+
+  // ---- once per forward: positional tables + standardised context rows (shared by all layers)
+  const int sD = h->segD;
+  if (h->seg4D != 4 * D)  // pad columns of the split hidden rows are never written by the gate epilogue
+    HN_CHECK_CUDA(cudaMemsetAsync(ws.hid, 0, sizeof(__half) * rows * 2 * h->seg4D, st));
+  bool mask_packed = false;
+  for (int m = 0; m < M; ++m) {
+    ModPlan& mp = ws.mod[m];
+    if (!mp.present) continue;
+    const float* raw = static_cast<const float*>(modality_ptrs[m]);
+    if (d.fourier_encode_data)
+      HN_TRY(launch_axis_tables(mp.tab, mp.axes, mp.n_axes, d.num_freq_bands, d.max_freq, st));
+    if (mp.small)
+      HN_TRY(launch_build_z_small(raw, mp.z, mp.zw, batch, mp.N, mp.c_raw, mp.n_axes, mp.axes, d.num_freq_bands,
+                                  mp.tab, d.fourier_encode_data, st));
+    else
+      HN_TRY(launch_build_z_large(raw, mp.z, mp.ldz, mp.precise ? mp.segC : 0, batch, mp.N, mp.c_raw, mp.n_axes,
+                                  mp.axes, d.num_freq_bands, mp.tab, d.fourier_encode_data, st));
+    if (mp.masked && !mask_packed) {
+      HN_TRY(launch_pack_mask(mask, ws.mask_bits, batch, mp.N, st));
+      mask_packed = true;
+    }
+  }
+  // ---- x = repeat(latents, 'n d -> b n d')   (healnet.py:225)
+  HN_TRY(launch_broadcast_rows(wl[0], ws.x, static_cast<long>(L) * D, batch, st));
+
+  for (int l = 0; l < d.depth; ++l) {
+    for (int m = 0; m < M; ++m) {
+      ModPlan& mp = ws.mod[m];
+      if (mp.present) {
+        const std::vector<const float*>& wa = h->w[slot_index(h, l, 2 * m)];
+        const std::vector<const float*>& wf = h->w[slot_index(h, l, 2 * m + 1)];
+        const AttnPacked& ap = h->attn[l * (M + 1) + m];
+        const FFPacked& fp = h->ff[l * (M + 1) + m];
+        const int H = d.x_heads, ow = H * HP;
+        // PreNorm + to_q (split operands; the small-C Q' keeps its hi part only)
+        HN_TRY(launch_layernorm_f16(ws.x, D, wa[0], wa[1], ws.xn, 2 * sD, sD, sD, rows, D, st));
+        const int qw = mp.small ? H * mp.zw : H * HP;
+        const bool q_split = !mp.small && mp.precise;
+        GemmArgs gq{ws.xn, mp.small ? ap.WqS : ap.Wq, static_cast<int>(rows), qw, D, 2 * sD, 2 * sD, EPI_F16, 0,
+                    nullptr, ws.q, q_split ? 2 * qw : qw, 3, sD, sD, q_split ? qw : 0};
+        HN_TRY(launch_gemm(gq, st));
+        AttnArgs aa{};
+        aa.Q = ws.q;
+        aa.q_ld = q_split ? 2 * qw : qw;
+        aa.batch = batch;
+        aa.L = L;
+        aa.H = H;
+        aa.N = mp.N;
+        aa.nsplit = mp.nsplit;
+        aa.mask_bits = mp.masked ? ws.mask_bits : nullptr;
+        aa.part_acc = ws.part_acc;
+        aa.part_ml = ws.part_ml;
+        if (mp.small) {
+          aa.KV = mp.z;
+          aa.kv_ld = mp.zw;
+          aa.shared_kv = 1;
+          aa.kd = mp.zw;
+          rc = profile_begin(h, m, aa, st);
+          if (rc != 0) return rc;
+          HN_TRY(launch_attention(aa, st));
+          profile_end(h, st);
+          HN_TRY(launch_combine_vproj(ws.part_acc, ws.part_ml, batch, mp.nsplit, H, L, mp.C, mp.zw,
+                                      d.cross_dim_head, ap.Wv, ap.bv, ws.o, 2 * ow, ow, st));
+        } else {
+          // K/V projection of the standardised context (context LayerNorm affine folded into the weights).
+          // Weights are always split (their rounding would not average out over tokens); z, K and V are split
+          // only on short token axes.
+          const long tok = static_cast<long>(batch) * mp.N;
+          HN_REQUIRE(tok < (1L << 31), "hn_forward: batch * tokens too large for the K/V projection");
+          const int kvw = 2 * H * HP;
+          GemmArgs gkv{mp.z, ap.Wkv, static_cast<int>(tok), kvw, mp.C, mp.ldz, 2 * mp.segC, EPI_F16, 0, ap.bkv,
+                       ws.kv, mp.precise ? 2 * kvw : kvw, mp.precise ? 3 : 2, mp.segC, mp.segC,
+                       mp.precise ? kvw : 0};
+          HN_TRY(launch_gemm(gkv, st));
+          aa.KV = ws.kv;
+          aa.kv_ld = mp.precise ? 2 * kvw : kvw;
+          aa.k_col0 = 0;
+          aa.v_col0 = H * HP;
+          aa.shared_kv = 0;
+          aa.kd = 64;
+          aa.precise = mp.precise ? 1 : 0;
+          aa.q_lo_off = qw;
+          aa.kv_lo_off = kvw;
+          rc = profile_begin(h, m, aa, st);
+          if (rc != 0) return rc;
+          HN_TRY(launch_attention(aa, st));
+          profile_end(h, st);
+          HN_TRY(launch_combine_generic(ws.part_acc, ws.part_ml, batch, mp.nsplit, H, L, ws.o, 2 * ow, ow, st));
+        }
+        // x = LeakyReLU(O Wo^T + bo) + x   (healnet.py:383-386, 426, 236)
+        GemmArgs go{ws.o, ap.Wo, static_cast<int>(rows), D, ow, 2 * ow, 2 * ow, EPI_RES_LEAKY, 0, wa[7], ws.x, D,
+                    3, ow, ow, 0};
+        HN_TRY(launch_gemm(go, st));
+        rc = run_ff(h, wf, fp, ws, rows, st);
+        if (rc != 0) return rc;
+      }
+      if (d.self_per_cross_attn && !(skip_latent_block != nullptr && skip_latent_block[m] != 0)) {
+        // inside the modality loop (healnet.py:241-245)
+        const std::vector<const float*>& wa = h->w[slot_index(h, l, 2 * M)];
+        const std::vector<const float*>& wf = h->w[slot_index(h, l, 2 * M + 1)];
+        const AttnPacked& ap = h->attn[l * (M + 1) + M];
+        const FFPacked& fp = h->ff[l * (M + 1) + M];
+        const int lh = d.l_heads, ow = lh * HP, qw = 3 * lh * HP;
+        const bool prec = ws.self_precise;
+        HN_TRY(launch_layernorm_f16(ws.x, D, wa[0], wa[1], ws.xn, 2 * sD, sD, sD, rows, D, st));
+        GemmArgs gq{ws.xn, ap.Wq, static_cast<int>(rows), qw, D, 2 * sD, 2 * sD, EPI_F16, 0, nullptr, ws.q,
+                    prec ? 2 * qw : qw, 3, sD, sD, prec ? qw : 0};
+        HN_TRY(launch_gemm(gq, st));
+        AttnArgs aa{};
+        aa.Q = ws.q;
+        aa.q_ld = prec ? 2 * qw : qw;
+        aa.KV = ws.q;
+        aa.kv_ld = aa.q_ld;
+        aa.k_col0 = lh * HP;
+        aa.v_col0 = 2 * lh * HP;
+        aa.shared_kv = 0;
+        aa.kd = 64;
+        aa.precise = prec ? 1 : 0;
+        aa.q_lo_off = qw;
+        aa.kv_lo_off = qw;
+        aa.batch = batch;
+        aa.L = L;
+        aa.H = lh;
+        aa.N = L;
+        aa.nsplit = ws.self_nsplit;
+        aa.mask_bits = nullptr;
+        aa.part_acc = ws.part_acc;
+        aa.part_ml = ws.part_ml;
+        HN_TRY(launch_attention(aa, st));
+        HN_TRY(launch_combine_generic(ws.part_acc, ws.part_ml, batch, ws.self_nsplit, lh, L, ws.o, 2 * ow, ow, st));
+        GemmArgs go{ws.o, ap.Wo, static_cast<int>(rows), D, ow, 2 * ow, 2 * ow, EPI_RES_LEAKY, 0, wa[5], ws.x, D,
+                    3, ow, ow, 0};
+        HN_TRY(launch_gemm(go, st));
+        rc = run_ff(h, wf, fp, ws, rows, st);
+        if (rc != 0) return rc;
+      }
+    }
+  }
+  if (latents_out != nullptr) {
+    HN_CHECK_CUDA(cudaMemcpyAsync(latents_out, ws.x, sizeof(float) * rows * D, cudaMemcpyDeviceToDevice, st));
+  }
+  if (logits_out != nullptr) {
+    const std::vector<const float*>& wh = h->w[slot_index(h, -1, 1)];
+    HN_TRY(launch_head(ws.x, batch, L, D, wh[0], wh[1], wh[2], wh[3], d.out_dims, logits_out, st));
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ stand-alone Attention
+namespace {
+struct AttnWs {
+  __half *xh, *ch, *wq, *wkv, *wo, *q, *kv, *o;
+  float *part_acc, *part_ml;
+  uint64_t* mask_bits;
+  int nsplit, sq, sc;
+  bool prec;
+  size_t bytes;
+};
+void plan_attn_ws(int batch, int n_q, long n_ctx, int qd, int cd, int heads, bool self, char* base, AttnWs& w) {
+  Arena ar;
+  ar.base = base;
+  w.sq = seg_of(qd);
+  w.sc = seg_of(cd);
+  w.prec = n_ctx <= PRECISE_MAX_TOKENS;
+  const long rows = static_cast<long>(batch) * n_q, toks = static_cast<long>(batch) * n_ctx;
+  const int hw = heads * HP;
+  w.xh = ar.take<__half>(rows * 2 * w.sq);
+  w.ch = self ? w.xh : ar.take<__half>(toks * (w.prec ? 2 * w.sc : ctx_ld(cd)));
+  w.wq = ar.take<__half>(static_cast<size_t>(hw) * 2 * w.sq);
+  w.wkv = ar.take<__half>(static_cast<size_t>(2) * hw * 2 * w.sc);
+  w.wo = ar.take<__half>(static_cast<size_t>(qd) * 2 * hw);
+  w.q = ar.take<__half>(rows * 2 * hw);
+  w.kv = ar.take<__half>(toks * 2 * hw * (w.prec ? 2 : 1));
+  w.o = ar.take<__half>(rows * 2 * hw);
+  w.nsplit = attention_pick_nsplit(batch, n_q, heads, n_ctx);
+  const int n_ltiles = (n_q + 127) / 128;
+  w.part_acc = ar.take<float>(static_cast<size_t>(batch) * w.nsplit * heads * n_ltiles * 128 * 64);
+  w.part_ml = ar.take<float>(static_cast<size_t>(batch) * w.nsplit * heads * n_ltiles * 128 * 2);
+  w.mask_bits = ar.take<uint64_t>(static_cast<size_t>(batch) * ((n_ctx + 63) / 64));
+  w.bytes = ar.off + 256;
+}
+}  // namespace
+
+size_t hn_attention_workspace_bytes(int batch, int n_q, long n_ctx, int query_dim, int context_dim, int heads,
+                                    int dim_head) {
+  if (batch < 1 || n_q < 1 || n_ctx < 1 || query_dim < 1 || context_dim < 1 || heads < 1 || dim_head < 1) return 0;
+  AttnWs w;
+  plan_attn_ws(batch, n_q, n_ctx, query_dim, context_dim, heads, false, nullptr, w);
+  return w.bytes;
+}
+
+int hn_attention_forward(int batch, int n_q, long n_ctx, int query_dim, int context_dim, int heads, int dim_head,
+                         const float* x, const float* context, const float* w_q, const float* w_kv,
+                         const float* w_out, const float* b_out, const uint8_t* mask, float* out, void* workspace,
+                         size_t workspace_bytes, void* cuda_stream) {
+  HN_REQUIRE(batch >= 1 && n_q >= 1 && query_dim >= 1 && heads >= 1, "hn_attention_forward: bad shape");
+  HN_REQUIRE(dim_head >= 1 && dim_head <= HP, "hn_attention_forward: dim_head must be in 1..64");
+  HN_REQUIRE(x && w_q && w_kv && w_out && b_out && out && workspace, "hn_attention_forward: null argument");
+  const bool self = (context == nullptr);
+  if (self) {
+    n_ctx = n_q;
+    context_dim = query_dim;
+  }
+  HN_REQUIRE(n_ctx >= 1 && context_dim >= 1, "hn_attention_forward: bad context shape");
+  HN_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "hn_attention_forward: workspace must be 256-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  AttnWs w;
+  plan_attn_ws(batch, n_q, n_ctx, query_dim, context_dim, heads, self, static_cast<char*>(workspace), w);
+  HN_REQUIRE(w.bytes <= workspace_bytes, "hn_attention_forward: workspace too small");
+  const int inner = heads * dim_head, hw = heads * HP, sq = w.sq, sc = w.sc;
+  const long rows = static_cast<long>(batch) * n_q, toks = static_cast<long>(batch) * n_ctx;
+  HN_REQUIRE(rows < (1L << 31) && toks < (1L << 31), "hn_attention_forward: problem too large");
+  const float scale = 2.f / std::sqrt(static_cast<float>(dim_head)) * LOG2E;
+  const int ldc = self ? 2 * sq : (w.prec ? 2 * sc : ctx_ld(context_dim));
+  const bool c_split = self || w.prec;
+  int rc;
+#define HN_TRY2(expr)         \
+  do {                        \
+    rc = (expr);              \
+    if (rc != 0) return rc;   \
+  } while (0)
+  HN_TRY2(pack_plain(w.xh, 2 * sq, x, query_dim, static_cast<int>(rows), query_dim, sq, sq, st));
+  if (!self)
+    HN_TRY2(pack_plain(w.ch, ldc, context, context_dim, static_cast<int>(toks), context_dim, w.prec ? sc : ldc,
+                       w.prec ? sc : 0, st));
+  HN_TRY2(pack_headpad_rows(w.wq, 2 * sq, 0, w_q, query_dim, 0, heads, dim_head, query_dim, scale, nullptr, sq, sq, st));
+  HN_TRY2(pack_headpad_rows(w.wkv, 2 * sc, 0, w_kv, context_dim, 0, heads, dim_head, context_dim, 1.f, nullptr, sc, sc,
+                            st));
+  HN_TRY2(pack_headpad_rows(w.wkv, 2 * sc, hw, w_kv, context_dim, inner, heads, dim_head, context_dim, 1.f, nullptr,
+                            sc, sc, st));
+  HN_TRY2(pack_headpad_cols(w.wo, 2 * hw, w_out, inner, query_dim, heads, dim_head, hw, hw, st));
+  GemmArgs gq{w.xh, w.wq, static_cast<int>(rows), hw, query_dim, 2 * sq, 2 * sq, EPI_F16, 0, nullptr, w.q,
+              w.prec ? 2 * hw : hw, 3, sq, sq, w.prec ? hw : 0};
+  HN_TRY2(launch_gemm(gq, st));
+  GemmArgs gkv{w.ch, w.wkv, static_cast<int>(toks), 2 * hw, context_dim, ldc, 2 * sc, EPI_F16, 0, nullptr, w.kv,
+               w.prec ? 4 * hw : 2 * hw, (c_split && w.prec) ? 3 : 2, sc, sc, w.prec ? 2 * hw : 0};
+  HN_TRY2(launch_gemm(gkv, st));
+  if (mask != nullptr) HN_TRY2(launch_pack_mask(mask, w.mask_bits, batch, n_ctx, st));
+  AttnArgs aa{};
+  aa.Q = w.q;
+  aa.q_ld = w.prec ? 2 * hw : hw;
+  aa.KV = w.kv;
+  aa.kv_ld = w.prec ? 4 * hw : 2 * hw;
+  aa.k_col0 = 0;
+  aa.v_col0 = hw;
+  aa.shared_kv = 0;
+  aa.kd = 64;
+  aa.precise = w.prec ? 1 : 0;
+  aa.q_lo_off = hw;
+  aa.kv_lo_off = 2 * hw;
+  aa.batch = batch;
+  aa.L = n_q;
+  aa.H = heads;
+  aa.N = n_ctx;
+  aa.nsplit = w.nsplit;
+  aa.mask_bits = mask ? w.mask_bits : nullptr;
+  aa.part_acc = w.part_acc;
+  aa.part_ml = w.part_ml;
+  HN_TRY2(launch_attention(aa, st));
+  HN_TRY2(launch_combine_generic(w.part_acc, w.part_ml, batch, w.nsplit, heads, n_q, w.o, 2 * hw, hw, st));
+  GemmArgs go{w.o, w.wo, static_cast<int>(rows), query_dim, hw, 2 * hw, 2 * hw, EPI_LEAKY_F32, 0, b_out, out,
+              query_dim, 3, hw, hw, 0};
+  HN_TRY2(launch_gemm(go, st));
+#undef HN_TRY2
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ kernel-level entry points
+int hn_op_gemm(const void* A, const void* B, int M, int N, int K, int lda, int ldb, int epi, int act,
+               const float* bias, void* out, int ldo, int terms, int a_seg, int b_seg, int out_seg,
+               void* cuda_stream) {
+  GemmArgs g{static_cast<const __half*>(A), static_cast<const __half*>(B), M, N, K, lda, ldb, epi, act, bias, out,
+             ldo, terms, a_seg, b_seg, out_seg};
+  return launch_gemm(g, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int hn_op_layernorm_f16(const float* x, int ldx, const float* gamma, const float* beta, void* y, int ldy, int seg,
+                        int lo_seg, long rows, int D, void* cuda_stream) {
+  return launch_layernorm_f16(x, ldx, gamma, beta, static_cast<__half*>(y), ldy, seg, lo_seg, rows, D,
+                              static_cast<cudaStream_t>(cuda_stream));
+}
+
+int hn_op_build_context(const float* raw, void* z, int ldz, int small, int batch, int c_raw, int n_axes,
+                        const int* axis_sizes, int n_bands, float max_freq, int fourier, float* tab,
+                        void* cuda_stream) {
+  HN_REQUIRE(raw && z && axis_sizes && n_axes >= 1 && n_axes <= HN_MAX_AXES, "hn_op_build_context: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  long N = 1;
+  for (int a = 0; a < n_axes; ++a) N *= axis_sizes[a];
+  if (fourier) {
+    HN_REQUIRE(tab != nullptr, "hn_op_build_context: table scratch required");
+    int rc = launch_axis_tables(tab, axis_sizes, n_axes, n_bands, max_freq, st);
+    if (rc != 0) return rc;
+  }
+  if (small)
+    return launch_build_z_small(raw, static_cast<__half*>(z), ldz, batch, N, c_raw, n_axes, axis_sizes, n_bands, tab,
+                                fourier, st);
+  return launch_build_z_large(raw, static_cast<__half*>(z), ldz, 0, batch, N, c_raw, n_axes, axis_sizes, n_bands,
+                              tab, fourier, st);
+}
+
+int hn_op_attention_nsplit(int batch, int L, int H, long N) { return attention_pick_nsplit(batch, L, H, N); }
+
+int hn_op_attention(const void* Q, int q_ld, const void* KV, long kv_ld, int k_col0, int v_col0, int shared_kv,
+                    int batch, int L, int H, long N, int nsplit, const uint8_t* mask, void* mask_bits_scratch,
+                    float* part_acc, float* part_ml, void* cuda_stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  AttnArgs aa{};
+  aa.Q = static_cast<const __half*>(Q);
+  aa.q_ld = q_ld;
+  aa.KV = static_cast<const __half*>(KV);
+  aa.kv_ld = kv_ld;
+  aa.k_col0 = k_col0;
+  aa.v_col0 = v_col0;
+  aa.shared_kv = shared_kv ? 1 : 0;
+  aa.kd = shared_kv ? static_cast<int>(kv_ld) : 64;
+  aa.batch = batch;
+  aa.L = L;
+  aa.H = H;
+  aa.N = N;
+  aa.nsplit = nsplit;
+  aa.part_acc = part_acc;
+  aa.part_ml = part_ml;
+  if (mask != nullptr) {
+    HN_REQUIRE(mask_bits_scratch != nullptr, "hn_op_attention: mask scratch required");
+    int rc = launch_pack_mask(mask, static_cast<uint64_t*>(mask_bits_scratch), batch, N, st);
+    if (rc != 0) return rc;
+    aa.mask_bits = static_cast<const uint64_t*>(mask_bits_scratch);
+  }
+  return launch_attention(aa, st);
+}
+
+int hn_op_combine(const float* part_acc, const float* part_ml, int batch, int nsplit, int H, int L, int small_C,
+                  int zw, int dh, const float* Wv, const float* bv, void* O, int o_ld, void* cuda_stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  if (small_C > 0)
+    return launch_combine_vproj(part_acc, part_ml, batch, nsplit, H, L, small_C, zw, dh, Wv, bv,
+                                static_cast<__half*>(O), o_ld, 0, st);
+  return launch_combine_generic(part_acc, part_ml, batch, nsplit, H, L, static_cast<__half*>(O), o_ld, 0, st);
+}
+
+}  // extern "C"

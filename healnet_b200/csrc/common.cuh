@@ -1,0 +1,124 @@
+// common.cuh — shared declarations of the HEALNet-B200 kernel library (internal; the public C ABI is
+// include/healnet_b200.h).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+namespace hn {
+
+// thread-local error string behind hn_last_error()
+void set_error(const std::string& msg);
+const char* get_error();
+
+#define HN_CHECK_CUDA(expr)                                                                          \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess) {                                                                         \
+      ::hn::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                           \
+      return -10;                                                                                    \
+    }                                                                                                \
+  } while (0)
+
+#define HN_REQUIRE(cond, msg)                                                                        \
+  do {                                                                                               \
+    if (!(cond)) {                                                                                   \
+      ::hn::set_error(std::string(msg) + " [" #cond "]");                                            \
+      return -1;                                                                                     \
+    }                                                                                                \
+  } while (0)
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+static inline long round_up_l(long x, long m) { return (x + m - 1) / m * m; }
+
+// ------------------------------------------------------------------ GEMM (gemm.cu)
+// C[M,N] = A[M,K] * B[N,K]^T, fp16 operands (row-major, K contiguous), fp32 accumulation in TMEM.
+enum GemmEpilogue : int {
+  EPI_F16 = 0,        // out_h[m][n] = half(acc + bias[n])                  (bias optional)
+  EPI_GATE_F16 = 1,   // out_h[m][n/2] = (acc[n]+b[n]) * act(acc[n+1]+b[n+1]) for even n   (FeedForward gate)
+  EPI_RES = 2,        // x[m][n] += acc + bias[n]                           (fp32 residual stream, in place)
+  EPI_RES_LEAKY = 3,  // x[m][n] += leaky_relu_0.01(acc + bias[n])
+  EPI_F32 = 4,        // out_f[m][n] = acc + bias[n]
+  EPI_LEAKY_F32 = 5,  // out_f[m][n] = leaky_relu_0.01(acc + bias[n])
+};
+enum GateAct : int { ACT_SELU = 0, ACT_GELU = 1 };
+
+struct GemmArgs {
+  const __half* A;  // [M][lda]
+  const __half* B;  // [N][ldb]
+  int M, N, K;
+  int lda, ldb;     // in elements, multiples of 8
+  int epi;
+  int act;
+  const float* bias;  // [N] or null
+  void* out;          // half* or float* depending on epi (x for the residual modes)
+  int ldo;            // in elements of the output type
+  // split-precision operands (gemm.cu header): terms = 1 plain; 2 = A.(B_hi + B_lo); 3 = A_hi.B_hi + A_lo.B_hi + A_hi.B_lo
+  int terms = 1;
+  int a_seg = 0, b_seg = 0;  // column offset of the lo segment inside A / B rows (multiple of 64, >= K)
+  int out_seg = 0;           // fp16 epilogues: > 0 -> lo part of the output stored at column + out_seg
+};
+int launch_gemm(const GemmArgs& a, cudaStream_t stream);
+
+// ------------------------------------------------------------------ row ops (rowops.cu)
+// y[r] = [hi | lo] split fp16 of LN(x[r]) * gamma + beta: hi in columns [0, seg), lo in [lo_seg, lo_seg + seg)
+// (lo_seg == 0: hi only); pad columns [D, seg) are zero-filled in both segments.
+int launch_layernorm_f16(const float* x, int ldx, const float* gamma, const float* beta, __half* y, int ldy, int seg,
+                         int lo_seg, long rows, int D, cudaStream_t stream);
+// per-axis Fourier tables: tab[axis_off[a] + j][2B+1] (fp32)
+int launch_axis_tables(float* tab, const int* axis_sizes, int n_axes, int n_bands, float max_freq,
+                       cudaStream_t stream);
+// standardised context rows, small-C layout: z[b][N][zw] fp16 = [(v-mean)*rstd (C values), 1, 0...], zw = 32 | 64
+int launch_build_z_small(const float* raw, __half* z, int zw, int batch, long N, int c_raw, int n_axes,
+                         const int* axis_sizes /*host*/, int n_bands, const float* tab, int fourier,
+                         cudaStream_t stream);
+// standardised context rows, generic layout: z[b*N][ldz] fp16 (pad cols zero); lo_seg > 0: split [hi | lo]
+int launch_build_z_large(const float* raw, __half* z, int ldz, int lo_seg, int batch, long N, int c_raw, int n_axes,
+                         const int* axis_sizes /*host*/, int n_bands, const float* tab, int fourier,
+                         cudaStream_t stream);
+// pooled head: logits[b][o] = LN(mean_L x[b]) . W[o] + bias[o]
+int launch_head(const float* x, int batch, int L, int D, const float* ln_w, const float* ln_b, const float* W,
+                const float* bias, int out_dims, float* logits, cudaStream_t stream);
+// user mask (b, N) bytes -> per-64-token-tile bit words (bit j = keep token tile*64+j)
+int launch_pack_mask(const uint8_t* mask, uint64_t* bits, int batch, long N, cudaStream_t stream);
+
+// ------------------------------------------------------------------ attention (xattn.cu)
+struct AttnArgs {
+  // Q: [batch][L][q_ld] fp16, head h at columns h*KD .. (KD = 32 small-C / 64 generic); pre-scaled by 2/sqrt(dh)*log2(e)
+  const __half* Q;
+  int q_ld;
+  // K/V: [batch][N][kv_ld] fp16. generic: head h K at k_col0 + h*64, V at v_col0 + h*64.
+  // small-C ("shared"): one 32-wide standardised-context tile serves as K and V for every head.
+  const __half* KV;
+  long kv_ld;
+  int k_col0, v_col0;
+  // precise mode (generic path, short token axes whose rounding errors do not average out): Q, K, V rows also
+  // carry lo = fp16(x - hi) parts at these column offsets; S = Qh.Kh + Ql.Kh + Qh.Kl, U += P.Vh + P.Vl
+  int precise = 0;
+  int q_lo_off = 0, kv_lo_off = 0;
+  int shared_kv;  // 1 = small-C path
+  int kd;         // operand width per head: 64 generic; 32 or 64 (= z row width) on the small-C path
+  int batch, L, H;
+  long N;
+  int nsplit;
+  const uint64_t* mask_bits;  // [batch][ceil(N/64)] or null
+  float* part_acc;            // [batch][nsplit][H][L][VD] fp32 un-normalised accumulators
+  float* part_ml;             // [batch][nsplit][H][L][2] (running max in log2 units, row sum (generic only))
+};
+int launch_attention(const AttnArgs& a, cudaStream_t stream);
+int attention_pick_nsplit(int batch, int L, int H, long N);
+
+// combine split partials. generic: O[b*L][h*64+d] = sum_s w_s acc_s[d] / sum_s w_s l_s   (fp16, ld = o_ld)
+// (lo_seg > 0: O rows are split [hi | lo], lo at column + lo_seg)
+int launch_combine_generic(const float* part_acc, const float* part_ml, int batch, int nsplit, int H, int L,
+                           __half* O, int o_ld, int lo_seg, cudaStream_t stream);
+// small-C: u = sum_s w_s acc_s[0..C) / sum_s w_s acc_s[C];  O[b*L][h*64+d] = u . Wv[h*dh+d][:] + bv[h*dh+d]
+int launch_combine_vproj(const float* part_acc, const float* part_ml, int batch, int nsplit, int H, int L, int C,
+                         int zw, int dh, const float* Wv /*[H*dh][zw]*/, const float* bv /*[H*dh]*/, __half* O,
+                         int o_ld, int lo_seg, cudaStream_t stream);
+// x[b][i] = src[i]  (latent broadcast, healnet.py:225)
+int launch_broadcast_rows(const float* src, float* dst, long n, int batch, cudaStream_t stream);
+
+}  // namespace hn

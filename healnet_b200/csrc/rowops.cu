@@ -1,0 +1,503 @@
+// rowops.cu — the HBM-bound row kernels around the tensor-core work:
+//   * LayerNorm of latent rows -> fp16 GEMM operands                    (PreNorm.norm, healnet.py:313-314)
+//   * Fourier positional tables + standardised context rows "z"         (healnet.py:211-221, 292-302, 318)
+//   * split-N partial combine (+ fused V projection on the small-C path)
+//   * mean-pool -> LayerNorm -> Linear head                             (healnet.py:181-185)
+// LayerNorm of the context is split as LN(c) = gamma * z + beta with z = (c - mean) * rstd: z depends only
+// on the input, so it is built ONCE per forward and shared by all `depth` layers; gamma/beta are folded
+// into the projection weights at pack time (pack.cu).
+#include "common.cuh"
+
+namespace hn {
+namespace {
+
+constexpr float LN_EPS = 1e-5f;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ------------------------------------------------------------------ LayerNorm rows -> split fp16
+// y[r] = [hi (seg cols) | lo (seg cols)] with hi = fp16(v), lo = fp16(v - hi), v = LN(x[r]) * gamma + beta;
+// pad columns [D, seg) of both segments are zero. lo_seg == 0: single fp16 row of `seg` columns.
+__device__ __forceinline__ void store_split(__half* yr, int c, int seg, int lo_seg, float v) {
+  const __half hi = __float2half_rn(v);
+  yr[c] = hi;
+  if (lo_seg > 0) yr[lo_seg + c] = __float2half_rn(v - __half2float(hi));
+}
+// one warp per row; row cached in registers (D <= 32*MAXV) else re-read from L2
+template <int MAXV>
+__global__ void __launch_bounds__(256) layernorm_f16_kernel(const float* __restrict__ x, int ldx,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, __half* __restrict__ y,
+                                                            int ldy, int seg, int lo_seg, long rows, int D) {
+  const int lane = threadIdx.x & 31;
+  const long row = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + row * ldx;
+  float v[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + i * 32;
+    v[i] = c < D ? xr[c] : 0.f;
+    s += v[i];
+  }
+  const float mean = warp_sum(s) / D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + i * 32;
+    const float d = c < D ? v[i] - mean : 0.f;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) / D + LN_EPS);
+  __half* yr = y + row * ldy;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + i * 32;
+    if (c < seg) store_split(yr, c, seg, lo_seg, c < D ? (v[i] - mean) * rstd * gamma[c] + beta[c] : 0.f);
+  }
+}
+
+__global__ void __launch_bounds__(256) layernorm_f16_big_kernel(const float* __restrict__ x, int ldx,
+                                                                const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta,
+                                                                __half* __restrict__ y, int ldy, int seg, int lo_seg,
+                                                                long rows, int D) {
+  const int lane = threadIdx.x & 31;
+  const long row = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + row * ldx;
+  float s = 0.f;
+  for (int c = lane; c < D; c += 32) s += xr[c];
+  const float mean = warp_sum(s) / D;
+  float q = 0.f;
+  for (int c = lane; c < D; c += 32) {
+    const float d = xr[c] - mean;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) / D + LN_EPS);
+  __half* yr = y + row * ldy;
+  for (int c = lane; c < seg; c += 32)
+    store_split(yr, c, seg, lo_seg, c < D ? (xr[c] - mean) * rstd * gamma[c] + beta[c] : 0.f);
+}
+
+// ------------------------------------------------------------------ Fourier axis tables
+// tab[(off_a + j) * (2B+1) + k]: k < B sin(pi p f_k), B <= k < 2B cos(pi p f_{k-B}), k == 2B: p
+// p = linspace(-1, 1, size)[j] (size 1 -> -1), f_k = linspace(1, max_freq/2, B)[k]   (healnet.py:212, 292-302)
+struct AxisInfo {
+  int n_axes;
+  int size[4];
+  int off[4];
+};
+__global__ void axis_tables_kernel(float* __restrict__ tab, AxisInfo ax, int B, float max_freq) {
+  const int F = 2 * B + 1;
+  int total = 0;
+  for (int a = 0; a < ax.n_axes; ++a) total += ax.size[a];
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total * F; idx += gridDim.x * blockDim.x) {
+    const int r = idx / F, k = idx % F;
+    int a = 0;
+    while (a + 1 < ax.n_axes && r >= ax.off[a + 1]) ++a;
+    const int j = r - ax.off[a], n = ax.size[a];
+    // torch.linspace fp32 semantics: step = (end-start)/(n-1); lower half start + j*step, upper half end - (n-1-j)*step
+    float p;
+    if (n == 1) {
+      p = -1.f;
+    } else {
+      const float step = 2.f / static_cast<float>(n - 1);
+      p = (j < n / 2) ? (-1.f + step * j) : (1.f - step * (n - 1 - j));
+    }
+    float out;
+    if (k == 2 * B) {
+      out = p;
+    } else {
+      const int kk = k < B ? k : k - B;
+      float f;
+      if (B == 1) {
+        f = 1.f;
+      } else {
+        const float fstep = (max_freq * 0.5f - 1.f) / static_cast<float>(B - 1);
+        f = (kk < B / 2) ? (1.f + fstep * kk) : (max_freq * 0.5f - fstep * (B - 1 - kk));
+      }
+      const float arg = p * f * 3.14159265358979323846f;  // fp32 product, as the reference computes it
+      out = k < B ? static_cast<float>(sin(static_cast<double>(arg))) : static_cast<float>(cos(static_cast<double>(arg)));
+    }
+    tab[idx] = out;
+  }
+}
+
+// ------------------------------------------------------------------ z rows, small-C layout (C <= ZW-1)
+// one thread per token: raw channels + table features -> standardise -> ZW fp16 = one 64/128-byte row
+template <int ZW>
+__global__ void __launch_bounds__(256) build_z_small_kernel(const float* __restrict__ raw, __half* __restrict__ z,
+                                                            long tokens_total, long N, int c_raw, AxisInfo ax,
+                                                            int F, const float* __restrict__ tab) {
+  const long t = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= tokens_total) return;
+  const long n = t % N;
+  float v[ZW];
+  const float* r = raw + t * c_raw;
+#pragma unroll
+  for (int i = 0; i < ZW; ++i) v[i] = i < c_raw ? r[i] : 0.f;
+  int C = c_raw;
+  // row-major token index -> per-axis coordinates
+  long rem = n;
+  int coord[4];
+  for (int a = ax.n_axes - 1; a >= 0; --a) {
+    coord[a] = static_cast<int>(rem % ax.size[a]);
+    rem /= ax.size[a];
+  }
+  if (F > 0) {
+    for (int a = 0; a < ax.n_axes; ++a) {
+      const float* tr = tab + static_cast<long>(ax.off[a] + coord[a]) * F;
+      for (int k = 0; k < F; ++k) {
+        const float tv = __ldg(tr + k);
+#pragma unroll
+        for (int i = 0; i < ZW; ++i)
+          if (i == C + k) v[i] = tv;
+      }
+      C += F;
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < ZW; ++i)
+    if (i < C) s += v[i];
+  const float mean = s / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < ZW; ++i)
+    if (i < C) {
+      const float d = v[i] - mean;
+      q += d * d;
+    }
+  const float rstd = rsqrtf(q / C + LN_EPS);
+#pragma unroll
+  for (int i = 0; i < ZW; ++i) {
+    float val = 0.f;
+    if (i < C) val = (v[i] - mean) * rstd;
+    if (i == C) val = 1.f;  // ones column: the PV UMMA accumulates the softmax denominator for free
+    v[i] = val;
+  }
+  uint4* dst = reinterpret_cast<uint4*>(z + t * ZW);
+#pragma unroll
+  for (int i = 0; i < ZW / 8; ++i) {
+    uint4 w;
+    __half2 h0 = __floats2half2_rn(v[8 * i + 0], v[8 * i + 1]);
+    __half2 h1 = __floats2half2_rn(v[8 * i + 2], v[8 * i + 3]);
+    __half2 h2 = __floats2half2_rn(v[8 * i + 4], v[8 * i + 5]);
+    __half2 h3 = __floats2half2_rn(v[8 * i + 6], v[8 * i + 7]);
+    w.x = *reinterpret_cast<uint32_t*>(&h0);
+    w.y = *reinterpret_cast<uint32_t*>(&h1);
+    w.z = *reinterpret_cast<uint32_t*>(&h2);
+    w.w = *reinterpret_cast<uint32_t*>(&h3);
+    dst[i] = w;
+  }
+}
+
+// ------------------------------------------------------------------ z rows, generic layout (any C)
+// one warp per token row
+__global__ void __launch_bounds__(256) build_z_large_kernel(const float* __restrict__ raw, __half* __restrict__ z,
+                                                            int ldz, int seg, int lo_seg, long tokens_total, long N,
+                                                            int c_raw, AxisInfo ax, int F,
+                                                            const float* __restrict__ tab) {
+  const int lane = threadIdx.x & 31;
+  const long t = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= tokens_total) return;
+  const long n = t % N;
+  const float* r = raw + t * c_raw;
+  const int n_feat = F * ax.n_axes;
+  const int C = c_raw + n_feat;
+  long rem = n;
+  int coord[4] = {0, 0, 0, 0};
+  for (int a = ax.n_axes - 1; a >= 0; --a) {
+    coord[a] = static_cast<int>(rem % ax.size[a]);
+    rem /= ax.size[a];
+  }
+  auto feat = [&](int c) -> float {
+    if (c < c_raw) return r[c];
+    const int k = c - c_raw;
+    const int a = k / F;
+    return __ldg(tab + static_cast<long>(ax.off[a] + coord[a]) * F + (k - a * F));
+  };
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += feat(c);
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float d = feat(c) - mean;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) / C + LN_EPS);
+  __half* zr = z + t * ldz;
+  for (int c = lane; c < seg; c += 32) store_split(zr, c, seg, lo_seg, c < C ? (feat(c) - mean) * rstd : 0.f);
+}
+
+// ------------------------------------------------------------------ head: mean_L -> LN -> Linear
+__global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ x, int L, int D,
+                                                   const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                                                   const float* __restrict__ W, const float* __restrict__ bias,
+                                                   int out_dims, float* __restrict__ logits) {
+  extern __shared__ float pooled[];  // D floats + 2
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  const float* xb = x + static_cast<size_t>(b) * L * D;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float s = 0.f;
+    for (int l = 0; l < L; ++l) s += xb[static_cast<size_t>(l) * D + d];
+    pooled[d] = s / L;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float s = 0.f;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) s += pooled[d];
+  s = warp_sum(s);
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  float tot = 0.f;
+  for (int w = 0; w < nw; ++w) tot += red[w];
+  const float mean = tot / D;
+  __syncthreads();
+  float q = 0.f;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const float dd = pooled[d] - mean;
+    q += dd * dd;
+  }
+  q = warp_sum(q);
+  if (lane == 0) red[warp] = q;
+  __syncthreads();
+  tot = 0.f;
+  for (int w = 0; w < nw; ++w) tot += red[w];
+  const float rstd = rsqrtf(tot / D + LN_EPS);
+  __syncthreads();
+  for (int d = threadIdx.x; d < D; d += blockDim.x) pooled[d] = (pooled[d] - mean) * rstd * ln_w[d] + ln_b[d];
+  __syncthreads();
+  for (int o = warp; o < out_dims; o += nw) {
+    float acc = 0.f;
+    for (int d = lane; d < D; d += 32) acc += pooled[d] * W[static_cast<size_t>(o) * D + d];
+    acc = warp_sum(acc);
+    if (lane == 0) logits[static_cast<size_t>(b) * out_dims + o] = acc + bias[o];
+  }
+}
+
+// ------------------------------------------------------------------ mask bytes -> tile bit words
+__global__ void pack_mask_kernel(const uint8_t* __restrict__ mask, uint64_t* __restrict__ bits, long N,
+                                 long tiles_per_sample, long total_tiles) {
+  const long w = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (w >= total_tiles) return;
+  const long b = w / tiles_per_sample, tile = w % tiles_per_sample;
+  uint64_t v = 0;
+  for (int j = 0; j < 64; ++j) {
+    const long n = tile * 64 + j;
+    if (n < N && mask[b * N + n]) v |= (1ull << j);
+  }
+  bits[w] = v;
+}
+
+// ------------------------------------------------------------------ split combine
+// part_acc [b][s][h][L][VD], part_ml [b][s][h][L][2]; one warp per (b, l, h)
+__global__ void __launch_bounds__(256) combine_generic_kernel(const float* __restrict__ part_acc,
+                                                              const float* __restrict__ part_ml, int batch,
+                                                              int nsplit, int H, int L, __half* __restrict__ O,
+                                                              int o_ld, int lo_seg) {
+  const int lane = threadIdx.x & 31;
+  const long wid = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long total = static_cast<long>(batch) * L * H;
+  if (wid >= total) return;
+  const int h = static_cast<int>(wid % H);
+  const int l = static_cast<int>((wid / H) % L);
+  const int b = static_cast<int>(wid / (static_cast<long>(H) * L));
+  float M = -INFINITY;
+  for (int s = lane; s < nsplit; s += 32)
+    M = fmaxf(M, part_ml[((((static_cast<long>(b) * nsplit + s) * H + h) * L) + l) * 2]);
+  M = warp_max(M);
+  float a0 = 0.f, a1 = 0.f, den = 0.f;
+  for (int s = 0; s < nsplit; ++s) {
+    const long base = (((static_cast<long>(b) * nsplit + s) * H + h) * L) + l;
+    const float m = part_ml[base * 2], ls = part_ml[base * 2 + 1];
+    const float w = (m == -INFINITY) ? 0.f : exp2f(m - M);
+    a0 += w * part_acc[base * 64 + lane];
+    a1 += w * part_acc[base * 64 + 32 + lane];
+    den += w * ls;
+  }
+  const float inv = 1.f / den;
+  __half* o = O + (static_cast<long>(b) * L + l) * o_ld + h * 64;
+  store_split(o, lane, 0, lo_seg, a0 * inv);
+  store_split(o, lane + 32, 0, lo_seg, a1 * inv);
+}
+
+// small-C: acc rows are zw wide: [sum_t p z_c (c < C), sum_t p (col C), 0...]; then the V projection
+// O[b*L + l][h*64 + d] = (u / den) . Wv'[h*dh + d][:] + bv[h*dh + d]; one warp per (b, l, h)
+__global__ void __launch_bounds__(256) combine_vproj_kernel(const float* __restrict__ part_acc,
+                                                            const float* __restrict__ part_ml, int batch,
+                                                            int nsplit, int H, int L, int C, int zw, int dh,
+                                                            const float* __restrict__ Wv,
+                                                            const float* __restrict__ bv, __half* __restrict__ O,
+                                                            int o_ld, int lo_seg) {
+  __shared__ float u_s[8][64];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const long wid = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + wib;
+  const long total = static_cast<long>(batch) * L * H;
+  if (wid >= total) return;
+  const int h = static_cast<int>(wid % H);
+  const int l = static_cast<int>((wid / H) % L);
+  const int b = static_cast<int>(wid / (static_cast<long>(H) * L));
+  float M = -INFINITY;
+  for (int s = lane; s < nsplit; s += 32)
+    M = fmaxf(M, part_ml[((((static_cast<long>(b) * nsplit + s) * H + h) * L) + l) * 2]);
+  M = warp_max(M);
+  float acc0 = 0.f, acc1 = 0.f;
+  for (int s = 0; s < nsplit; ++s) {
+    const long base = (((static_cast<long>(b) * nsplit + s) * H + h) * L) + l;
+    const float m = part_ml[base * 2];
+    const float w = (m == -INFINITY) ? 0.f : exp2f(m - M);
+    acc0 += w * part_acc[base * zw + lane];
+    if (zw > 32) acc1 += w * part_acc[base * zw + 32 + lane];
+  }
+  u_s[wib][lane] = acc0;
+  u_s[wib][lane + 32] = acc1;
+  __syncwarp();
+  const float inv = 1.f / u_s[wib][C];
+  __half* o = O + (static_cast<long>(b) * L + l) * o_ld + h * 64;
+  for (int d0 = 0; d0 < 64; d0 += 32) {
+    const int d = d0 + lane;
+    float out = 0.f;
+    if (d < dh) {
+      const float* wr = Wv + static_cast<long>(h * dh + d) * zw;
+      for (int c = 0; c < C; ++c) out += u_s[wib][c] * wr[c];
+      out = out * inv + bv[h * dh + d];
+    }
+    store_split(o, d, 0, lo_seg, out);
+  }
+}
+
+__global__ void broadcast_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, long n, int batch) {
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const float v = src[i];
+    for (int b = 0; b < batch; ++b) dst[static_cast<long>(b) * n + i] = v;
+  }
+}
+
+AxisInfo make_axis(const int* sizes, int n_axes) {
+  AxisInfo ax{};
+  ax.n_axes = n_axes;
+  int off = 0;
+  for (int a = 0; a < 4; ++a) {
+    ax.size[a] = a < n_axes ? sizes[a] : 1;
+    ax.off[a] = off;
+    if (a < n_axes) off += sizes[a];
+  }
+  return ax;
+}
+}  // namespace
+
+int launch_layernorm_f16(const float* x, int ldx, const float* gamma, const float* beta, __half* y, int ldy, int seg,
+                         int lo_seg, long rows, int D, cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  HN_REQUIRE(seg >= D && (lo_seg == 0 || lo_seg >= seg) && ldy >= lo_seg + seg, "layernorm: bad output layout");
+  const int wpb = 8;
+  const unsigned grid = static_cast<unsigned>((rows + wpb - 1) / wpb);
+  if (seg <= 128)
+    layernorm_f16_kernel<4><<<grid, wpb * 32, 0, stream>>>(x, ldx, gamma, beta, y, ldy, seg, lo_seg, rows, D);
+  else if (seg <= 512)
+    layernorm_f16_kernel<16><<<grid, wpb * 32, 0, stream>>>(x, ldx, gamma, beta, y, ldy, seg, lo_seg, rows, D);
+  else if (seg <= 1024)
+    layernorm_f16_kernel<32><<<grid, wpb * 32, 0, stream>>>(x, ldx, gamma, beta, y, ldy, seg, lo_seg, rows, D);
+  else
+    layernorm_f16_big_kernel<<<grid, wpb * 32, 0, stream>>>(x, ldx, gamma, beta, y, ldy, seg, lo_seg, rows, D);
+  HN_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_axis_tables(float* tab, const int* axis_sizes, int n_axes, int n_bands, float max_freq,
+                       cudaStream_t stream) {
+  HN_REQUIRE(n_axes >= 1 && n_axes <= 4, "at most 4 spatial axes are supported");
+  AxisInfo ax = make_axis(axis_sizes, n_axes);
+  axis_tables_kernel<<<8, 256, 0, stream>>>(tab, ax, n_bands, max_freq);
+  HN_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_build_z_small(const float* raw, __half* z, int zw, int batch, long N, int c_raw, int n_axes,
+                         const int* axis_sizes, int n_bands, const float* tab, int fourier, cudaStream_t stream) {
+  const int F = fourier ? 2 * n_bands + 1 : 0;
+  const int C = c_raw + F * n_axes;
+  HN_REQUIRE(zw == 32 || zw == 64, "small-C context rows are 32 or 64 wide");
+  HN_REQUIRE(C <= zw - 1, "small-C context path needs C <= row width - 1");
+  AxisInfo ax = make_axis(axis_sizes, n_axes);
+  const long total = static_cast<long>(batch) * N;
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  if (zw == 32)
+    build_z_small_kernel<32><<<grid, 256, 0, stream>>>(raw, z, total, N, c_raw, ax, F, tab);
+  else
+    build_z_small_kernel<64><<<grid, 256, 0, stream>>>(raw, z, total, N, c_raw, ax, F, tab);
+  HN_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_build_z_large(const float* raw, __half* z, int ldz, int lo_seg, int batch, long N, int c_raw, int n_axes,
+                         const int* axis_sizes, int n_bands, const float* tab, int fourier, cudaStream_t stream) {
+  const int F = fourier ? 2 * n_bands + 1 : 0;
+  const int seg = lo_seg > 0 ? lo_seg : ldz;
+  HN_REQUIRE(seg >= c_raw + F * n_axes && ldz >= lo_seg + seg, "build_z_large: bad output layout");
+  AxisInfo ax = make_axis(axis_sizes, n_axes);
+  const long total = static_cast<long>(batch) * N;
+  const unsigned grid = static_cast<unsigned>((total + 7) / 8);
+  build_z_large_kernel<<<grid, 256, 0, stream>>>(raw, z, ldz, seg, lo_seg, total, N, c_raw, ax, F, tab);
+  HN_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_head(const float* x, int batch, int L, int D, const float* ln_w, const float* ln_b, const float* W,
+                const float* bias, int out_dims, float* logits, cudaStream_t stream) {
+  head_kernel<<<batch, 256, (D + 2) * sizeof(float), stream>>>(x, L, D, ln_w, ln_b, W, bias, out_dims, logits);
+  HN_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_pack_mask(const uint8_t* mask, uint64_t* bits, int batch, long N, cudaStream_t stream) {
+  const long tiles = (N + 63) / 64;
+  const long total = tiles * batch;
+  pack_mask_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, stream>>>(mask, bits, N, tiles, total);
+  HN_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_combine_generic(const float* part_acc, const float* part_ml, int batch, int nsplit, int H, int L,
+                           __half* O, int o_ld, int lo_seg, cudaStream_t stream) {
+  const long total = static_cast<long>(batch) * L * H;
+  combine_generic_kernel<<<static_cast<unsigned>((total + 7) / 8), 256, 0, stream>>>(part_acc, part_ml, batch,
+                                                                                      nsplit, H, L, O, o_ld, lo_seg);
+  HN_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_combine_vproj(const float* part_acc, const float* part_ml, int batch, int nsplit, int H, int L, int C,
+                         int zw, int dh, const float* Wv, const float* bv, __half* O, int o_ld, int lo_seg,
+                         cudaStream_t stream) {
+  HN_REQUIRE((zw == 32 || zw == 64) && C <= zw - 1 && dh <= 64, "combine_vproj: C < zw and dim_head <= 64 required");
+  const long total = static_cast<long>(batch) * L * H;
+  combine_vproj_kernel<<<static_cast<unsigned>((total + 7) / 8), 256, 0, stream>>>(part_acc, part_ml, batch, nsplit,
+                                                                                    H, L, C, zw, dh, Wv, bv, O, o_ld,
+                                                                                    lo_seg);
+  HN_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_broadcast_rows(const float* src, float* dst, long n, int batch, cudaStream_t stream) {
+  const unsigned grid = static_cast<unsigned>(n / 256 + 1 < 1184 ? n / 256 + 1 : 1184);
+  broadcast_rows_kernel<<<grid, 256, 0, stream>>>(src, dst, n, batch);
+  HN_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace hn

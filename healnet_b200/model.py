@@ -1,0 +1,503 @@
+"""Drop-in `HealNet` / `Attention` modules backed by libhealnet_b200.so (hand-written sm_100a kernels).
+
+Mirrors the reference's model surface (healnet/models/healnet.py): the keyword-only `HealNet(...)`
+constructor (:15-38) with its asserts (:121-122), `forward(tensors, mask, return_embeddings, verbose)`
+(:190-195), `get_attention_weights()` (:252-262), `Attention(query_dim, context_dim, heads, dim_head,
+dropout)` (:370), and — because checkpoints move both ways (explainer.py:359,400) — the exact parameter
+names / shapes / creation order of the reference's `state_dict()`. The modules below own parameters
+only; all arithmetic of the forward pass happens in the CUDA library behind the C ABI
+(include/healnet_b200.h). There is no PyTorch or CPU fallback: without the library or a CUDA device the
+forward raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import warnings
+from typing import List, Optional, Sequence, Union
+
+import torch
+from torch import nn
+
+from . import _lib
+from ._lib import HN_MAX_AXES, HN_MAX_MODALITIES, check, hn_desc, load_library
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Parameter containers. Names of attributes are part of the checkpoint format.
+# ----------------------------------------------------------------------------------------------------------
+class _FusedOnly(nn.Module):
+    def forward(self, *args, **kwargs):  # pragma: no cover - guard
+        raise RuntimeError(f"{type(self).__name__} is evaluated inside the fused HealNet forward "
+                           "(libhealnet_b200.so); call the owning HealNet module instead")
+
+
+class _GateMarker(_FusedOnly):
+    """Stands where the reference puts its SELU()/GELU() gate module (healnet.py:323-331) — no parameters;
+    keeps `net.2` the index of the second Linear."""
+
+    def __init__(self, kind: str):
+        super().__init__()
+        self.kind = kind
+
+    def extra_repr(self) -> str:
+        return f"a * {self.kind}(gates)"
+
+
+class _MeanOverLatents(_FusedOnly):
+    """Stands where the reference puts Reduce('b n d -> b d', 'mean') (healnet.py:182) — keeps LayerNorm /
+    Linear at indices 1 / 2 of `to_logits`."""
+
+
+class FeedForward(_FusedOnly):
+    """Parameters of the gated feed-forward (healnet.py:339-351): Linear(D, 8D) -> a*act(g) -> Linear(4D, D)."""
+
+    def __init__(self, dim: int, mult: int = 4, dropout: float = 0., snn: bool = False):
+        super().__init__()
+        self.net = nn.Sequential(
+            nn.Linear(dim, dim * mult * 2),
+            _GateMarker("selu" if snn else "gelu"),
+            nn.Linear(dim * mult, dim),
+            nn.Dropout(dropout),
+        )
+
+
+class Attention(nn.Module):
+    """Multi-head attention with the reference's 0.5 softmax temperature and LeakyReLU output projection
+    (healnet.py:369-426). Usable stand-alone: `Attention(query_dim, context_dim)(x, context=ctx, mask=m)`
+    runs `hn_attention_forward`; inside HealNet it only holds the parameters."""
+
+    def __init__(self, query_dim: int, context_dim: Optional[int] = None, heads: int = 8, dim_head: int = 64,
+                 dropout: float = 0.):
+        super().__init__()
+        inner = dim_head * heads
+        context_dim = query_dim if context_dim is None else context_dim
+        self.scale = dim_head ** -0.5
+        self.heads = heads
+        self.dim_head = dim_head
+        self.query_dim = query_dim
+        self.context_dim = context_dim
+        self.to_q = nn.Linear(query_dim, inner, bias=False)
+        self.to_kv = nn.Linear(context_dim, inner * 2, bias=False)
+        self.dropout = nn.Dropout(dropout)
+        self.to_out = nn.Sequential(nn.Linear(inner, query_dim), nn.LeakyReLU(negative_slope=1e-2))
+        self.attn_weights = None  # the streaming kernel never materialises the attention matrix
+        self._ws = None
+
+    def forward(self, x: torch.Tensor, context: Optional[torch.Tensor] = None,
+                mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        lib = load_library()
+        dev = _compute_device(self.to_q.weight)
+        if self.dropout.p > 0 and self.training:
+            raise NotImplementedError("attention dropout > 0 in training mode is not supported (forward-only path)")
+        ret_dev, ret_dtype = x.device, x.dtype
+        xs = x.detach().to(device=dev, dtype=torch.float32).contiguous()
+        b, n_q, qd = xs.shape
+        if qd != self.query_dim:
+            raise ValueError(f"x has width {qd}, expected query_dim={self.query_dim}")
+        cs = None
+        n_ctx, cd = n_q, qd
+        if context is not None:
+            cs = context.detach().to(device=dev, dtype=torch.float32).contiguous()
+            if cs.dim() != 3 or cs.shape[0] != b or cs.shape[2] != self.context_dim:
+                raise ValueError(f"context must be (batch, n, {self.context_dim}); got {tuple(cs.shape)}")
+            n_ctx, cd = cs.shape[1], cs.shape[2]
+        ms = None
+        if mask is not None:
+            ms = mask.detach().to(device=dev).reshape(b, -1).to(torch.uint8).contiguous()
+            if ms.shape[1] != n_ctx:
+                raise ValueError(f"mask has {ms.shape[1]} tokens per sample, context has {n_ctx}")
+        w = [_f32_dev(p, dev) for p in (self.to_q.weight, self.to_kv.weight, self.to_out[0].weight,
+                                        self.to_out[0].bias)]
+        out = torch.empty(b, n_q, qd, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            need = lib.hn_attention_workspace_bytes(b, n_q, n_ctx, qd, cd, self.heads, self.dim_head)
+            if need == 0:
+                raise _lib.HealNetLibraryError("hn_attention_workspace_bytes rejected the shape")
+            if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+                self._ws = torch.empty(need, device=dev, dtype=torch.uint8)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            check(lib.hn_attention_forward(b, n_q, n_ctx, qd, cd, self.heads, self.dim_head, xs.data_ptr(),
+                                           cs.data_ptr() if cs is not None else None, w[0].data_ptr(),
+                                           w[1].data_ptr(), w[2].data_ptr(), w[3].data_ptr(),
+                                           ms.data_ptr() if ms is not None else None, out.data_ptr(),
+                                           self._ws.data_ptr(), self._ws.numel(), stream), "hn_attention_forward")
+        return out.to(device=ret_dev, dtype=ret_dtype)
+
+
+class PreNorm(_FusedOnly):
+    """LayerNorm(s) in front of `fn` (healnet.py:306-321); parameters only."""
+
+    def __init__(self, dim: int, fn: nn.Module, context_dim: Optional[int] = None):
+        super().__init__()
+        self.fn = fn
+        self.norm = nn.LayerNorm(dim)
+        self.norm_context = nn.LayerNorm(context_dim) if context_dim is not None else None
+
+
+def _memoize(factory):
+    """Constructor-time weight tying: with `_cache=True` the same module instance is returned for a key
+    (behaviour of the reference's cache_fn, healnet.py:278-290)."""
+    made = {}
+
+    def get(_cache: bool = True, key=None):
+        if not _cache:
+            return factory()
+        if key not in made:
+            made[key] = factory()
+        return made[key]
+
+    return get
+
+
+def _compute_device(param: torch.Tensor) -> torch.device:
+    if param.device.type == "cuda":
+        return param.device
+    if not torch.cuda.is_available():
+        raise _lib.HealNetLibraryError(
+            "healnet_b200 needs a CUDA device (NVIDIA B200, sm_100a): there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _f32_dev(p: torch.Tensor, dev: torch.device) -> torch.Tensor:
+    t = p.detach()
+    if t.device != dev or t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.to(device=dev, dtype=torch.float32).contiguous()
+    return t
+
+
+# ----------------------------------------------------------------------------------------------------------
+class HealNet(nn.Module):
+    """HEALNet fusion model — same constructor, parameters and forward contract as the reference
+    (healnet/models/healnet.py:14-262); the forward pass runs as sm_100a kernels through the C ABI.
+
+    Differences, all deliberate and documented in DESIGN.md:
+      * forward does not mutate the caller's list (the reference does, :222);
+      * the attention matrices are never materialised, so `get_attention_weights()` returns `None`
+        entries (the reference keeps b*h*L*N floats per Attention module, :420);
+      * forward-only: outputs carry no autograd graph.
+    Quirks that ARE reproduced: softmax temperature 0.5 on top of dim_head**-0.5 (:375,:419); the latent
+    self-attention block runs after every modality (:228-245); a missing / mismatching modality skips only
+    its cross-attention + cross-FF unless `verbose=True` (:229-239); layer-0 weights are never tied (:161).
+    """
+
+    def __init__(
+        self,
+        *,
+        n_modalities: int,
+        channel_dims: List,
+        num_spatial_axes: List,
+        out_dims: int,
+        depth: int = 3,
+        num_freq_bands: int = 2,
+        max_freq: float = 10.,
+        l_c: int = 128,
+        l_d: int = 128,
+        x_heads: int = 8,
+        l_heads: int = 8,
+        cross_dim_head: int = 64,
+        latent_dim_head: int = 64,
+        attn_dropout: float = 0.,
+        ff_dropout: float = 0.,
+        weight_tie_layers: bool = False,
+        fourier_encode_data: bool = True,
+        self_per_cross_attn: int = 1,
+        final_classifier_head: bool = True,
+        snn: bool = True,
+    ):
+        super().__init__()
+        assert len(channel_dims) == len(num_spatial_axes), 'input channels and input axis must be of the same length'
+        assert len(num_spatial_axes) == n_modalities, 'input axis must be of the same length as the number of modalities'
+
+        self.input_axes = list(num_spatial_axes)
+        self.input_channels = list(channel_dims)
+        self.max_freq = max_freq
+        self.num_freq_bands = num_freq_bands
+        self.modalities = n_modalities
+        self.self_per_cross_attn = self_per_cross_attn
+        self.fourier_encode_data = fourier_encode_data
+        self._hparams = dict(depth=depth, l_c=l_c, l_d=l_d, x_heads=x_heads, l_heads=l_heads,
+                             cross_dim_head=cross_dim_head, latent_dim_head=latent_dim_head, out_dims=out_dims,
+                             snn=snn, final_classifier_head=final_classifier_head, attn_dropout=attn_dropout,
+                             ff_dropout=ff_dropout)
+
+        per_axis = (2 * num_freq_bands + 1) if fourier_encode_data else 0
+        input_dims = [c + a * per_axis for c, a in zip(channel_dims, num_spatial_axes)]
+
+        # Parameter creation order follows the reference (:143-185) so that a given torch seed yields the
+        # same initial weights: latents; per layer [latent attn, latent ff, then per modality cross attn,
+        # cross ff]; head last.
+        self.latents = nn.Parameter(torch.randn(l_c, l_d))
+
+        def cross_attn_factory(m):
+            return lambda: PreNorm(l_d, Attention(l_d, input_dims[m], heads=x_heads, dim_head=cross_dim_head,
+                                                  dropout=attn_dropout), context_dim=input_dims[m])
+
+        get_cross_attn = [_memoize(cross_attn_factory(m)) for m in range(n_modalities)]
+        get_latent_attn = _memoize(lambda: PreNorm(l_d, Attention(l_d, heads=l_heads, dim_head=latent_dim_head,
+                                                                  dropout=attn_dropout)))
+        get_cross_ff = _memoize(lambda: PreNorm(l_d, FeedForward(l_d, dropout=ff_dropout, snn=snn)))
+        get_latent_ff = _memoize(lambda: PreNorm(l_d, FeedForward(l_d, dropout=ff_dropout, snn=snn)))
+
+        self.layers = nn.ModuleList([])
+        for i in range(depth):
+            tie = i > 0 and weight_tie_layers
+            latent_block = nn.ModuleList([])
+            for block in range(self_per_cross_attn):
+                latent_block.append(get_latent_attn(_cache=tie, key=block))
+                latent_block.append(get_latent_ff(_cache=tie, key=block))
+            entries = []
+            for m in range(n_modalities):
+                entries.append(get_cross_attn[m](_cache=tie))
+                entries.append(get_cross_ff(_cache=tie))
+            self.layers.append(nn.ModuleList([*entries, latent_block]))
+
+        self.to_logits = nn.Sequential(
+            _MeanOverLatents(),
+            nn.LayerNorm(l_d),
+            nn.Linear(l_d, out_dims),
+        ) if final_classifier_head else nn.Identity()
+
+        # native state (not part of the checkpoint)
+        self._handle = None
+        self._handle_dev = None
+        self._weights_sig = None
+        self._staged = []       # keeps staged fp32 device copies alive while the handle borrows them
+        self._workspace = None
+        self.last_launch_count = 0
+        self._warned = set()
+
+    # ------------------------------------------------------------------------------------------------ native
+    _NATIVE_DEFAULTS = dict(_handle=None, _handle_dev=None, _weights_sig=None, _staged=(), _workspace=None)
+
+    def __getstate__(self):
+        """copy.deepcopy / pickle / torch.save(model): the native handle, staged weights and workspace are
+        per-object caches and are rebuilt lazily by the copy."""
+        state = dict(self.__dict__)
+        for k, v in self._NATIVE_DEFAULTS.items():
+            state[k] = [] if k == "_staged" else v
+        state["_warned"] = set()
+        return state
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def _release(self):
+        if getattr(self, "_handle", None) is not None:
+            load_library().hn_destroy(self._handle)
+            self._handle = None
+
+    def _desc(self) -> hn_desc:
+        hp = self._hparams
+        if self.modalities > HN_MAX_MODALITIES:
+            raise ValueError(f"at most {HN_MAX_MODALITIES} modalities are supported")
+        d = hn_desc()
+        d.n_modalities = self.modalities
+        d.depth = hp["depth"]
+        d.l_c, d.l_d = hp["l_c"], hp["l_d"]
+        d.x_heads, d.cross_dim_head = hp["x_heads"], hp["cross_dim_head"]
+        d.l_heads, d.latent_dim_head = hp["l_heads"], hp["latent_dim_head"]
+        d.num_freq_bands = self.num_freq_bands
+        d.out_dims = hp["out_dims"]
+        d.self_per_cross_attn = self.self_per_cross_attn
+        d.snn = 1 if hp["snn"] else 0
+        d.final_classifier_head = 1 if hp["final_classifier_head"] else 0
+        d.fourier_encode_data = 1 if self.fourier_encode_data else 0
+        d.max_freq = float(self.max_freq)
+        for m in range(self.modalities):
+            d.channel_dims[m] = int(self.input_channels[m])
+            d.num_spatial_axes[m] = int(self.input_axes[m])
+        return d
+
+    def _slot_params(self):
+        """[(layer, slot, [parameters in the order hn_set_weights documents])]"""
+        M = self.modalities
+        out = [(-1, 0, [self.latents])]
+        if self._hparams["final_classifier_head"]:
+            ln, lin = self.to_logits[1], self.to_logits[2]
+            out.append((-1, 1, [ln.weight, ln.bias, lin.weight, lin.bias]))
+        for l, layer in enumerate(self.layers):
+            for m in range(M):
+                pa, pf = layer[2 * m], layer[2 * m + 1]
+                out.append((l, 2 * m, [pa.norm.weight, pa.norm.bias, pa.norm_context.weight, pa.norm_context.bias,
+                                       pa.fn.to_q.weight, pa.fn.to_kv.weight, pa.fn.to_out[0].weight,
+                                       pa.fn.to_out[0].bias]))
+                out.append((l, 2 * m + 1, [pf.norm.weight, pf.norm.bias, pf.fn.net[0].weight, pf.fn.net[0].bias,
+                                           pf.fn.net[2].weight, pf.fn.net[2].bias]))
+            if self.self_per_cross_attn > 0:
+                pa, pf = layer[-1][0], layer[-1][1]
+                out.append((l, 2 * M, [pa.norm.weight, pa.norm.bias, pa.fn.to_q.weight, pa.fn.to_kv.weight,
+                                       pa.fn.to_out[0].weight, pa.fn.to_out[0].bias]))
+                out.append((l, 2 * M + 1, [pf.norm.weight, pf.norm.bias, pf.fn.net[0].weight, pf.fn.net[0].bias,
+                                           pf.fn.net[2].weight, pf.fn.net[2].bias]))
+        return out
+
+    def _sync_native(self, dev: torch.device, stream: int):
+        """Creates the native handle on first use and re-registers / repacks weights whenever a parameter's
+        storage, device or in-place version changed (optimizer steps, load_state_dict, .to())."""
+        lib = load_library()
+        if self.self_per_cross_attn not in (0, 1):
+            # the reference unpacks `self_attn, self_ff = layer[-1]` (healnet.py:242)
+            raise ValueError("too many values to unpack: self_per_cross_attn must be 0 or 1")
+        if self._handle is not None and self._handle_dev != dev:
+            self._release()
+        if self._handle is None:
+            hp = ctypes.c_void_p()
+            d = self._desc()
+            check(lib.hn_create(ctypes.byref(d), ctypes.byref(hp)), "hn_create")
+            self._handle, self._handle_dev, self._weights_sig = hp, dev, None
+        slots = self._slot_params()
+        sig = tuple((p.data_ptr(), p._version, p.dtype, p.device) for _, _, ps in slots for p in ps)
+        if sig == self._weights_sig:
+            return
+        staged = []
+        for layer, slot, ps in slots:
+            ts = [_f32_dev(p, dev) for p in ps]
+            staged.extend(ts)
+            arr = (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+            check(lib.hn_set_weights(self._handle, layer, slot, arr, len(ts)), "hn_set_weights")
+        self._staged = staged
+        check(lib.hn_pack_weights(self._handle, stream), "hn_pack_weights")
+        self._weights_sig = sig
+
+    def _warn_once(self, key, msg):
+        if key not in self._warned:
+            self._warned.add(key)
+            warnings.warn(msg, RuntimeWarning, stacklevel=3)
+
+    # ------------------------------------------------------------------------------------------------ forward
+    def forward(self,
+                tensors: List[Union[torch.Tensor, None]],
+                mask: Optional[torch.Tensor] = None,
+                return_embeddings: bool = False,
+                verbose: bool = False):
+        lib = load_library()
+        hp = self._hparams
+        if self.training and (hp["attn_dropout"] > 0 or hp["ff_dropout"] > 0):
+            raise NotImplementedError("dropout > 0 in training mode is not supported (forward-only path)")
+        dev = _compute_device(self.latents)
+        M = self.modalities
+        n_given = len(tensors)
+        missing_idx = [i for i, t in enumerate(tensors) if t is None]
+        if verbose:
+            print(f"Missing modalities indices: {missing_idx}")
+
+        batch = None
+        ret_dev, ret_dtype = None, None
+        staged: List[Optional[torch.Tensor]] = [None] * M
+        axis_sizes = (ctypes.c_int * (HN_MAX_MODALITIES * HN_MAX_AXES))()
+        for i in range(min(n_given, M)):
+            data = tensors[i]
+            if data is None:
+                continue
+            b, *axis, c = data.shape
+            assert len(axis) == self.input_axes[i], (f'input data for modality {i + 1} must hav'
+                                                     f' the same number of axis as the input axis parameter')
+            batch = b  # the reference takes the batch size from the last modality it encodes (:206,:225)
+            ret_dev, ret_dtype = data.device, data.dtype
+            if c != self.input_channels[i]:
+                # the reference fails inside its try/except and silently skips this modality (:235-239)
+                self._warn_once(("chan", i), f"modality {i}: got {c} channels, model expects "
+                                f"{self.input_channels[i]}; its cross-attention is skipped (reference behaviour)")
+                continue
+            if len(axis) > HN_MAX_AXES:
+                raise ValueError(f"at most {HN_MAX_AXES} spatial axes per modality are supported")
+            staged[i] = data.detach().to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+            for a, s in enumerate(axis):
+                axis_sizes[i * HN_MAX_AXES + a] = int(s)
+        if batch is None:
+            # reference: `b` is unbound -> UnboundLocalError at :225
+            raise UnboundLocalError("cannot infer the batch size: every modality is missing")
+        for i, t in enumerate(staged):
+            if t is not None and t.shape[0] != batch:
+                raise ValueError("all modalities must share the batch dimension")
+        # `verbose=True` turns a missing modality into a full skip (self-attention included, :229-232)
+        skip_self = [False] * M
+        if verbose:
+            for i in missing_idx:
+                if i < M:
+                    print(f"Skipping update in fusion layer for missing modality {i + 1}")
+                    skip_self[i] = True
+
+        mask_dev, mask_tokens = None, 0
+        if mask is not None:
+            mask_dev = mask.detach().to(device=dev).reshape(mask.shape[0], -1).to(torch.uint8).contiguous()
+            if mask_dev.shape[0] != batch:
+                raise ValueError("mask must have the batch dimension of the inputs")
+            mask_tokens = int(mask_dev.shape[1])
+            for i, t in enumerate(staged):
+                if t is not None:
+                    n_tok = t.numel() // (batch * t.shape[-1])
+                    if n_tok != mask_tokens and mask_tokens != 1:
+                        # the reference's masked_fill_ raises on the shape mismatch and the modality is skipped
+                        self._warn_once(("mask", i), f"modality {i}: mask has {mask_tokens} tokens, modality has "
+                                        f"{n_tok}; its cross-attention is skipped (reference behaviour)")
+                        staged[i] = None
+            if mask_tokens == 1 and any(t is not None and t.numel() // (batch * t.shape[-1]) != 1 for t in staged):
+                raise NotImplementedError("a single-token mask broadcast over longer modalities is not supported")
+
+        want_latents = return_embeddings or not hp["final_classifier_head"]
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            self._sync_native(dev, stream)
+            out = self._launch(lib, staged, axis_sizes, skip_self, mask_dev, mask_tokens, batch, want_latents, dev,
+                               stream)
+        if ret_dtype is not None and not ret_dtype.is_floating_point:
+            ret_dtype = torch.float32
+        return out.to(device=ret_dev, dtype=ret_dtype)
+
+    def _launch(self, lib, staged, axis_sizes, skip_self, mask_dev, mask_tokens, batch, want_latents, dev, stream):
+        hp = self._hparams
+        M = self.modalities
+        ptrs = (ctypes.c_void_p * HN_MAX_MODALITIES)()
+        sizes = (ctypes.c_int * (HN_MAX_MODALITIES * HN_MAX_AXES))(*axis_sizes)
+        for i in range(M):
+            ptrs[i] = staged[i].data_ptr() if staged[i] is not None else None
+            if staged[i] is None:
+                for a in range(HN_MAX_AXES):   # sizing needs sane extents for absent modalities too
+                    sizes[i * HN_MAX_AXES + a] = max(1, sizes[i * HN_MAX_AXES + a])
+        need = lib.hn_workspace_bytes(self._handle, batch, sizes)
+        if need == 0:
+            raise _lib.HealNetLibraryError(f"hn_workspace_bytes failed: {_lib.last_error()}")
+        if self._workspace is None or self._workspace.device != dev or self._workspace.numel() < need:
+            self._workspace = None
+            self._workspace = torch.empty(need, device=dev, dtype=torch.uint8)
+        if want_latents:
+            out = torch.empty(batch, hp["l_c"], hp["l_d"], device=dev, dtype=torch.float32)
+            lat_ptr, log_ptr = out.data_ptr(), None
+        else:
+            out = torch.empty(batch, hp["out_dims"], device=dev, dtype=torch.float32)
+            lat_ptr, log_ptr = None, out.data_ptr()
+        skip = (ctypes.c_int * HN_MAX_MODALITIES)(*[1 if f else 0 for f in skip_self]) if any(skip_self) else None
+        check(lib.hn_forward(self._handle, batch, ptrs, sizes, skip,
+                             mask_dev.data_ptr() if mask_dev is not None else None,
+                             mask_tokens, lat_ptr, log_ptr, self._workspace.data_ptr(), self._workspace.numel(),
+                             stream), "hn_forward")
+        self.last_launch_count = lib.hn_last_launch_count(self._handle)
+        return out
+
+    # ------------------------------------------------------------------------------------------- measurement
+    def enable_kernel_timing(self, on: bool = True) -> None:
+        """Brackets every cross-attention kernel of subsequent forwards with CUDA events (hn_profile_enable)."""
+        if self._handle is None:
+            dev = _compute_device(self.latents)
+            with torch.cuda.device(dev):
+                self._sync_native(dev, torch.cuda.current_stream(dev).cuda_stream)
+        check(load_library().hn_profile_enable(self._handle, 1 if on else 0), "hn_profile_enable")
+
+    def read_kernel_timing(self, modality: int) -> dict:
+        """Device time / launches / executed tensor FLOPs / exponentials of modality `modality`'s cross-attention
+        kernels in the last forward. Synchronise the stream first."""
+        ms, n = ctypes.c_float(), ctypes.c_int()
+        fl, ex = ctypes.c_double(), ctypes.c_double()
+        check(load_library().hn_profile_read(self._handle, modality, ctypes.byref(ms), ctypes.byref(n),
+                                             ctypes.byref(fl), ctypes.byref(ex)), "hn_profile_read")
+        return dict(ms=ms.value, launches=n.value, flops=fl.value, exps=ex.value)
+
+    def get_attention_weights(self) -> List[Optional[torch.Tensor]]:
+        """One entry per Attention module, in module order (healnet.py:252-262). The streaming kernels never
+        materialise the (b*h, L, N) attention matrices, so the entries are None (as in the reference before
+        its first forward)."""
+        return [m.attn_weights for m in self.modules() if isinstance(m, Attention)]

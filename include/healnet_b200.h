@@ -1,0 +1,154 @@
+/* healnet_b200.h — C ABI of the B200-native HEALNet fusion-forward library (libhealnet_b200.so).
+ *
+ * The reference (konst-int-i/healnet) has no FFI / plugin interface: its boundary for this path is the
+ * Python nn.Module surface of `HealNet` / `Attention` (healnet/models/healnet.py:14-262, 369-426).
+ * This header is the native boundary underneath the drop-in module `healnet_b200.HealNet`; every entry
+ * point names the reference code it replaces. Conventions: plain pointers and sizes only, all buffers
+ * caller-owned device memory (fp32 unless stated), every call is stream-ordered on the given CUDA stream
+ * and never synchronises the host, returns 0 on success or a negative code (message via
+ * hn_last_error()), never throws or exits. One handle may be used from one stream at a time.
+ */
+#ifndef HEALNET_B200_H_
+#define HEALNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define HN_API __attribute__((visibility("default")))
+#else
+#define HN_API
+#endif
+
+#define HN_MAX_MODALITIES 16
+#define HN_MAX_AXES 4
+
+typedef struct hn_handle hn_handle;
+
+/* Constructor hyper-parameters; field names follow HealNet.__init__ (healnet/models/healnet.py:15-38). */
+typedef struct hn_desc {
+  int n_modalities;
+  int depth;
+  int l_c;              /* number of latents (rows of the latent array) */
+  int l_d;              /* latent width */
+  int x_heads;
+  int cross_dim_head;
+  int l_heads;
+  int latent_dim_head;
+  int num_freq_bands;
+  int out_dims;
+  int self_per_cross_attn;   /* 0 or 1 (the reference breaks for >= 2, healnet.py:242) */
+  int snn;                   /* 1: a*selu(g) gate, 0: a*gelu(g) (healnet.py:323-331,342) */
+  int final_classifier_head;
+  int fourier_encode_data;
+  float max_freq;
+  int channel_dims[HN_MAX_MODALITIES];
+  int num_spatial_axes[HN_MAX_MODALITIES];
+} hn_desc;
+
+/* Replaces HealNet.__init__ (healnet.py:121-185): validates the configuration, sizes the packed-weight
+ * store. No parameters are created here — they stay torch nn.Parameters owned by the caller. */
+HN_API int hn_create(const hn_desc* desc, hn_handle** out);
+HN_API int hn_destroy(hn_handle* h);
+
+/* Thread-local description of the last failure on the calling thread. */
+HN_API const char* hn_last_error(void);
+
+/* Registers the (borrowed, fp32, contiguous, device) parameter tensors of one module, in state_dict
+ * naming:
+ *   layer >= 0, slot 2m     cross-attention of modality m (healnet.py:146-149):
+ *        {norm.weight, norm.bias, norm_context.weight, norm_context.bias,
+ *         fn.to_q.weight, fn.to_kv.weight, fn.to_out.0.weight, fn.to_out.0.bias}            n = 8
+ *   layer >= 0, slot 2m+1   cross feed-forward (healnet.py:153):
+ *        {norm.weight, norm.bias, fn.net.0.weight, fn.net.0.bias, fn.net.2.weight, fn.net.2.bias}  n = 6
+ *   layer >= 0, slot 2M     latent self-attention (healnet.py:151):
+ *        {norm.weight, norm.bias, fn.to_q.weight, fn.to_kv.weight, fn.to_out.0.weight, fn.to_out.0.bias}  n = 6
+ *   layer >= 0, slot 2M+1   latent feed-forward (healnet.py:154): as the cross feed-forward      n = 6
+ *   layer == -1, slot 0     {latents}                                                        n = 1
+ *   layer == -1, slot 1     {to_logits.1.weight, to_logits.1.bias, to_logits.2.weight, to_logits.2.bias} n = 4
+ * Tied layers (weight_tie_layers, healnet.py:161, 278-290) simply register the same pointers again. */
+HN_API int hn_set_weights(hn_handle* h, int layer, int slot, const void* const* dev_ptrs, int n);
+
+/* Repacks the registered fp32 parameters into the fp16 tensor-core operand layouts (scale / LayerNorm
+ * affine folding, head padding, gate interleave). Call once after hn_set_weights and again whenever
+ * parameter values change. Allocates the packed store on first use. */
+HN_API int hn_pack_weights(hn_handle* h, void* cuda_stream);
+
+/* Scratch requirement of hn_forward for `batch` samples whose modality m has spatial extents
+ * axis_sizes[m*HN_MAX_AXES + a] (a < num_spatial_axes[m]). Returns 0 on error. */
+HN_API size_t hn_workspace_bytes(const hn_handle* h, int batch, const int* axis_sizes);
+
+/* Replaces HealNet.forward (healnet.py:190-250), default verbose=False semantics.
+ *   modality_ptrs[m] : fp32 (batch, *axes_m, channel_dims[m]) row-major channel-last, or NULL when the
+ *                      modality is missing (its cross-attention + cross-FF are skipped, the latent
+ *                      self-attention block still runs — healnet.py:229-245).
+ *   skip_latent_block: optional n_modalities flags; nonzero also skips the latent self-attention + FF that
+ *                      follows modality m (the reference's `verbose=True` + missing-modality path, healnet.py:229-232).
+ *   mask             : optional uint8 (batch, mask_tokens), nonzero = keep (healnet.py:411-415); applied to
+ *                      every cross-attention whose token count equals mask_tokens.
+ *   latents_out      : optional fp32 (batch, l_c, l_d) — the `return_embeddings=True` result.
+ *   logits_out       : optional fp32 (batch, out_dims)  — to_logits(x) (healnet.py:181-185,250).
+ * The caller's input buffers are never written (the reference mutates its input list, healnet.py:222). */
+HN_API int hn_forward(hn_handle* h, int batch, const void* const* modality_ptrs, const int* axis_sizes,
+                      const int* skip_latent_block, const uint8_t* mask, long mask_tokens, float* latents_out,
+                      float* logits_out, void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* Number of kernels hn_forward enqueued on its last call for this handle (for bench accounting). */
+HN_API int hn_last_launch_count(const hn_handle* h);
+
+/* Measurement hook (bench.py roofline): when enabled, hn_forward brackets every cross-attention kernel launch
+ * with CUDA events on its own stream. After the caller has synchronised the stream, hn_profile_read sums, for one
+ * modality, the device time of those launches in the LAST forward, their count, the tensor-core FLOPs they executed
+ * (padded tiles included) and the softmax exponentials they evaluated. */
+HN_API int hn_profile_enable(hn_handle* h, int on);
+HN_API int hn_profile_read(hn_handle* h, int modality, float* ms, int* launches, double* flops, double* exps);
+
+/* Replaces Attention.forward (healnet.py:400-426) for the stand-alone `Attention` module:
+ *   out = LeakyReLU_0.01( softmax(2 q k^T / sqrt(dim_head)) v  Wo^T + bo ),  q = x Wq^T, [k,v] = ctx Wkv^T.
+ * x (batch, n_q, query_dim), context (batch, n_ctx, context_dim) (NULL: self-attention on x),
+ * weights in reference layout (to_q.weight, to_kv.weight, to_out.0.weight, to_out.0.bias), all fp32.
+ * workspace: hn_attention_workspace_bytes(...) bytes of device scratch. */
+HN_API size_t hn_attention_workspace_bytes(int batch, int n_q, long n_ctx, int query_dim, int context_dim, int heads,
+                                    int dim_head);
+HN_API int hn_attention_forward(int batch, int n_q, long n_ctx, int query_dim, int context_dim, int heads, int dim_head,
+                         const float* x, const float* context, const float* w_q, const float* w_kv,
+                         const float* w_out, const float* b_out, const uint8_t* mask, float* out, void* workspace,
+                         size_t workspace_bytes, void* cuda_stream);
+
+/* ---- kernel-level entry points (used by the parity tests and profiling scripts) ------------------ */
+/* C[M,N] = A[M,K] B[N,K]^T on tcgen05; A, B fp16 row-major; epi: 0 f16 out, 1 gated f16 out (N/2 cols),
+ * 2 fp32 residual +=, 3 fp32 residual += leaky, 4 fp32 out, 5 fp32 leaky out; act: 0 selu, 1 gelu.
+ * Split precision: operand rows may hold [hi | lo] fp16 pairs (lo = fp16(x - hi)) with the lo part a_seg / b_seg
+ * columns (multiple of 64, >= K) after the hi part; terms 1: A.B, 2: A.(B_hi + B_lo),
+ * 3: A_hi.B_hi + A_lo.B_hi + A_hi.B_lo. out_seg > 0 (fp16 epilogues): lo part of the result at column + out_seg. */
+HN_API int hn_op_gemm(const void* A, const void* B, int M, int N, int K, int lda, int ldb, int epi, int act,
+                      const float* bias, void* out, int ldo, int terms, int a_seg, int b_seg, int out_seg,
+                      void* cuda_stream);
+/* y rows = [hi (seg cols) | lo at column lo_seg (0: none)] of LayerNorm(x) * gamma + beta, zero padded to seg. */
+HN_API int hn_op_layernorm_f16(const float* x, int ldx, const float* gamma, const float* beta, void* y, int ldy,
+                               int seg, int lo_seg, long rows, int D, void* cuda_stream);
+/* Fourier tables + standardised context rows z (fp16). small != 0: dense (batch, N, ldz) rows, ldz = 32 or 64,
+ * with the ones column at index C < ldz; else (batch*N, ldz). tab: scratch of sum(axis sizes)*(2*bands+1) floats. */
+HN_API int hn_op_build_context(const float* raw, void* z, int ldz, int small, int batch, int c_raw, int n_axes,
+                        const int* axis_sizes, int n_bands, float max_freq, int fourier, float* tab,
+                        void* cuda_stream);
+HN_API int hn_op_attention_nsplit(int batch, int L, int H, long N);
+/* Streaming attention partials + combine. shared_kv != 0: small-C path (Q rows kv_ld = 32 | 64 wide per head,
+ * KV = z rows); part_acc rows are kv_ld (small-C) or 64 (generic) floats wide. */
+HN_API int hn_op_attention(const void* Q, int q_ld, const void* KV, long kv_ld, int k_col0, int v_col0, int shared_kv,
+                    int batch, int L, int H, long N, int nsplit, const uint8_t* mask, void* mask_bits_scratch,
+                    float* part_acc, float* part_ml, void* cuda_stream);
+HN_API int hn_op_combine(const float* part_acc, const float* part_ml, int batch, int nsplit, int H, int L, int small_C,
+                  int zw, int dh, const float* Wv, const float* bv, void* O, int o_ld, void* cuda_stream);
+/* test-only: one-tile UMMA/TMA/TMEM convention probe (probe.cu) */
+HN_API int hn_debug_probe(const void* Q, const void* K, const void* V, int kd, int vd, float* S_out, float* U_out,
+                   const int* overrides, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HEALNET_B200_H_ */

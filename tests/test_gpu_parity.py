@@ -1,0 +1,180 @@
+"""GPU (B200): parity of the CUDA path, called through the drop-in module -> C ABI, against
+  (a) the committed reference-run fixtures (tests/golden), and
+  (b) the oracle on seeded inputs at sizes it finishes in seconds.
+Tolerance (BASELINE.json north_star): rtol 1e-3 / atol 1e-4 in fp32 for logits; the latent array is
+compared at the same rtol with atol 5e-4 (it is 2-3 orders of magnitude larger in scale than the logits'
+atol: |latents| ~ 1..10 after `depth` residual updates)."""
+import copy
+
+import pytest
+import torch
+
+import healnet_b200
+from healnet_b200 import Attention, HealNet
+from oracle import healnet_oracle as O
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-3, 1e-4
+LAT_ATOL = 5e-4
+CASES = ["tri_small", "omic_wsi_tied", "plain_no_head", "two_ltiles"]
+
+
+def _model(meta, sd):
+    m = HealNet(**meta["kwargs"])
+    m.load_state_dict(sd)
+    return m.cuda().eval()
+
+
+def _inputs(ins, n):
+    return [ins[str(i)].cuda() for i in range(n)]
+
+
+def _cfg(kwargs):
+    return O.OracleConfig(**{k: v for k, v in kwargs.items() if k in O.OracleConfig.__dataclass_fields__})
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_golden_forward(golden, name):
+    meta, sd, ins, outs, _ = golden(name)
+    m = _model(meta, sd)
+    x = _inputs(ins, meta["kwargs"]["n_modalities"])
+    keep = [t.clone() for t in x]
+    lat = m(list(x), return_embeddings=True)
+    assert lat.device.type == "cuda" and lat.dtype == torch.float32
+    torch.testing.assert_close(lat.cpu(), outs["latents"], rtol=RTOL, atol=LAT_ATOL)
+    if "logits" in outs:
+        torch.testing.assert_close(m(list(x)).cpu(), outs["logits"], rtol=RTOL, atol=ATOL)
+    else:  # final_classifier_head=False -> Identity head returns the latent array (healnet.py:185)
+        torch.testing.assert_close(m(list(x)).cpu(), outs["latents"], rtol=RTOL, atol=LAT_ATOL)
+    for a, b in zip(x, keep):  # unlike the reference (healnet.py:222) the caller's tensors are untouched
+        assert torch.equal(a, b)
+    assert m.last_launch_count > 0
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_golden_missing_modalities(golden, name):
+    meta, sd, ins, outs, _ = golden(name)
+    m = _model(meta, sd)
+    x = _inputs(ins, meta["kwargs"]["n_modalities"])
+    miss = [x[0], None] + x[2:]
+    torch.testing.assert_close(m(miss, return_embeddings=True).cpu(), outs["missing1_latents"], rtol=RTOL, atol=LAT_ATOL)
+    torch.testing.assert_close(m(miss, return_embeddings=True, verbose=True).cpu(), outs["missing1_verbose_latents"],
+                               rtol=RTOL, atol=LAT_ATOL)
+    torch.testing.assert_close(m([x[0]], return_embeddings=True).cpu(), outs["short_list_latents"], rtol=RTOL,
+                               atol=LAT_ATOL)
+
+
+def test_golden_mask(golden):
+    meta, sd, ins, outs, _ = golden("masked")
+    m = _model(meta, sd)
+    out = m([ins["0"].cuda()], mask=ins["mask"].cuda())
+    torch.testing.assert_close(out.cpu(), outs["logits"], rtol=RTOL, atol=ATOL)
+    lat = m([ins["0"].cuda()], mask=ins["mask"].cuda(), return_embeddings=True)
+    torch.testing.assert_close(lat.cpu(), outs["latents"], rtol=RTOL, atol=LAT_ATOL)
+
+
+def test_golden_attention_module(golden):
+    meta, sd, ins, outs, extra = golden("attention")
+    att = Attention(**meta["kwargs"])
+    att.load_state_dict(sd)
+    att = att.cuda().eval()
+    x, ctx, mask = ins["x"].cuda(), ins["context"].cuda(), ins["mask"].cuda()
+    torch.testing.assert_close(att(x, context=ctx).cpu(), outs["cross"], rtol=RTOL, atol=2e-4)
+    torch.testing.assert_close(att(x, context=ctx, mask=mask).cpu(), outs["cross_masked"], rtol=RTOL, atol=2e-4)
+    att2 = Attention(**meta["kwargs_self"])
+    att2.load_state_dict({k.split("/", 1)[1]: v for k, v in extra.items() if k.startswith("sd2/")})
+    torch.testing.assert_close(att2.cuda()(x).cpu(), outs["self"], rtol=RTOL, atol=2e-4)
+
+
+def test_reference_unit_tests_shapes():
+    """The bodies of the reference's healnet/tests/test_healnet.py:26-67 (CPU tensors, CPU-constructed
+    modules) against the drop-in classes."""
+    b, t_d, i_c, l_c, l_d = 10, 2189, 100, 256, 32
+    query = torch.randn(b, 1, t_d)
+    latent = torch.randn(b, l_c, l_d)
+    attention = Attention(query_dim=l_d, context_dim=t_d)
+    assert attention(x=latent, context=query).shape == (b, l_c, l_d)
+    tabular = torch.randn(b, 1, t_d)
+    image = torch.randn(b, 224, 224, i_c)
+    m1 = HealNet(n_modalities=1, channel_dims=[t_d], num_spatial_axes=[1], out_dims=5)
+    out1 = m1([tabular])
+    assert out1.shape == (b, 5) and out1.device.type == "cpu" and bool(torch.isfinite(out1).all())
+    m2 = HealNet(n_modalities=2, channel_dims=[t_d, i_c], num_spatial_axes=[1, 2], out_dims=4)
+    out2 = m2([tabular, image])
+    assert out2.shape == (b, 4) and bool(torch.isfinite(out2).all())
+    with pytest.raises(AssertionError):
+        HealNet(n_modalities=1, channel_dims=[t_d, i_c], num_spatial_axes=[1, 1], out_dims=4)
+
+
+def _randomise(model, seed):
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith("norm.weight") or n.endswith("norm_context.weight") or n == "to_logits.1.weight":
+                p.copy_(1.0 + 0.3 * torch.randn(p.shape, generator=g))
+            elif n.endswith(".bias"):
+                p.copy_(0.3 * torch.randn(p.shape, generator=g))
+
+
+ORACLE_CASES = {
+    # README-shaped 3-modality model at reduced spatial extent (cfg 1 family): tab wide-context, img/vol small-C
+    "readme_reduced": (dict(n_modalities=3, channel_dims=[2000, 3, 3], num_spatial_axes=[1, 2, 3], out_dims=4,
+                            l_c=256, l_d=128), [(2, 1, 2000), (2, 56, 56, 3), (2, 4, 40, 40, 3)]),
+    # cfg 2 family: omic + WSI patch features (generic K/V projection path), latent 256 x 512 at reduced N
+    "omic_wsi": (dict(n_modalities=2, channel_dims=[2000, 1024], num_spatial_axes=[1, 1], out_dims=4, l_c=256,
+                      l_d=512, depth=2), [(2, 1, 2000), (2, 700, 1024)]),
+    # tuned production hyper-parameters (config/best_hyperparams.yml:8-18,30): tiny odd latents, 1 head of 63
+    "production_odd": (dict(n_modalities=2, channel_dims=[300, 96], num_spatial_axes=[1, 1], out_dims=4, l_c=25,
+                            l_d=119, x_heads=1, cross_dim_head=63, self_per_cross_attn=0),
+                       [(3, 1, 300), (3, 333, 96)]),
+}
+
+
+@pytest.mark.parametrize("name", list(ORACLE_CASES))
+def test_against_oracle(name):
+    kw, shapes = ORACLE_CASES[name]
+    torch.manual_seed(11)
+    model = HealNet(**kw).eval()
+    _randomise(model, 5)
+    g = torch.Generator().manual_seed(3)
+    xs = [torch.rand(s, generator=g) for s in shapes]
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    want = O.forward(sd, _cfg(kw), xs)
+    want_lat = O.forward(sd, _cfg(kw), xs, return_embeddings=True)
+    model.cuda()
+    got = model([t.cuda() for t in xs]).cpu()
+    got_lat = model([t.cuda() for t in xs], return_embeddings=True).cpu()
+    torch.testing.assert_close(got_lat, want_lat, rtol=RTOL, atol=LAT_ATOL)
+    torch.testing.assert_close(got, want, rtol=RTOL, atol=ATOL)
+
+
+def test_repack_after_inplace_update_and_device_moves():
+    kw, shapes = ORACLE_CASES["production_odd"]
+    torch.manual_seed(2)
+    model = HealNet(**kw).eval().cuda()
+    xs = [torch.rand(s).cuda() for s in shapes]
+    a = model(xs)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.mul_(1.05)
+    b = model(xs)
+    assert not torch.allclose(a, b)
+    sd = {k: v.cpu() for k, v in model.state_dict().items()}
+    want = O.forward(sd, _cfg(kw), [t.cpu() for t in xs])
+    torch.testing.assert_close(b.cpu(), want, rtol=RTOL, atol=ATOL)
+    # CPU-resident module + CPU inputs: staged to the GPU, result returned on the CPU
+    c = copy.deepcopy(model).cpu()([t.cpu() for t in xs])
+    assert c.device.type == "cpu"
+    torch.testing.assert_close(c, b.cpu(), rtol=1e-5, atol=1e-6)
+
+
+def test_batch_independence_and_determinism():
+    kw, shapes = ORACLE_CASES["readme_reduced"]
+    torch.manual_seed(4)
+    model = HealNet(**kw).eval().cuda()
+    xs = [torch.rand(s).cuda() for s in shapes]
+    full = model(xs)
+    assert torch.equal(full, model(xs)), "forward must be deterministic (fixed split-combine order)"
+    for i in range(xs[0].shape[0]):
+        one = model([t[i:i + 1] for t in xs])
+        torch.testing.assert_close(one, full[i:i + 1], rtol=1e-4, atol=2e-5)

@@ -1,0 +1,55 @@
+"""GPU (B200): size-independent properties at BASELINE.json's full token counts, where the oracle would take
+minutes and tens of GB. Softmax attention over a set of tokens offers:
+  * replication invariance: with Fourier features off, N identical tokens attend exactly like 1 token;
+  * mask == removal: masking tokens out equals deleting them (set semantics without positional features);
+  * permutation invariance over the token axis (no positional features);
+and the path as a whole is per-sample (batch independence at full size)."""
+import pytest
+import torch
+
+from healnet_b200 import HealNet
+
+pytestmark = pytest.mark.gpu
+
+
+def _m(**kw):
+    torch.manual_seed(0)
+    base = dict(n_modalities=1, channel_dims=[3], num_spatial_axes=[3], out_dims=4, l_c=512, l_d=512,
+                fourier_encode_data=False)
+    base.update(kw)
+    return HealNet(**base).eval().cuda()
+
+
+def test_replication_invariance_full_volume():
+    """602 112 identical voxels (cfg 1 volume extent 12x224x224) == a single voxel."""
+    m = _m()
+    tok = torch.rand(2, 1, 1, 1, 3, device="cuda")
+    big = tok.expand(2, 12, 224, 224, 3).contiguous()
+    torch.testing.assert_close(m([big]), m([tok]), rtol=1e-3, atol=1e-4)
+
+
+def test_mask_equals_removal_and_permutation_full_wsi():
+    """cfg 4 WSI extent: 8192 tokens x 768 features (generic K/V projection path)."""
+    m = _m(channel_dims=[768], num_spatial_axes=[1], depth=1)
+    x = torch.rand(2, 8192, 768, device="cuda")
+    keep = torch.rand(2, 8192, device="cuda") > 0.5
+    keep[1] = keep[0]  # same kept count per sample so the removed version is rectangular
+    masked = m([x], mask=keep)
+    removed = m([x[:, keep[0]]])
+    torch.testing.assert_close(masked, removed, rtol=1e-3, atol=1e-4)
+    perm = torch.randperm(8192, device="cuda")
+    torch.testing.assert_close(m([x[:, perm]]), m([x]), rtol=1e-3, atol=1e-4)
+
+
+def test_batch_independence_cfg1_full_size():
+    """BASELINE config 1 shapes (tab 1x2000, img 224x224x3, vol 12x224x224x3, latent 512x512), batch 2 vs 1+1."""
+    torch.manual_seed(0)
+    m = HealNet(n_modalities=3, channel_dims=[2000, 3, 3], num_spatial_axes=[1, 2, 3], out_dims=4, l_c=512,
+                l_d=512).eval().cuda()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    xs = [torch.rand(2, 1, 2000, device="cuda", generator=g), torch.rand(2, 224, 224, 3, device="cuda", generator=g),
+          torch.rand(2, 12, 224, 224, 3, device="cuda", generator=g)]
+    full = m(xs)
+    assert bool(torch.isfinite(full).all())
+    for i in range(2):
+        torch.testing.assert_close(m([t[i:i + 1] for t in xs]), full[i:i + 1], rtol=1e-3, atol=1e-4)
