@@ -66,8 +66,8 @@ SIGNATURES = {
                                     c_int, c_void_p]),
     "hn_op_build_context": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, POINTER(c_int), c_int,
                                     c_float, c_int, c_void_p, c_void_p]),
-    "hn_op_attention_nsplit": (c_int, [c_int, c_int, c_int, c_long]),
-    "hn_op_attention": (c_int, [c_void_p, c_int, c_void_p, c_long, c_int, c_int, c_int, c_int, c_int, c_int,
+    "hn_op_attention_nsplit": (c_int, [c_int, c_int, c_int, c_long, c_int]),
+    "hn_op_attention": (c_int, [c_void_p, c_int, c_void_p, c_long, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                 c_long, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hn_op_combine": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
                               c_void_p, c_void_p, c_int, c_void_p]),

@@ -247,7 +247,8 @@ int plan_workspace(const hn_handle* h, int batch, const int* axis_sizes, const b
       qw = qw > d.x_heads * HP ? qw : d.x_heads * HP;
     }
     ow = ow > d.x_heads * HP ? ow : d.x_heads * HP;
-    mp.nsplit = attention_pick_nsplit(batch, L, d.x_heads, mp.N);
+    mp.nsplit = mp.small ? small_attention_pick_nsplit(batch, L, d.x_heads, mp.N, vd)
+                         : attention_pick_nsplit(batch, L, d.x_heads, mp.N);
     const size_t pa = static_cast<size_t>(batch) * mp.nsplit * d.x_heads * n_ltiles * 128 * vd;
     const size_t pm = static_cast<size_t>(batch) * mp.nsplit * d.x_heads * n_ltiles * 128 * 2;
     part_acc_elems = pa > part_acc_elems ? pa : part_acc_elems;
@@ -591,6 +592,7 @@ int hn_forward(hn_handle* h, int batch, const void* const* modality_ptrs, const 
           aa.kv_ld = mp.zw;
           aa.shared_kv = 1;
           aa.kd = mp.zw;
+          aa.c_ones = mp.C;
           rc = profile_begin(h, m, aa, st);
           if (rc != 0) return rc;
           HN_TRY(launch_attention(aa, st));
@@ -835,11 +837,15 @@ int hn_op_build_context(const float* raw, void* z, int ldz, int small, int batch
                               tab, fourier, st);
 }
 
-int hn_op_attention_nsplit(int batch, int L, int H, long N) { return attention_pick_nsplit(batch, L, H, N); }
+int hn_op_attention_nsplit(int batch, int L, int H, long N, int small_kd) {
+  if (small_kd > 0) return small_attention_pick_nsplit(batch, L, H, N, small_kd);
+  return attention_pick_nsplit(batch, L, H, N);
+}
 
 int hn_op_attention(const void* Q, int q_ld, const void* KV, long kv_ld, int k_col0, int v_col0, int shared_kv,
-                    int batch, int L, int H, long N, int nsplit, const uint8_t* mask, void* mask_bits_scratch,
-                    float* part_acc, float* part_ml, void* cuda_stream) {
+                    int c_ones, int batch, int L, int H, long N, int nsplit, const uint8_t* mask,
+                    void* mask_bits_scratch, float* part_acc, float* part_ml, void* cuda_stream) {
+  // shared_kv: 0 generic, 1 small-context kernel (xattn_small.cu), 2 first-generation small-context kernel
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   AttnArgs aa{};
   aa.Q = static_cast<const __half*>(Q);
@@ -849,6 +855,8 @@ int hn_op_attention(const void* Q, int q_ld, const void* KV, long kv_ld, int k_c
   aa.k_col0 = k_col0;
   aa.v_col0 = v_col0;
   aa.shared_kv = shared_kv ? 1 : 0;
+  aa.legacy_small = shared_kv == 2 ? 1 : 0;
+  aa.c_ones = c_ones;
   aa.kd = shared_kv ? static_cast<int>(kv_ld) : 64;
   aa.batch = batch;
   aa.L = L;

@@ -98,6 +98,8 @@ struct AttnArgs {
   // carry lo = fp16(x - hi) parts at these column offsets; S = Qh.Kh + Ql.Kh + Qh.Kl, U += P.Vh + P.Vl
   int precise = 0;
   int q_lo_off = 0, kv_lo_off = 0;
+  int c_ones = 0;        // shared_kv only: index of the 1.0 column of z (= context width C)
+  int legacy_small = 0;  // shared_kv only: run the first-generation kernel (xattn.cu) instead of xattn_small.cu
   int shared_kv;  // 1 = small-C path
   int kd;         // operand width per head: 64 generic; 32 or 64 (= z row width) on the small-C path
   int batch, L, H;
@@ -109,6 +111,9 @@ struct AttnArgs {
 };
 int launch_attention(const AttnArgs& a, cudaStream_t stream);
 int attention_pick_nsplit(int batch, int L, int H, long N);
+// small-context streaming kernel (xattn_small.cu): shared_kv path, one CTA per SM, several row blocks per CTA
+int launch_small_attention(const AttnArgs& a, cudaStream_t stream);
+int small_attention_pick_nsplit(int batch, int L, int H, long N, int kd);
 
 // combine split partials. generic: O[b*L][h*64+d] = sum_s w_s acc_s[d] / sum_s w_s l_s   (fp16, ld = o_ld)
 // (lo_seg > 0: O rows are split [hi | lo], lo at column + lo_seg)

@@ -368,7 +368,8 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
     HN_REQUIRE(a.kd == 32 || a.kd == 64, "attention: shared-context rows must be 32 or 64 wide");
     HN_REQUIRE(a.kv_ld == a.kd, "attention: shared-context rows must be dense");
     HN_REQUIRE(!a.precise, "attention: the precise mode exists on the generic path only");
-    return a.kd == 32 ? launch_t<32, true, false>(a, stream) : launch_t<64, true, false>(a, stream);
+    if (a.legacy_small) return a.kd == 32 ? launch_t<32, true, false>(a, stream) : launch_t<64, true, false>(a, stream);
+    return launch_small_attention(a, stream);
   }
   if (a.precise) {
     HN_REQUIRE(a.q_lo_off > 0 && a.kv_lo_off > 0, "attention: precise mode needs the lo-part offsets");

@@ -1,0 +1,462 @@
+// xattn_small.cu — the hot kernel of the path: streaming softmax attention of the latent array against a LONG
+// token axis of NARROW context rows (image pixels / volume voxels: C = channels + Fourier features <= 63).
+//
+// Replaces  sim = q k^T * dh^-0.5 ; attn = softmax(sim / 0.5) ; out = attn v   (healnet.py:409-424) for such
+// modalities in the reassociated form (see xattn.cu): with LN(c) = gamma*z + beta,
+//     q.k_t = Q'.z_t + const,   Q' = (Wk' ^T q) (KD = 32 | 64 wide),    sum_t p_t v_t = Wv' (sum_t p_t z_t) + Wv beta
+// so ONE 64-token x KD tile of standardised context z is K and V of every head and latent tile. Column C of z
+// is 1.0, so accumulator column C is the softmax denominator.
+//
+// The kernel is bound by the softmax exponentials (H*L*N per pass; MUFU.EX2 = 16/clk/SM measured), not by the
+// tensor pipe, so it is organised around keeping the MUFU *and* FMA pipes of all four SM sub-partitions busy:
+//   * one CTA per SM owns G = 3 (KD 32) / 2 (KD 64) "row blocks" (128 latent rows of one head) that stream the
+//     SAME z tiles: 4 softmax warps per row block -> 12 softmax warps per SM, 3 per scheduler, so that one
+//     group's TMEM / mbarrier latency is covered by the others; the z tile is fetched once per G row blocks;
+//   * S is double-buffered in TMEM (P(i) is written over the first half of S(i), which frees the columns for a
+//     second S buffer): S(i+1) is complete long before the softmax of tile i ends, so no tensor-pipe latency
+//     sits on the critical path;
+//   * softmax threads own one latent row (one TMEM lane) and work in 32-column chunks (S -> P in place of
+//     registers, ~80 regs/thread);
+//   * a third of the exponentials are evaluated on the FMA pipe (Cody-Waite range reduction + degree-3 minimax
+//     polynomial, rel. error 7.5e-5 < fp16 rounding of P) so MUFU only sees the other two thirds (measured
+//     pipe mix: 23 elem/clk/SM vs 16 for MUFU alone, tools/microbench/mb_pipes.cu);
+//   * the running max is a lazily raised reference: the steady state does no max pass at all — it only tracks
+//     the max of the packed fp16 P words (VIMNMX3.U16x2, a quarter of an instruction per element) and falls
+//     back to the exact two-pass path when a P exceeds 2^8 (or on the first / a masked / the ragged last tile);
+//   * the "- max" of the softmax costs nothing: Q' carries -m_ref (fp16) in the column where z holds its 1.0,
+//     so the S UMMA delivers q.z - m_ref directly; the owning thread rewrites that smem element on the rare raise.
+// Warp roles: warps 0..4G-1 = softmax groups (4 warps each); warps 4G..5G-1 = one UMMA issuer warp per group
+// (S = Q'.z^T (SS) ; U += P.z (TS, P from TMEM)), each blocking on its own group's barrier — a single issuer
+// polling several groups' mbarriers (~150 clk per test) starved the groups, and letting a softmax warp issue
+// stretched that warp's tile and with it the whole group's; last warp = TMA producer (Q' tiles once, z tiles
+// through an 8-stage mbarrier ring). TMEM per group: S/P buffer 0 (64) | S/P buffer 1 (64) | U (KD).
+#include "common.cuh"
+#include "tc05.cuh"
+
+namespace hn {
+namespace {
+using namespace tc05;
+
+constexpr int BM = 128;  // latent rows per row block
+constexpr int BT = 64;   // tokens per tile
+constexpr int NST = 8;   // z ring depth
+constexpr int MAXG = 4;
+constexpr uint32_t P_RAISE_BITS = 0x5C00u;  // fp16(256): a larger P triggers the exact path (raises the reference max)
+constexpr float RESCALE_THRESHOLD = 8.f;    // log2 units, = log2(256)
+
+struct SmallDev {
+  int L, H, batch, nsplit, n_ltiles, n_rb;  // n_rb = H * n_ltiles row blocks per (sample, split)
+  int ctas_per_stream;                       // ceil(n_rb / G)
+  int tiles_total;
+  int c_ones;  // column of z that is 1.0 (= context width C): Q' carries -m_ref there
+  long N;
+  const uint64_t* mask_bits;
+  float* part_acc;
+  float* part_ml;
+};
+
+__device__ __forceinline__ float ex2_mufu(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// 2^x on the FMA / ALU pipes: n = rint(x) via the 1.5*2^23 trick, degree-3 minimax of 2^f on [-0.5, 0.5],
+// exponent inserted with one integer multiply-add. x <= 16 here; x below -125 (masked: -inf) clamps to ~0.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;
+  const float f = x - (t - 12582912.f);
+  float p = 0.05517167f;
+  p = fmaf(p, f, 0.24261112f);
+  p = fmaf(p, f, 0.69326099f);
+  p = fmaf(p, f, 0.99992807f);
+  return __int_as_float(__float_as_int(t) * 8388608 + __float_as_int(p));
+}
+__device__ __forceinline__ uint32_t vmaxu2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("max.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+// element j of a 32-column chunk goes to the FMA-pipe polynomial when POLY(j); ~1/3 of the elements, spread so
+// that every packed pair mixes the two pipes
+__device__ __forceinline__ constexpr bool poly_slot(int j) { return (j % 3) == 1; }
+
+// byte offset of element (row, col) inside a TMA-swizzled [rows][KD] fp16 tile (64-byte rows -> SWIZZLE_64B,
+// 128-byte rows -> SWIZZLE_128B): the 16-byte chunk index is XORed with the low bits of (row-pair | row)
+template <int KD>
+__device__ __forceinline__ uint32_t swizzled_off(int row, int col) {
+  const uint32_t chunk = static_cast<uint32_t>(col * 2) >> 4, within = static_cast<uint32_t>(col * 2) & 15u;
+  if (KD == 32) return row * 64 + ((chunk ^ ((static_cast<uint32_t>(row) >> 1) & 3u)) << 4) + within;
+  return row * 128 + ((chunk ^ (static_cast<uint32_t>(row) & 7u)) << 4) + within;
+}
+
+template <int KD, int G>
+__global__ void __launch_bounds__((5 * G + 1) * 32, 1)
+attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmZ, SmallDev p) {
+  constexpr int VD = KD;
+  constexpr int Q_TILE = BM * KD * 2;
+  constexpr int Z_BYTES = BT * KD * 2;
+  constexpr uint32_t LAYOUT = (KD == 64) ? SWZ_128B : SWZ_64B;
+  constexpr uint32_t SBO = 8 * KD * 2;
+  constexpr uint32_t V_KADV = 16 * VD * 2;
+  constexpr int GCOLS = 2 * 64 + VD;  // S/P buffer 0 | S/P buffer 1 | U   (P(i) overwrites the first 32 columns of S(i))
+  static_assert(G * GCOLS <= 512, "TMEM budget");
+  constexpr uint32_t idesc_s = idesc_f16(BM, BT, false, false);  // S[128x64]  = Q'[128xKD] . z[64xKD]^T
+  constexpr uint32_t idesc_u = idesc_f16(BM, VD, false, true);   // U[128xVD] += P[128x64] . z[64xVD] (MN-major B)
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sZ = smem + G * Q_TILE;
+  __shared__ uint64_t q_full, z_full[NST], z_empty[NST];
+  __shared__ uint64_t s_full[MAXG][2], p_ready[MAXG], u_done[MAXG], acc_done[MAXG];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int idx = blockIdx.x;
+  const int cta_rb = idx % p.ctas_per_stream;
+  idx /= p.ctas_per_stream;
+  const int b = idx % p.batch;
+  const int split = idx / p.batch;
+  const int rb0 = cta_rb * G;
+  const int n_active = (p.n_rb - rb0) < G ? (p.n_rb - rb0) : G;
+  const int t_begin = static_cast<int>(static_cast<long>(p.tiles_total) * split / p.nsplit);
+  const int t_end = static_cast<int>(static_cast<long>(p.tiles_total) * (split + 1) / p.nsplit);
+  const int n = t_end - t_begin;
+
+  if (n <= 0) {  // more splits than tiles: publish empty partials
+    for (int g = 0; g < n_active; ++g) {
+      const int rb = rb0 + g, h = rb / p.n_ltiles, lt = rb % p.n_ltiles;
+      const long row0 = ((static_cast<long>(b) * p.nsplit + split) * p.H + h) * p.L + lt * BM;
+      for (int r = threadIdx.x; r < BM; r += blockDim.x) {
+        if (lt * BM + r < p.L) {
+          float* acc = p.part_acc + (row0 + r) * VD;
+          for (int c = 0; c < VD; ++c) acc[c] = 0.f;
+          p.part_ml[(row0 + r) * 2] = -INFINITY;
+          p.part_ml[(row0 + r) * 2 + 1] = 0.f;
+        }
+      }
+    }
+    return;
+  }
+
+  if (threadIdx.x == 0) {
+    mbar_init(&q_full, 1);
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(&z_full[s], 1);
+      mbar_init(&z_empty[s], n_active);
+    }
+    for (int g = 0; g < MAXG; ++g) {
+      mbar_init(&s_full[g][0], 1);
+      mbar_init(&s_full[g][1], 1);
+      mbar_init(&p_ready[g], 4);
+      mbar_init(&u_done[g], 1);
+      mbar_init(&acc_done[g], 1);
+    }
+    fence_mbar_init();
+  }
+  constexpr int PRODUCER_WARP = 5 * G;
+  if (warp == PRODUCER_WARP) tmem_alloc<512>(&tmem_base_s);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == PRODUCER_WARP) {
+    // ------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmZ);
+      mbar_arrive_expect_tx(&q_full, n_active * Q_TILE);
+      for (int g = 0; g < n_active; ++g) {
+        const int rb = rb0 + g, h = rb / p.n_ltiles, lt = rb % p.n_ltiles;
+        tma_load_3d(sQ + g * Q_TILE, &tmQ, &q_full, h * KD, lt * BM, b);
+      }
+      for (int i = 0; i < n; ++i) {
+        const int s = i % NST;
+        mbar_wait(&z_empty[s], ((i / NST) & 1) ^ 1);
+        mbar_arrive_expect_tx(&z_full[s], Z_BYTES);
+        tma_load_3d(sZ + s * Z_BYTES, &tmZ, &z_full[s], 0, (t_begin + i) * BT, b);
+      }
+    }
+  } else if (warp >= 4 * G) {
+    // ------------------------------------------------------------ UMMA issuers: one warp (one elected thread) per
+    // group, each on its own scheduler. Once all four softmax warps have published P(i) the thread issues PV(i)
+    // and, right behind it, S(i+2) into the buffer P(i) occupied — so S(i+1) is always complete before the
+    // softmax needs it and no tensor-pipe or issue latency sits on the softmax warps' critical path.
+    const int g = warp - 4 * G;
+    if (g < n_active && elect_one()) {
+      const uint32_t tG = tmem + g * GCOLS;
+      const uint32_t q0 = smem_u32(sQ + g * Q_TILE);
+      auto issue_s = [&](int i) {
+        const int s = i % NST;
+        mbar_wait(&z_full[s], (i / NST) & 1);
+        fence_after_sync();
+        const uint32_t z0 = smem_u32(sZ + s * Z_BYTES);
+#pragma unroll
+        for (int k = 0; k < KD / 16; ++k)
+          umma_ss(tG + (i & 1) * 64, smem_desc(q0 + k * 32, 16, SBO, LAYOUT), smem_desc(z0 + k * 32, 16, SBO, LAYOUT),
+                  idesc_s, k != 0);
+        umma_commit(&s_full[g][i & 1]);
+      };
+      mbar_wait(&q_full, 0);
+      issue_s(0);
+      if (n > 1) issue_s(1);
+      for (int i = 0; i < n; ++i) {
+        mbar_wait(&p_ready[g], i & 1);  // all four warps: S(i) consumed, P(i) in TMEM, Q' fold up to date
+        fence_after_sync();
+        const int s = i % NST;
+        const uint32_t z0 = smem_u32(sZ + s * Z_BYTES);
+#pragma unroll
+        for (int k = 0; k < BT / 16; ++k)
+          umma_ts(tG + 128, tG + (i & 1) * 64 + k * 8, smem_desc(z0 + k * V_KADV, 16, SBO, LAYOUT), idesc_u,
+                  (i | k) != 0);
+        umma_commit(&z_empty[s]);
+        umma_commit(&u_done[g]);
+        if (i + 2 < n) issue_s(i + 2);
+        if (i + 1 == n) umma_commit(&acc_done[g]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ softmax groups: thread = latent row
+    const int g = warp >> 2;
+    if (g < n_active) {
+      const int rb = rb0 + g, h = rb / p.n_ltiles, lt = rb % p.n_ltiles;
+      const uint32_t lane_base = (warp & 3) * 32;
+      const int trow = lane_base + lane;  // row inside the 128-row block
+      const int row = lt * BM + trow;
+      const long part_row = ((static_cast<long>(b) * p.nsplit + split) * p.H + h) * p.L + row;
+      const uint32_t tG = tmem + g * GCOLS;  // group columns (lane field 0)
+      const uint32_t tL = tmem_addr(tG, lane_base, 0);
+      const uint32_t tU = tL + 128;
+      uint8_t* qrow_fold = sQ + g * Q_TILE;  // Q'[trow][C_ones] holds -m_ref (fp16): the UMMA subtracts the max for us
+      float m_ref = -INFINITY;  // reference max (log2 units), always exactly representable in fp16
+      float m_in0 = 0.f, m_in1 = 0.f;  // offset baked into S buffer 0 / 1 by the fold (0: none)
+
+      // tiles [0, n_full) of this CTA's range are complete 64-token tiles; only the globally last tile can be ragged
+      const int n_full = (t_end == p.tiles_total && (p.N % BT) != 0) ? n - 1 : n;
+      const bool has_mask = p.mask_bits != nullptr;
+      int stale = 0;  // warp-uniform: > 0 while the S buffer about to be read was computed before the last raise
+
+      for (int i = 0; i < n; ++i) {
+        const int buf = i & 1;
+        const uint32_t tS = tL + buf * 64;
+
+        mbar_wait(&s_full[g][buf], (i >> 1) & 1);
+        fence_after_sync();
+
+        // steady state needs: a full unmasked tile whose folded offset is the current reference (all warp-uniform)
+        bool exact = has_mask || i >= n_full || i == 0 || stale > 0;
+        stale = 0;
+        uint32_t pk[32];  // P(i) as packed fp16 pairs; stored over S columns 0..31 once the whole row is known good
+        if (!exact) {
+          // ---------------- steady state: P = 2^S chunk by chunk; no max pass, no subtraction, no mask
+          uint32_t pmax = 0;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t s[32];
+            tmem_ld32(tS + c * 32, s);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float x0 = __uint_as_float(s[2 * j]), x1 = __uint_as_float(s[2 * j + 1]);
+              const float e0 = poly_slot(2 * j) ? ex2_poly(x0) : ex2_mufu(x0);
+              const float e1 = poly_slot(2 * j + 1) ? ex2_poly(x1) : ex2_mufu(x1);
+              pk[c * 16 + j] = pack_half2(e0, e1);
+              pmax = vmaxu2(pmax, pk[c * 16 + j]);
+            }
+          }
+          const bool big = ((pmax & 0xFFFFu) > P_RAISE_BITS) || ((pmax >> 16) > P_RAISE_BITS);
+          exact = __any_sync(0xffffffffu, big);  // some P above 2^8 (or inf / garbage): redo with a raised reference
+        }
+        if (exact) {
+          // ---------------- exact path (first tiles, masked / ragged tile, stale fold, or the reference max has
+          // to be raised): max pass, rescale, exp pass. TMEM holds s - m_in (nothing has been overwritten yet).
+          const int tile = t_begin + i;
+          uint64_t bits = ~0ull;
+          if (has_mask) bits = p.mask_bits[static_cast<long>(b) * p.tiles_total + tile];
+          const long rem = p.N - static_cast<long>(tile) * BT;
+          if (rem < BT) bits &= (1ull << rem) - 1ull;
+          const float m_in = buf ? m_in1 : m_in0;
+          float mx = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t s[32];
+            tmem_ld32(tS + c * 32, s);
+            tmem_wait_ld();
+            const uint32_t mb = static_cast<uint32_t>(bits >> (32 * c));
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const float a = ((mb >> j) & 1u) ? __uint_as_float(s[j]) : -INFINITY;
+              const float bb = ((mb >> (j + 1)) & 1u) ? __uint_as_float(s[j + 1]) : -INFINITY;
+              mx = fmax3(mx, a, bb);
+            }
+          }
+          mx += m_in;  // true row max of this tile (-inf stays -inf)
+          // raise lazily: keep the reference while the tile stays within 2^8 of it
+          const bool raise = __any_sync(0xffffffffu, mx > m_ref + RESCALE_THRESHOLD);
+          if (raise) {
+            // round the new reference to fp16 so that the folded offset IS the reference
+            const float m_new = fmaxf(m_ref, __half2float(__float2half_rn(mx)));
+            if (i > 0) {
+              mbar_wait(&u_done[g], (i - 1) & 1);  // PV(i-1) landed; PV(i) cannot start before our p_ready arrive
+              fence_after_sync();
+              const float sc = (m_new == -INFINITY || m_ref == m_new) ? 1.f : ex2_mufu(m_ref - m_new);
+              if (__any_sync(0xffffffffu, sc != 1.f)) {
+#pragma unroll
+                for (int c = 0; c < VD; c += 32) {
+                  uint32_t u[32];
+                  tmem_ld32(tU + c, u);
+                  tmem_wait_ld();
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) u[j] = __float_as_uint(__uint_as_float(u[j]) * sc);
+                  tmem_st32(tU + c, u);
+                }
+              }
+            }
+            // S(i+1) may still be reading Q': wait for it before changing the folded offset
+            if (i + 1 < n) mbar_wait(&s_full[g][buf ^ 1], ((i + 1) >> 1) & 1);
+            m_ref = m_new;
+            const float fold = (m_ref == -INFINITY) ? 0.f : -m_ref;
+            *reinterpret_cast<__half*>(qrow_fold + swizzled_off<KD>(trow, p.c_ones)) = __float2half_rn(fold);
+            fence_proxy_async_smem();
+            stale = 1;  // S(i+1) was computed with the previous offset
+          }
+          const float delta = m_in - ((m_ref == -INFINITY) ? 0.f : m_ref);
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t s[32];
+            tmem_ld32(tS + c * 32, s);
+            tmem_wait_ld();
+            const uint32_t mb = static_cast<uint32_t>(bits >> (32 * c));
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float a = ((mb >> (2 * j)) & 1u) ? __uint_as_float(s[2 * j]) : -INFINITY;
+              const float bb = ((mb >> (2 * j + 1)) & 1u) ? __uint_as_float(s[2 * j + 1]) : -INFINITY;
+              pk[c * 16 + j] = pack_half2(ex2_mufu(a + delta), ex2_mufu(bb + delta));
+            }
+          }
+        }
+        tmem_st32(tS, pk);  // P(i) over S columns 0..31 (this thread has read all 64 of them)
+        tmem_wait_st();
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) {
+          // a warp may run one tile ahead of its group (S is double-buffered) but must not arrive twice in one
+          // barrier phase: phase i-1 has to be complete before the arrival for tile i
+          if (i > 0) mbar_wait(&p_ready[g], (i - 1) & 1);
+          mbar_arrive(&p_ready[g]);
+        }
+        __syncwarp();
+        if (exact) {  // the buffer S(i+2) will land in carries the current reference
+          if (buf) m_in1 = (m_ref == -INFINITY) ? 0.f : m_ref; else m_in0 = (m_ref == -INFINITY) ? 0.f : m_ref;
+        }
+      }
+      // ---- epilogue: un-normalised accumulator rows + reference max
+      mbar_wait(&acc_done[g], 0);
+      fence_after_sync();
+#pragma unroll
+      for (int c = 0; c < VD; c += 32) {
+        uint32_t u[32];
+        tmem_ld32(tU + c, u);
+        tmem_wait_ld();
+        if (row < p.L) {
+          float4* dst = reinterpret_cast<float4*>(p.part_acc + part_row * VD + c);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            dst[j] = make_float4(__uint_as_float(u[4 * j]), __uint_as_float(u[4 * j + 1]),
+                                 __uint_as_float(u[4 * j + 2]), __uint_as_float(u[4 * j + 3]));
+        }
+        __syncwarp();
+      }
+      if (row < p.L) {
+        float2* ml = reinterpret_cast<float2*>(p.part_ml + part_row * 2);
+        *ml = make_float2(m_ref, 0.f);
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == PRODUCER_WARP) tmem_dealloc<512>(tmem);
+}
+
+template <int KD, int G>
+int launch_small_t(const AttnArgs& a, cudaStream_t stream) {
+  CUtensorMap tmQ, tmZ;
+  const CUtensorMapSwizzle swz = KD == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  if (!make_tmap_3d_f16(&tmQ, a.Q, a.batch, a.L, a.q_ld, static_cast<uint64_t>(a.q_ld) * 2,
+                        static_cast<uint64_t>(a.L) * a.q_ld * 2, BM, KD, swz) ||
+      !make_tmap_3d_f16(&tmZ, a.KV, a.batch, a.N, a.kv_ld, static_cast<uint64_t>(a.kv_ld) * 2,
+                        static_cast<uint64_t>(a.N) * a.kv_ld * 2, BT, KD, swz)) {
+    set_error("attention: cuTensorMapEncodeTiled failed");
+    return -2;
+  }
+  SmallDev p;
+  p.L = a.L;
+  p.H = a.H;
+  p.batch = a.batch;
+  p.nsplit = a.nsplit;
+  p.n_ltiles = (a.L + BM - 1) / BM;
+  p.n_rb = p.n_ltiles * a.H;
+  p.ctas_per_stream = (p.n_rb + G - 1) / G;
+  p.tiles_total = static_cast<int>((a.N + BT - 1) / BT);
+  p.N = a.N;
+  p.c_ones = a.c_ones;
+  p.mask_bits = a.mask_bits;
+  p.part_acc = a.part_acc;
+  p.part_ml = a.part_ml;
+  // at least 120 KB so that a second CTA can never share the SM (each CTA allocates all 512 TMEM columns)
+  constexpr int SMEM_NEED = G * BM * KD * 2 + NST * BT * KD * 2 + 1024;
+  constexpr int SMEM = SMEM_NEED > 120 * 1024 ? SMEM_NEED : 120 * 1024;
+  HN_CHECK_CUDA(cudaFuncSetAttribute(attn_small_kernel<KD, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+  const long grid = static_cast<long>(p.ctas_per_stream) * a.batch * a.nsplit;
+  HN_REQUIRE(grid > 0 && grid < 2147483647L, "attention: grid too large");
+  attn_small_kernel<KD, G><<<static_cast<unsigned>(grid), (5 * G + 1) * 32, SMEM, stream>>>(tmQ, tmZ, p);
+  HN_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+}  // namespace
+
+int small_attention_groups(int kd) { return kd == 32 ? 3 : 2; }
+
+// Split the token axis so that the grid is a whole number of waves of one CTA per SM while each CTA still
+// streams enough tiles to amortise its prologue / epilogue.
+int small_attention_pick_nsplit(int batch, int L, int H, long N, int kd) {
+  const int G = small_attention_groups(kd);
+  const long n_rb = static_cast<long>((L + BM - 1) / BM) * H;
+  const long base = ((n_rb + G - 1) / G) * batch;
+  const long tiles = (N + BT - 1) / BT;
+  const long slots = 148;
+  if (tiles <= 16) return 1;
+  long best = 1;
+  double best_cost = 1e30;
+  const long max_split = tiles / 16 > 0 ? tiles / 16 : 1;
+  for (long s = 1; s <= max_split && s <= 1024; ++s) {
+    const long ctas = base * s;
+    const long waves = (ctas + slots - 1) / slots;
+    const long per = (tiles + s - 1) / s;
+    const double cost = static_cast<double>(waves) * (per + 8.0);
+    if (cost < best_cost * 0.999) {
+      best_cost = cost;
+      best = s;
+    }
+  }
+  return static_cast<int>(best);
+}
+
+int launch_small_attention(const AttnArgs& a, cudaStream_t stream) {
+  HN_REQUIRE(a.batch > 0 && a.L > 0 && a.H > 0 && a.N > 0 && a.nsplit > 0, "attention: empty problem");
+  HN_REQUIRE(a.kd == 32 || a.kd == 64, "attention: shared-context rows must be 32 or 64 wide");
+  HN_REQUIRE(a.kv_ld == a.kd, "attention: shared-context rows must be dense");
+  HN_REQUIRE(a.q_ld % 8 == 0, "attention: row pitches must be multiples of 8 elements");
+  HN_REQUIRE(a.N < (1L << 31), "attention: token axis too long");
+  HN_REQUIRE(a.c_ones >= 1 && a.c_ones < a.kd, "attention: ones column must lie inside the context row");
+  return a.kd == 32 ? launch_small_t<32, 3>(a, stream) : launch_small_t<64, 2>(a, stream);
+}
+
+}  // namespace hn

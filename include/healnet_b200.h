@@ -136,12 +136,14 @@ HN_API int hn_op_layernorm_f16(const float* x, int ldx, const float* gamma, cons
 HN_API int hn_op_build_context(const float* raw, void* z, int ldz, int small, int batch, int c_raw, int n_axes,
                         const int* axis_sizes, int n_bands, float max_freq, int fourier, float* tab,
                         void* cuda_stream);
-HN_API int hn_op_attention_nsplit(int batch, int L, int H, long N);
+/* token-axis split count the library would choose; small_kd = 32 | 64 for the small-context kernel, 0 generic */
+HN_API int hn_op_attention_nsplit(int batch, int L, int H, long N, int small_kd);
 /* Streaming attention partials + combine. shared_kv != 0: small-C path (Q rows kv_ld = 32 | 64 wide per head,
- * KV = z rows); part_acc rows are kv_ld (small-C) or 64 (generic) floats wide. */
+ * KV = z rows whose column c_ones is 1.0; Q column c_ones must be 0); part_acc rows are kv_ld (small-C) or 64
+ * (generic) floats wide. */
 HN_API int hn_op_attention(const void* Q, int q_ld, const void* KV, long kv_ld, int k_col0, int v_col0, int shared_kv,
-                    int batch, int L, int H, long N, int nsplit, const uint8_t* mask, void* mask_bits_scratch,
-                    float* part_acc, float* part_ml, void* cuda_stream);
+                           int c_ones, int batch, int L, int H, long N, int nsplit, const uint8_t* mask,
+                           void* mask_bits_scratch, float* part_acc, float* part_ml, void* cuda_stream);
 HN_API int hn_op_combine(const float* part_acc, const float* part_ml, int batch, int nsplit, int H, int L, int small_C,
                   int zw, int dh, const float* Wv, const float* bv, void* O, int o_ld, void* cuda_stream);
 /* test-only: one-tile UMMA/TMA/TMEM convention probe (probe.cu) */

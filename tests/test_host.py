@@ -128,7 +128,11 @@ def test_hn_create_validation_and_workspace_sizing():
 def test_attention_split_heuristic_covers_the_chip():
     lib = healnet_b200.load_library()
     # cfg 1 volume modality: 4 samples x 8 heads x 4 latent tiles = 128 base CTAs -> must split the token axis
-    ns = lib.hn_op_attention_nsplit(4, 512, 8, 602112)
+    ns = lib.hn_op_attention_nsplit(4, 512, 8, 602112, 0)
     assert ns >= 2 and 4 * 8 * 4 * ns >= 2 * 148
-    assert lib.hn_op_attention_nsplit(4, 512, 8, 1) == 1
-    assert lib.hn_op_attention_nsplit(1, 25, 1, 64 * 16) == 1
+    assert lib.hn_op_attention_nsplit(4, 512, 8, 1, 0) == 1
+    assert lib.hn_op_attention_nsplit(1, 25, 1, 64 * 16, 0) == 1
+    # small-context kernel: one CTA per SM, 3 row blocks per CTA -> 4 * ceil(32 / 3) * ns CTAs, close to whole waves
+    ns = lib.hn_op_attention_nsplit(4, 512, 8, 602112, 32)
+    ctas = 4 * 11 * ns
+    assert ns >= 3 and ctas >= 148 and (ctas % 148 == 0 or ctas % 148 >= 110)
