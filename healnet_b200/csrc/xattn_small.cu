@@ -17,9 +17,9 @@
 //     sits on the critical path;
 //   * softmax threads own one latent row (one TMEM lane) and work in 32-column chunks (S -> P in place of
 //     registers, ~80 regs/thread);
-//   * a third of the exponentials are evaluated on the FMA pipe (Cody-Waite range reduction + degree-3 minimax
-//     polynomial, rel. error 7.5e-5 < fp16 rounding of P) so MUFU only sees the other two thirds (measured
-//     pipe mix: 23 elem/clk/SM vs 16 for MUFU alone, tools/microbench/mb_pipes.cu);
+//   * a quarter of the exponentials are evaluated on the FMA pipe (Cody-Waite range reduction + degree-3 minimax
+//     polynomial, rel. error 7.5e-5 < fp16 rounding of P) so MUFU only sees the rest (pipe microbenchmark:
+//     23 elem/clk/SM for a 3/8 mix vs 16 for MUFU alone, tools/microbench/mb_pipes.cu; in this kernel 1/4 measured best);
 //   * the running max is a lazily raised reference: the steady state does no max pass at all — it only tracks
 //     the max of the packed fp16 P words (VIMNMX3.U16x2, a quarter of an instruction per element) and falls
 //     back to the exact two-pass path when a P exceeds 2^8 (or on the first / a masked / the ragged last tile);
@@ -30,6 +30,8 @@
 // polling several groups' mbarriers (~150 clk per test) starved the groups, and letting a softmax warp issue
 // stretched that warp's tile and with it the whole group's; last warp = TMA producer (Q' tiles once, z tiles
 // through an 8-stage mbarrier ring). TMEM per group: S/P buffer 0 (64) | S/P buffer 1 (64) | U (KD).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "tc05.cuh"
 
@@ -84,7 +86,18 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 }
 // element j of a 32-column chunk goes to the FMA-pipe polynomial when POLY(j); ~1/3 of the elements, spread so
 // that every packed pair mixes the two pipes
-__device__ __forceinline__ constexpr bool poly_slot(int j) { return (j % 3) == 1; }
+// PMODE: 0 = none (all MUFU), 1 = 1/4, 2 = 1/3, 3 = 3/8, 4 = 1/2
+template <int PMODE>
+__device__ __forceinline__ constexpr bool poly_slot(int j) {
+  return PMODE == 0 ? false
+         : PMODE == 1 ? (j % 4) == 1
+         : PMODE == 2 ? (j % 3) == 1
+         : PMODE == 3 ? ((j % 8) == 1 || (j % 8) == 4 || (j % 8) == 6)
+                      : (j % 2) == 1;
+}
+__device__ __forceinline__ void mbar_wait_sleepy(uint64_t* bar, uint32_t parity, unsigned ns) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(ns);  // waiter off the critical path: do not burn issue slots
+}
 
 // byte offset of element (row, col) inside a TMA-swizzled [rows][KD] fp16 tile (64-byte rows -> SWIZZLE_64B,
 // 128-byte rows -> SWIZZLE_128B): the 16-byte chunk index is XORed with the low bits of (row-pair | row)
@@ -95,7 +108,7 @@ __device__ __forceinline__ uint32_t swizzled_off(int row, int col) {
   return row * 128 + ((chunk ^ (static_cast<uint32_t>(row) & 7u)) << 4) + within;
 }
 
-template <int KD, int G>
+template <int KD, int G, int PMODE>
 __global__ void __launch_bounds__((5 * G + 1) * 32, 1)
 attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmZ, SmallDev p) {
   constexpr int VD = KD;
@@ -179,7 +192,7 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
       for (int i = 0; i < n; ++i) {
         const int s = i % NST;
-        mbar_wait(&z_empty[s], ((i / NST) & 1) ^ 1);
+        mbar_wait_sleepy(&z_empty[s], ((i / NST) & 1) ^ 1, 200);
         mbar_arrive_expect_tx(&z_full[s], Z_BYTES);
         tma_load_3d(sZ + s * Z_BYTES, &tmZ, &z_full[s], 0, (t_begin + i) * BT, b);
       }
@@ -208,7 +221,7 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       issue_s(0);
       if (n > 1) issue_s(1);
       for (int i = 0; i < n; ++i) {
-        mbar_wait(&p_ready[g], i & 1);  // all four warps: S(i) consumed, P(i) in TMEM, Q' fold up to date
+        mbar_wait_sleepy(&p_ready[g], i & 1, 100);  // all four warps: S(i) consumed, P(i) in TMEM, Q' fold up to date
         fence_after_sync();
         const int s = i % NST;
         const uint32_t z0 = smem_u32(sZ + s * Z_BYTES);
@@ -265,8 +278,8 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float x0 = __uint_as_float(s[2 * j]), x1 = __uint_as_float(s[2 * j + 1]);
-              const float e0 = poly_slot(2 * j) ? ex2_poly(x0) : ex2_mufu(x0);
-              const float e1 = poly_slot(2 * j + 1) ? ex2_poly(x1) : ex2_mufu(x1);
+              const float e0 = poly_slot<PMODE>(2 * j) ? ex2_poly(x0) : ex2_mufu(x0);
+              const float e1 = poly_slot<PMODE>(2 * j + 1) ? ex2_poly(x1) : ex2_mufu(x1);
               pk[c * 16 + j] = pack_half2(e0, e1);
               pmax = vmaxu2(pmax, pk[c * 16 + j]);
             }
@@ -385,7 +398,7 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   if (warp == PRODUCER_WARP) tmem_dealloc<512>(tmem);
 }
 
-template <int KD, int G>
+template <int KD, int G, int PMODE>
 int launch_small_t(const AttnArgs& a, cudaStream_t stream) {
   CUtensorMap tmQ, tmZ;
   const CUtensorMapSwizzle swz = KD == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -413,10 +426,11 @@ int launch_small_t(const AttnArgs& a, cudaStream_t stream) {
   // at least 120 KB so that a second CTA can never share the SM (each CTA allocates all 512 TMEM columns)
   constexpr int SMEM_NEED = G * BM * KD * 2 + NST * BT * KD * 2 + 1024;
   constexpr int SMEM = SMEM_NEED > 120 * 1024 ? SMEM_NEED : 120 * 1024;
-  HN_CHECK_CUDA(cudaFuncSetAttribute(attn_small_kernel<KD, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+  HN_CHECK_CUDA(
+      cudaFuncSetAttribute(attn_small_kernel<KD, G, PMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
   const long grid = static_cast<long>(p.ctas_per_stream) * a.batch * a.nsplit;
   HN_REQUIRE(grid > 0 && grid < 2147483647L, "attention: grid too large");
-  attn_small_kernel<KD, G><<<static_cast<unsigned>(grid), (5 * G + 1) * 32, SMEM, stream>>>(tmQ, tmZ, p);
+  attn_small_kernel<KD, G, PMODE><<<static_cast<unsigned>(grid), (5 * G + 1) * 32, SMEM, stream>>>(tmQ, tmZ, p);
   HN_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -456,7 +470,19 @@ int launch_small_attention(const AttnArgs& a, cudaStream_t stream) {
   HN_REQUIRE(a.q_ld % 8 == 0, "attention: row pitches must be multiples of 8 elements");
   HN_REQUIRE(a.N < (1L << 31), "attention: token axis too long");
   HN_REQUIRE(a.c_ones >= 1 && a.c_ones < a.kd, "attention: ones column must lie inside the context row");
-  return a.kd == 32 ? launch_small_t<32, 3>(a, stream) : launch_small_t<64, 2>(a, stream);
+  if (a.kd == 64) return launch_small_t<64, 2, 1>(a, stream);
+  static int pmode = -1;  // tuning knob (HN_POLY_MODE=0..4); default 1/4 of the exponentials on the FMA pipe (measured best)
+  if (pmode < 0) {
+    const char* e = getenv("HN_POLY_MODE");
+    pmode = (e != nullptr && e[0] >= '0' && e[0] <= '4') ? e[0] - '0' : 1;
+  }
+  switch (pmode) {
+    case 0: return launch_small_t<32, 3, 0>(a, stream);
+    case 2: return launch_small_t<32, 3, 2>(a, stream);
+    case 3: return launch_small_t<32, 3, 3>(a, stream);
+    case 4: return launch_small_t<32, 3, 4>(a, stream);
+    default: return launch_small_t<32, 3, 1>(a, stream);
+  }
 }
 
 }  // namespace hn
