@@ -46,6 +46,15 @@ WORKLOADS = {
 METRIC = "HealNet forward samples/sec (3-modality, latent 512x512)"
 
 
+def load_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "r1_attn_small_kernel_summary.json")
+    try:
+        return float(json.load(open(p))["dram_bytes_per_launch"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -292,8 +301,10 @@ def run_gpu_arm(args):
                      h2d_bytes_per_step=sum(t.numel() * 4 for t in host), d2h_bytes_per_step=out_h.numel() * 4),
             gpu_launches=launches,
             roofline=dict(bound="tensor", achieved=achieved, peak=peaks["tflops"], unit="TFLOP/s",
-                          frac=achieved / peaks["tflops"], traffic=None, peak_source=peaks["src"],
-                          kernel="attn_kernel<32,shared> (volume cross-attention)", kernel_ms=k_ms,
+                          frac=achieved / peaks["tflops"],
+                          traffic=load_traffic() if args.workload == "cfg1" and batch == 4 else None,
+                          peak_source=peaks["src"],
+                          kernel="attn_small_kernel<32,3,1> (volume cross-attention, xattn_small.cu)", kernel_ms=k_ms,
                           kernel_share_of_step=kt["ms"] / ms_per_step if ms_per_step > 0 else None,
                           flops="executed (reassociated small-context form, padded tiles)",
                           exp_per_s=exp_rate, exp_frac_of_mufu=exp_rate / (148 * 16 * sm_hz)),
