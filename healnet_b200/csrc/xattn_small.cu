@@ -17,9 +17,10 @@
 //     sits on the critical path;
 //   * softmax threads own one latent row (one TMEM lane) and work in 32-column chunks (S -> P in place of
 //     registers, ~80 regs/thread);
-//   * a quarter of the exponentials are evaluated on the FMA pipe (Cody-Waite range reduction + degree-3 minimax
-//     polynomial, rel. error 7.5e-5 < fp16 rounding of P) so MUFU only sees the rest (pipe microbenchmark:
-//     23 elem/clk/SM for a 3/8 mix vs 16 for MUFU alone, tools/microbench/mb_pipes.cu; in this kernel 1/4 measured best);
+//   * half of the exponentials are evaluated on the FMA / ALU pipes, two at a time in half2 arithmetic (Cody-Waite
+//     range reduction + degree-3 minimax polynomial + integer exponent insert, 12 instructions per column pair
+//     incl. the fp16 pack) so MUFU only sees the other half (pipe microbenchmark: 23 elem/clk/SM for a 3/8 fp32
+//     mix vs 16 for MUFU alone, tools/microbench/mb_pipes.cu; HN_POLY_MODE sweeps the share, 1/2 measured best);
 //   * the running max is a lazily raised reference: the steady state does no max pass at all — it only tracks
 //     the max of the packed fp16 P words (VIMNMX3.U16x2, a quarter of an instruction per element) and falls
 //     back to the exact two-pass path when a P exceeds 2^8 (or on the first / a masked / the ragged last tile);
@@ -43,8 +44,13 @@ constexpr int BM = 128;  // latent rows per row block
 constexpr int BT = 64;   // tokens per tile
 constexpr int NST = 8;   // z ring depth
 constexpr int MAXG = 4;
-constexpr uint32_t P_RAISE_BITS = 0x5C00u;  // fp16(256): a larger P triggers the exact path (raises the reference max)
-constexpr float RESCALE_THRESHOLD = 8.f;    // log2 units, = log2(256)
+// P = 2^(s - m_ref) is stored in fp16 (subnormals included: representable down to 2^-24). A raise puts the
+// reference AT the row max seen so far; it then stays put until some P exceeds 2^5 (or is inf / garbage), i.e.
+// until the running max has grown by another 5 log2 units; that triggers the exact path, which raises it again.
+// (2^5 rather than fp16's 2^15 because the half2 polynomial below builds 2^(x+10) before scaling back.)
+constexpr float REF_SHIFT = 0.f;
+constexpr uint32_t P_RAISE_BITS = 0x5000u;  // fp16(32)
+constexpr float RESCALE_THRESHOLD = 5.f;    // log2 units
 
 struct SmallDev {
   int L, H, batch, nsplit, n_ltiles, n_rb;  // n_rb = H * n_ltiles row blocks per (sample, split)
@@ -94,6 +100,34 @@ __device__ __forceinline__ constexpr bool poly_slot(int j) {
          : PMODE == 2 ? (j % 3) == 1
          : PMODE == 3 ? ((j % 8) == 1 || (j % 8) == 4 || (j % 8) == 6)
                       : (j % 2) == 1;
+}
+// packed-pair variant: both exponentials of a column pair on the FMA / ALU pipes in half2 arithmetic (12
+// instructions per PAIR incl. the fp16 pack, vs 17 for two fp32 polynomials + pack). n = rint(x) via the magic
+// constant trick (fp16 ulp is 1 in [1024, 2048)); the constant is 1536 + 10, so the integer that lands in the low
+// mantissa bits is n + 10 and the exponent insert (a lane-wise integer add) builds 2^(x+10) — normal fp16 for
+// every x >= -24 — which one exact HMUL2 by 2^-10 brings back, denormalising correctly. x above 5.5 overflows the
+// exponent field into inf / NaN / the sign bit: all of them read as "> 2^5" by the unsigned max check that
+// triggers the exact path. Relative error ~6e-4 rms (3x the fp16 rounding of P itself, zero-mean).
+__device__ __forceinline__ uint32_t ex2_pair_h2(float x0, float x1) {
+  __half2 xh = __floats2half2_rn(x0, x1);
+  xh = __hmax2(xh, __float2half2_rn(-24.f));
+  const __half2 magic = __float2half2_rn(1546.f);
+  const __half2 t = __hadd2(xh, magic);
+  const __half2 f = __hsub2(xh, __hsub2(t, magic));  // t = 1546 + rint(x) exactly
+  __half2 p = __float2half2_rn(0.05517167f);
+  p = __hfma2(p, f, __float2half2_rn(0.24261112f));
+  p = __hfma2(p, f, __float2half2_rn(0.69326099f));
+  p = __hfma2(p, f, __float2half2_rn(0.99992807f));
+  const uint32_t e = (*reinterpret_cast<const uint32_t*>(&t) << 10) & 0xFC00FC00u;
+  uint32_t r;
+  asm("add.u16x2 %0, %1, %2;" : "=r"(r) : "r"(*reinterpret_cast<const uint32_t*>(&p)), "r"(e));
+  const __half2 scaled = __hmul2(*reinterpret_cast<const __half2*>(&r), __float2half2_rn(0.0009765625f));
+  return *reinterpret_cast<const uint32_t*>(&scaled);
+}
+// PMODE >= 5: which column PAIRS take the half2 polynomial: 5 = 1/3, 6 = 1/2, 7 = 2/3, 8 = 3/4
+template <int PMODE>
+__device__ __forceinline__ constexpr bool poly_pair(int j) {
+  return PMODE == 5 ? (j % 3) == 1 : PMODE == 6 ? (j % 2) == 1 : PMODE == 7 ? (j % 3) != 1 : PMODE == 8 ? (j % 4) != 1 : false;
 }
 __device__ __forceinline__ void mbar_wait_sleepy(uint64_t* bar, uint32_t parity, unsigned ns) {
   while (!mbar_try_wait(bar, parity)) __nanosleep(ns);  // waiter off the critical path: do not burn issue slots
@@ -278,9 +312,13 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float x0 = __uint_as_float(s[2 * j]), x1 = __uint_as_float(s[2 * j + 1]);
-              const float e0 = poly_slot<PMODE>(2 * j) ? ex2_poly(x0) : ex2_mufu(x0);
-              const float e1 = poly_slot<PMODE>(2 * j + 1) ? ex2_poly(x1) : ex2_mufu(x1);
-              pk[c * 16 + j] = pack_half2(e0, e1);
+              if (PMODE >= 5 && poly_pair<PMODE>(j)) {
+                pk[c * 16 + j] = ex2_pair_h2(x0, x1);
+              } else {
+                const float e0 = (PMODE < 5 && poly_slot<PMODE>(2 * j)) ? ex2_poly(x0) : ex2_mufu(x0);
+                const float e1 = (PMODE < 5 && poly_slot<PMODE>(2 * j + 1)) ? ex2_poly(x1) : ex2_mufu(x1);
+                pk[c * 16 + j] = pack_half2(e0, e1);
+              }
               pmax = vmaxu2(pmax, pk[c * 16 + j]);
             }
           }
@@ -315,7 +353,7 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           const bool raise = __any_sync(0xffffffffu, mx > m_ref + RESCALE_THRESHOLD);
           if (raise) {
             // round the new reference to fp16 so that the folded offset IS the reference
-            const float m_new = fmaxf(m_ref, __half2float(__float2half_rn(mx)));
+            const float m_new = fmaxf(m_ref, __half2float(__float2half_rn(mx - REF_SHIFT)));
             if (i > 0) {
               mbar_wait(&u_done[g], (i - 1) & 1);  // PV(i-1) landed; PV(i) cannot start before our p_ready arrive
               fence_after_sync();
@@ -470,18 +508,22 @@ int launch_small_attention(const AttnArgs& a, cudaStream_t stream) {
   HN_REQUIRE(a.q_ld % 8 == 0, "attention: row pitches must be multiples of 8 elements");
   HN_REQUIRE(a.N < (1L << 31), "attention: token axis too long");
   HN_REQUIRE(a.c_ones >= 1 && a.c_ones < a.kd, "attention: ones column must lie inside the context row");
-  if (a.kd == 64) return launch_small_t<64, 2, 1>(a, stream);
-  static int pmode = -1;  // tuning knob (HN_POLY_MODE=0..4); default 1/4 of the exponentials on the FMA pipe (measured best)
+  if (a.kd == 64) return launch_small_t<64, 2, 6>(a, stream);
+  static int pmode = -1;  // tuning knob (HN_POLY_MODE=0..8); default 6: every other column pair on the FMA pipe (half2), measured best
   if (pmode < 0) {
     const char* e = getenv("HN_POLY_MODE");
-    pmode = (e != nullptr && e[0] >= '0' && e[0] <= '4') ? e[0] - '0' : 1;
+    pmode = (e != nullptr && e[0] >= '0' && e[0] <= '8') ? e[0] - '0' : 6;
   }
   switch (pmode) {
     case 0: return launch_small_t<32, 3, 0>(a, stream);
     case 2: return launch_small_t<32, 3, 2>(a, stream);
     case 3: return launch_small_t<32, 3, 3>(a, stream);
     case 4: return launch_small_t<32, 3, 4>(a, stream);
-    default: return launch_small_t<32, 3, 1>(a, stream);
+    case 5: return launch_small_t<32, 3, 5>(a, stream);
+    case 7: return launch_small_t<32, 3, 7>(a, stream);
+    case 8: return launch_small_t<32, 3, 8>(a, stream);
+    case 1: return launch_small_t<32, 3, 1>(a, stream);
+    default: return launch_small_t<32, 3, 6>(a, stream);
   }
 }
 
