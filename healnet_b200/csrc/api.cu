@@ -188,6 +188,7 @@ struct Workspace {
   float* part_acc = nullptr;
   float* part_ml = nullptr;
   uint64_t* mask_bits = nullptr;
+  float* pooled = nullptr;   // [b][D] mean over latents (head)
   int self_nsplit = 1;
   size_t bytes = 0;
 };
@@ -262,6 +263,7 @@ int plan_workspace(const hn_handle* h, int batch, const int* axis_sizes, const b
   ws.part_acc = ar.take<float>(part_acc_elems);
   ws.part_ml = ar.take<float>(part_ml_elems);
   ws.mask_bits = ar.take<uint64_t>(mask_words);
+  ws.pooled = ar.take<float>(static_cast<size_t>(batch) * D);
   ws.bytes = ar.off + 256;
   return 0;
 }
@@ -325,9 +327,11 @@ int hn_create(const hn_desc* desc, hn_handle** out) {
   HN_REQUIRE(d.l_c >= 1 && d.l_d >= 1, "hn_create: latent array must be non-empty");
   HN_REQUIRE(d.x_heads >= 1 && d.l_heads >= 1, "hn_create: head counts must be >= 1");
   HN_REQUIRE(d.cross_dim_head >= 1 && d.cross_dim_head <= HP, "hn_create: cross_dim_head must be in 1..64");
-  HN_REQUIRE(d.latent_dim_head >= 1 && d.latent_dim_head <= HP, "hn_create: latent_dim_head must be in 1..64");
   HN_REQUIRE(d.self_per_cross_attn == 0 || d.self_per_cross_attn == 1,
              "hn_create: self_per_cross_attn must be 0 or 1 (the reference fails for >= 2, healnet.py:242)");
+  // with self_per_cross_attn == 0 no latent attention module exists (healnet.py:166-168): its head size is unused
+  HN_REQUIRE(d.latent_dim_head >= 1 && (d.self_per_cross_attn == 0 || d.latent_dim_head <= HP),
+             "hn_create: latent_dim_head must be in 1..64");
   HN_REQUIRE(d.num_freq_bands >= 1 || !d.fourier_encode_data, "hn_create: num_freq_bands must be >= 1");
   HN_REQUIRE(!d.final_classifier_head || d.out_dims >= 1, "hn_create: out_dims must be >= 1");
   hn_handle* h = new (std::nothrow) hn_handle();
@@ -679,7 +683,8 @@ int hn_forward(hn_handle* h, int batch, const void* const* modality_ptrs, const 
   }
   if (logits_out != nullptr) {
     const std::vector<const float*>& wh = h->w[slot_index(h, -1, 1)];
-    HN_TRY(launch_head(ws.x, batch, L, D, wh[0], wh[1], wh[2], wh[3], d.out_dims, logits_out, st));
+    HN_TRY(launch_head(ws.x, batch, L, D, wh[0], wh[1], wh[2], wh[3], d.out_dims, ws.pooled, logits_out, st));
+    ++h->launches;
   }
   return 0;
 }

@@ -79,8 +79,9 @@ int launch_build_z_large(const float* raw, __half* z, int ldz, int lo_seg, int b
                          const int* axis_sizes /*host*/, int n_bands, const float* tab, int fourier,
                          cudaStream_t stream);
 // pooled head: logits[b][o] = LN(mean_L x[b]) . W[o] + bias[o]
+// (pooled: batch * D floats of scratch)
 int launch_head(const float* x, int batch, int L, int D, const float* ln_w, const float* ln_b, const float* W,
-                const float* bias, int out_dims, float* logits, cudaStream_t stream);
+                const float* bias, int out_dims, float* pooled, float* logits, cudaStream_t stream);
 // user mask (b, N) bytes -> per-64-token-tile bit words (bit j = keep token tile*64+j)
 int launch_pack_mask(const uint8_t* mask, uint64_t* bits, int batch, long N, cudaStream_t stream);
 

@@ -242,19 +242,33 @@ __global__ void __launch_bounds__(256) build_z_large_kernel(const float* __restr
 }
 
 // ------------------------------------------------------------------ head: mean_L -> LN -> Linear
-__global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ x, int L, int D,
+// stage 1: pooled[b][d] = mean_l x[b][l][d]; block = (sample, 32 columns), 8 warps stride the rows
+__global__ void __launch_bounds__(256) pool_kernel(const float* __restrict__ x, int L, int D,
+                                                   float* __restrict__ pooled) {
+  __shared__ float part[8][33];
+  const int b = blockIdx.y, d = blockIdx.x * 32 + (threadIdx.x & 31), w = threadIdx.x >> 5;
+  const float* xb = x + static_cast<size_t>(b) * L * D;
+  float s = 0.f;
+  if (d < D)
+    for (int l = w; l < L; l += 8) s += xb[static_cast<size_t>(l) * D + d];
+  part[w][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (w == 0 && d < D) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += part[i][threadIdx.x];
+    pooled[static_cast<size_t>(b) * D + d] = t / L;
+  }
+}
+// stage 2: logits[b][o] = LN(pooled[b]) . W[o] + bias[o]; one block per sample
+__global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ pooled_g, int D,
                                                    const float* __restrict__ ln_w, const float* __restrict__ ln_b,
                                                    const float* __restrict__ W, const float* __restrict__ bias,
                                                    int out_dims, float* __restrict__ logits) {
-  extern __shared__ float pooled[];  // D floats + 2
+  extern __shared__ float pooled[];  // D floats
   __shared__ float red[32];
   const int b = blockIdx.x;
-  const float* xb = x + static_cast<size_t>(b) * L * D;
-  for (int d = threadIdx.x; d < D; d += blockDim.x) {
-    float s = 0.f;
-    for (int l = 0; l < L; ++l) s += xb[static_cast<size_t>(l) * D + d];
-    pooled[d] = s / L;
-  }
+  for (int d = threadIdx.x; d < D; d += blockDim.x) pooled[d] = pooled_g[static_cast<size_t>(b) * D + d];
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   float s = 0.f;
@@ -335,46 +349,53 @@ __global__ void __launch_bounds__(256) combine_generic_kernel(const float* __res
 }
 
 // small-C: acc rows are zw wide: [sum_t p z_c (c < C), sum_t p (col C), 0...]; then the V projection
-// O[b*L + l][h*64 + d] = (u / den) . Wv'[h*dh + d][:] + bv[h*dh + d]; one warp per (b, l, h)
+// O[b*L + l][h*64 + d] = (u / den) . Wv'[h*dh + d][:] + bv[h*dh + d].
+// Block = (32 latent rows, head, sample): warp w merges the splits of 4 rows (lane = column), the head's Wv' sits
+// transposed in shared memory so the projection reads are conflict-free broadcasts.
 __global__ void __launch_bounds__(256) combine_vproj_kernel(const float* __restrict__ part_acc,
                                                             const float* __restrict__ part_ml, int batch,
                                                             int nsplit, int H, int L, int C, int zw, int dh,
                                                             const float* __restrict__ Wv,
                                                             const float* __restrict__ bv, __half* __restrict__ O,
                                                             int o_ld, int lo_seg) {
-  __shared__ float u_s[8][64];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const long wid = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + wib;
-  const long total = static_cast<long>(batch) * L * H;
-  if (wid >= total) return;
-  const int h = static_cast<int>(wid % H);
-  const int l = static_cast<int>((wid / H) % L);
-  const int b = static_cast<int>(wid / (static_cast<long>(H) * L));
-  float M = -INFINITY;
-  for (int s = lane; s < nsplit; s += 32)
-    M = fmaxf(M, part_ml[((((static_cast<long>(b) * nsplit + s) * H + h) * L) + l) * 2]);
-  M = warp_max(M);
-  float acc0 = 0.f, acc1 = 0.f;
-  for (int s = 0; s < nsplit; ++s) {
-    const long base = (((static_cast<long>(b) * nsplit + s) * H + h) * L) + l;
-    const float m = part_ml[base * 2];
-    const float w = (m == -INFINITY) ? 0.f : exp2f(m - M);
-    acc0 += w * part_acc[base * zw + lane];
-    if (zw > 32) acc1 += w * part_acc[base * zw + 32 + lane];
+  __shared__ float wT[64][65];   // wT[c][d] = Wv'[h*dh + d][c]
+  __shared__ float u_s[32][65];  // merged, normalised rows
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int l0 = blockIdx.x * 32, h = blockIdx.y, b = blockIdx.z;
+  for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+    const int d = i / 64, c = i % 64;
+    wT[c][d] = (d < dh && c < C) ? Wv[static_cast<long>(h * dh + d) * zw + c] : 0.f;
   }
-  u_s[wib][lane] = acc0;
-  u_s[wib][lane + 32] = acc1;
-  __syncwarp();
-  const float inv = 1.f / u_s[wib][C];
-  __half* o = O + (static_cast<long>(b) * L + l) * o_ld + h * 64;
-  for (int d0 = 0; d0 < 64; d0 += 32) {
-    const int d = d0 + lane;
+  for (int r = w; r < 32; r += 8) {
+    const int l = l0 + r;
+    float acc0 = 0.f, acc1 = 0.f;
+    if (l < L) {
+      float M = -INFINITY;
+      for (int s = lane; s < nsplit; s += 32)
+        M = fmaxf(M, part_ml[((((static_cast<long>(b) * nsplit + s) * H + h) * L) + l) * 2]);
+      M = warp_max(M);
+      for (int s = 0; s < nsplit; ++s) {
+        const long base = (((static_cast<long>(b) * nsplit + s) * H + h) * L) + l;
+        const float m = part_ml[base * 2];
+        const float wgt = (m == -INFINITY) ? 0.f : exp2f(m - M);
+        acc0 += wgt * part_acc[base * zw + lane];
+        if (zw > 32) acc1 += wgt * part_acc[base * zw + 32 + lane];
+      }
+    }
+    u_s[r][lane] = acc0;
+    u_s[r][lane + 32] = acc1;
+  }
+  __syncthreads();
+  // 32 rows x 64 output columns = 2048 outputs over 256 threads
+  for (int i = threadIdx.x; i < 32 * 64; i += 256) {
+    const int r = i / 64, d = i % 64, l = l0 + r;
+    if (l >= L) continue;
     float out = 0.f;
     if (d < dh) {
-      const float* wr = Wv + static_cast<long>(h * dh + d) * zw;
-      for (int c = 0; c < C; ++c) out += u_s[wib][c] * wr[c];
-      out = out * inv + bv[h * dh + d];
+      for (int c = 0; c < C; ++c) out += u_s[r][c] * wT[c][d];
+      out = out / u_s[r][C] + bv[h * dh + d];
     }
+    __half* o = O + (static_cast<long>(b) * L + l) * o_ld + h * 64;
     store_split(o, d, 0, lo_seg, out);
   }
 }
@@ -458,8 +479,10 @@ int launch_build_z_large(const float* raw, __half* z, int ldz, int lo_seg, int b
 }
 
 int launch_head(const float* x, int batch, int L, int D, const float* ln_w, const float* ln_b, const float* W,
-                const float* bias, int out_dims, float* logits, cudaStream_t stream) {
-  head_kernel<<<batch, 256, (D + 2) * sizeof(float), stream>>>(x, L, D, ln_w, ln_b, W, bias, out_dims, logits);
+                const float* bias, int out_dims, float* pooled, float* logits, cudaStream_t stream) {
+  pool_kernel<<<dim3((D + 31) / 32, batch), 256, 0, stream>>>(x, L, D, pooled);
+  HN_CHECK_CUDA(cudaGetLastError());
+  head_kernel<<<batch, 256, (D + 2) * sizeof(float), stream>>>(pooled, D, ln_w, ln_b, W, bias, out_dims, logits);
   HN_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -485,10 +508,8 @@ int launch_combine_vproj(const float* part_acc, const float* part_ml, int batch,
                          int zw, int dh, const float* Wv, const float* bv, __half* O, int o_ld, int lo_seg,
                          cudaStream_t stream) {
   HN_REQUIRE((zw == 32 || zw == 64) && C <= zw - 1 && dh <= 64, "combine_vproj: C < zw and dim_head <= 64 required");
-  const long total = static_cast<long>(batch) * L * H;
-  combine_vproj_kernel<<<static_cast<unsigned>((total + 7) / 8), 256, 0, stream>>>(part_acc, part_ml, batch, nsplit,
-                                                                                    H, L, C, zw, dh, Wv, bv, O, o_ld,
-                                                                                    lo_seg);
+  combine_vproj_kernel<<<dim3((L + 31) / 32, H, batch), 256, 0, stream>>>(part_acc, part_ml, batch, nsplit, H, L, C,
+                                                                             zw, dh, Wv, bv, O, o_ld, lo_seg);
   HN_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

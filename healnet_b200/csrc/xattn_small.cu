@@ -17,10 +17,10 @@
 //     sits on the critical path;
 //   * softmax threads own one latent row (one TMEM lane) and work in 32-column chunks (S -> P in place of
 //     registers, ~80 regs/thread);
-//   * half of the exponentials are evaluated on the FMA / ALU pipes, two at a time in half2 arithmetic (Cody-Waite
+//   * a third of the exponentials are evaluated on the FMA / ALU pipes, two at a time in half2 arithmetic (Cody-Waite
 //     range reduction + degree-3 minimax polynomial + integer exponent insert, 12 instructions per column pair
-//     incl. the fp16 pack) so MUFU only sees the other half (pipe microbenchmark: 23 elem/clk/SM for a 3/8 fp32
-//     mix vs 16 for MUFU alone, tools/microbench/mb_pipes.cu; HN_POLY_MODE sweeps the share, 1/2 measured best);
+//     incl. the fp16 pack) so MUFU only sees the rest (pipe microbenchmark: 23 elem/clk/SM for a 3/8 fp32
+//     mix vs 16 for MUFU alone, tools/microbench/mb_pipes.cu; HN_POLY_MODE sweeps the share, 1/3 .. 1/2 measured best);
 //   * the running max is a lazily raised reference: the steady state does no max pass at all — it only tracks
 //     the max of the packed fp16 P words (VIMNMX3.U16x2, a quarter of an instruction per element) and falls
 //     back to the exact two-pass path when a P exceeds 2^8 (or on the first / a masked / the ragged last tile);
@@ -129,8 +129,19 @@ template <int PMODE>
 __device__ __forceinline__ constexpr bool poly_pair(int j) {
   return PMODE == 5 ? (j % 3) == 1 : PMODE == 6 ? (j % 2) == 1 : PMODE == 7 ? (j % 3) != 1 : PMODE == 8 ? (j % 4) != 1 : false;
 }
-__device__ __forceinline__ void mbar_wait_sleepy(uint64_t* bar, uint32_t parity, unsigned ns) {
-  while (!mbar_try_wait(bar, parity)) __nanosleep(ns);  // waiter off the critical path: do not burn issue slots
+// waiter off the critical path: let the hardware suspend the thread (try_wait with a long suspend-time hint)
+// instead of spinning through issue slots the softmax warps need
+__device__ __forceinline__ void mbar_wait_sleepy(uint64_t* bar, uint32_t parity, unsigned hint_ns) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+        : "memory");
+  } while (!ok);
 }
 
 // byte offset of element (row, col) inside a TMA-swizzled [rows][KD] fp16 tile (64-byte rows -> SWIZZLE_64B,
@@ -226,7 +237,7 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
       for (int i = 0; i < n; ++i) {
         const int s = i % NST;
-        mbar_wait_sleepy(&z_empty[s], ((i / NST) & 1) ^ 1, 200);
+        mbar_wait_sleepy(&z_empty[s], ((i / NST) & 1) ^ 1, 20000);
         mbar_arrive_expect_tx(&z_full[s], Z_BYTES);
         tma_load_3d(sZ + s * Z_BYTES, &tmZ, &z_full[s], 0, (t_begin + i) * BT, b);
       }
@@ -255,7 +266,7 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       issue_s(0);
       if (n > 1) issue_s(1);
       for (int i = 0; i < n; ++i) {
-        mbar_wait_sleepy(&p_ready[g], i & 1, 100);  // all four warps: S(i) consumed, P(i) in TMEM, Q' fold up to date
+        mbar_wait_sleepy(&p_ready[g], i & 1, 20000);  // all four warps: S(i) consumed, P(i) in TMEM, Q' fold up to date
         fence_after_sync();
         const int s = i % NST;
         const uint32_t z0 = smem_u32(sZ + s * Z_BYTES);
@@ -508,22 +519,22 @@ int launch_small_attention(const AttnArgs& a, cudaStream_t stream) {
   HN_REQUIRE(a.q_ld % 8 == 0, "attention: row pitches must be multiples of 8 elements");
   HN_REQUIRE(a.N < (1L << 31), "attention: token axis too long");
   HN_REQUIRE(a.c_ones >= 1 && a.c_ones < a.kd, "attention: ones column must lie inside the context row");
-  if (a.kd == 64) return launch_small_t<64, 2, 6>(a, stream);
-  static int pmode = -1;  // tuning knob (HN_POLY_MODE=0..8); default 6: every other column pair on the FMA pipe (half2), measured best
+  if (a.kd == 64) return launch_small_t<64, 2, 5>(a, stream);
+  static int pmode = -1;  // tuning knob (HN_POLY_MODE=0..8); default 5: every third column pair on the FMA pipe (half2); 5 and 6 measured equal and best
   if (pmode < 0) {
     const char* e = getenv("HN_POLY_MODE");
-    pmode = (e != nullptr && e[0] >= '0' && e[0] <= '8') ? e[0] - '0' : 6;
+    pmode = (e != nullptr && e[0] >= '0' && e[0] <= '8') ? e[0] - '0' : 5;
   }
   switch (pmode) {
     case 0: return launch_small_t<32, 3, 0>(a, stream);
     case 2: return launch_small_t<32, 3, 2>(a, stream);
     case 3: return launch_small_t<32, 3, 3>(a, stream);
     case 4: return launch_small_t<32, 3, 4>(a, stream);
-    case 5: return launch_small_t<32, 3, 5>(a, stream);
     case 7: return launch_small_t<32, 3, 7>(a, stream);
     case 8: return launch_small_t<32, 3, 8>(a, stream);
     case 1: return launch_small_t<32, 3, 1>(a, stream);
-    default: return launch_small_t<32, 3, 6>(a, stream);
+    case 6: return launch_small_t<32, 3, 6>(a, stream);
+    default: return launch_small_t<32, 3, 5>(a, stream);
   }
 }
 
