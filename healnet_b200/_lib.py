@@ -68,8 +68,8 @@ SIGNATURES = {
                                     c_float, c_int, c_void_p, c_void_p]),
     "hn_op_attention_nsplit": (c_int, [c_int, c_int, c_int, c_long, c_int]),
     "hn_op_attention": (c_int, [c_void_p, c_int, c_void_p, c_long, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                                c_long, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "hn_op_combine": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                c_int, c_long, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hn_op_combine": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
                               c_void_p, c_void_p, c_int, c_void_p]),
     "hn_debug_probe": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                c_void_p]),

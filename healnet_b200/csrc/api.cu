@@ -21,7 +21,9 @@ const char* get_error() { return g_error.c_str(); }
 
 namespace {
 
-constexpr int HP = 64;  // head pitch: every head occupies 64 columns of Q / K / V / O (zero padded)
+// head pitch: every head occupies 64 (dim_head <= 64) or 128 columns of Q / K / V / O, zero padded
+constexpr int MAX_DIM_HEAD = 128;
+inline int head_pitch(int dim_head) { return dim_head <= 64 ? 64 : 128; }
 constexpr float LOG2E = 1.4426950408889634074f;
 
 // bump allocator over a caller-provided (or handle-owned) device buffer; 256-byte aligned pieces
@@ -70,6 +72,7 @@ using namespace hn;
 struct hn_handle {
   hn_desc d;
   int M = 0, I = 0, lI = 0;
+  int hpx = 64, hpl = 64;         // head pitch of the cross / latent attention (64 or 128 columns per head)
   int segD = 0, seg4D = 0;        // hi/lo segment widths of D-wide / 4D-wide split operands (multiples of 64)
   int C[HN_MAX_MODALITIES];       // context width per modality
   // registered fp32 parameters: index (layer + 1) * slots_per_layer + slot
@@ -124,8 +127,8 @@ int plan_packed(hn_handle* h, Arena& ar) {
         AttnPacked p;
         if (self) {
           p.C = D;
-          p.Wq = ar.take<__half>(static_cast<size_t>(3) * d.l_heads * HP * 2 * h->segD);
-          p.Wo = ar.take<__half>(static_cast<size_t>(D) * 2 * d.l_heads * HP);
+          p.Wq = ar.take<__half>(static_cast<size_t>(3) * d.l_heads * h->hpl * 2 * h->segD);
+          p.Wo = ar.take<__half>(static_cast<size_t>(D) * 2 * d.l_heads * h->hpl);
         } else {
           p.C = h->C[m];
           p.small = p.C <= 63;
@@ -135,10 +138,10 @@ int plan_packed(hn_handle* h, Arena& ar) {
             p.Wv = ar.take<float>(static_cast<size_t>(h->I) * p.zw);
             p.bv = ar.take<float>(h->I);
           }
-          p.Wq = ar.take<__half>(static_cast<size_t>(d.x_heads) * HP * 2 * h->segD);
-          p.Wkv = ar.take<__half>(static_cast<size_t>(2) * d.x_heads * HP * 2 * seg_of(p.C));
-          p.bkv = ar.take<float>(static_cast<size_t>(2) * d.x_heads * HP);
-          p.Wo = ar.take<__half>(static_cast<size_t>(D) * 2 * d.x_heads * HP);
+          p.Wq = ar.take<__half>(static_cast<size_t>(d.x_heads) * h->hpx * 2 * h->segD);
+          p.Wkv = ar.take<__half>(static_cast<size_t>(2) * d.x_heads * h->hpx * 2 * seg_of(p.C));
+          p.bkv = ar.take<float>(static_cast<size_t>(2) * d.x_heads * h->hpx);
+          p.Wo = ar.take<__half>(static_cast<size_t>(D) * 2 * d.x_heads * h->hpx);
         }
         attn_seen[ka] = p;
         h->attn[l * (M + 1) + m] = p;
@@ -203,14 +206,14 @@ int plan_workspace(const hn_handle* h, int batch, const int* axis_sizes, const b
   const long rows = static_cast<long>(batch) * L;
   ws.x = ar.take<float>(rows * D);
   ws.xn = ar.take<__half>(rows * 2 * h->segD);
-  int qw = d.self_per_cross_attn ? 3 * d.l_heads * HP : 0;
-  int ow = d.self_per_cross_attn ? d.l_heads * HP : 0;
+  int qw = d.self_per_cross_attn ? 3 * d.l_heads * h->hpl : 0;
+  int ow = d.self_per_cross_attn ? d.l_heads * h->hpl : 0;
   size_t part_acc_elems = 0, part_ml_elems = 0, kv_elems = 0, mask_words = 0;
   const int n_ltiles = (L + 127) / 128;
   ws.self_precise = L <= PRECISE_MAX_TOKENS;
   if (d.self_per_cross_attn) {
     ws.self_nsplit = attention_pick_nsplit(batch, L, d.l_heads, L);
-    part_acc_elems = static_cast<size_t>(batch) * ws.self_nsplit * d.l_heads * n_ltiles * 128 * 64;
+    part_acc_elems = static_cast<size_t>(batch) * ws.self_nsplit * d.l_heads * n_ltiles * 128 * h->hpl;
     part_ml_elems = static_cast<size_t>(batch) * ws.self_nsplit * d.l_heads * n_ltiles * 128 * 2;
   }
   for (int m = 0; m < M; ++m) {
@@ -233,7 +236,7 @@ int plan_workspace(const hn_handle* h, int batch, const int* axis_sizes, const b
     int axsum = 0;
     for (int a = 0; a < mp.n_axes; ++a) axsum += mp.axes[a];
     mp.tab = ar.take<float>(static_cast<size_t>(axsum) * (2 * d.num_freq_bands + 1));
-    const int vd = mp.small ? (mp.C <= 31 ? 32 : 64) : 64;
+    const int vd = mp.small ? (mp.C <= 31 ? 32 : 64) : h->hpx;
     if (mp.small) {
       mp.zw = vd;
       mp.z = ar.take<__half>(static_cast<size_t>(batch) * mp.N * mp.zw);
@@ -243,11 +246,11 @@ int plan_workspace(const hn_handle* h, int batch, const int* axis_sizes, const b
       mp.segC = seg_of(mp.C);
       mp.ldz = mp.precise ? 2 * mp.segC : ctx_ld(mp.C);
       mp.z = ar.take<__half>(static_cast<size_t>(batch) * mp.N * mp.ldz);
-      const size_t kv = static_cast<size_t>(batch) * mp.N * 2 * d.x_heads * HP * (mp.precise ? 2 : 1);
+      const size_t kv = static_cast<size_t>(batch) * mp.N * 2 * d.x_heads * h->hpx * (mp.precise ? 2 : 1);
       kv_elems = kv > kv_elems ? kv : kv_elems;
-      qw = qw > d.x_heads * HP ? qw : d.x_heads * HP;
+      qw = qw > d.x_heads * h->hpx ? qw : d.x_heads * h->hpx;
     }
-    ow = ow > d.x_heads * HP ? ow : d.x_heads * HP;
+    ow = ow > d.x_heads * h->hpx ? ow : d.x_heads * h->hpx;
     mp.nsplit = mp.small ? small_attention_pick_nsplit(batch, L, d.x_heads, mp.N, vd)
                          : attention_pick_nsplit(batch, L, d.x_heads, mp.N);
     const size_t pa = static_cast<size_t>(batch) * mp.nsplit * d.x_heads * n_ltiles * 128 * vd;
@@ -326,12 +329,12 @@ int hn_create(const hn_desc* desc, hn_handle** out) {
   HN_REQUIRE(d.depth >= 1, "hn_create: depth must be >= 1");
   HN_REQUIRE(d.l_c >= 1 && d.l_d >= 1, "hn_create: latent array must be non-empty");
   HN_REQUIRE(d.x_heads >= 1 && d.l_heads >= 1, "hn_create: head counts must be >= 1");
-  HN_REQUIRE(d.cross_dim_head >= 1 && d.cross_dim_head <= HP, "hn_create: cross_dim_head must be in 1..64");
+  HN_REQUIRE(d.cross_dim_head >= 1 && d.cross_dim_head <= MAX_DIM_HEAD, "hn_create: cross_dim_head must be in 1..128");
   HN_REQUIRE(d.self_per_cross_attn == 0 || d.self_per_cross_attn == 1,
              "hn_create: self_per_cross_attn must be 0 or 1 (the reference fails for >= 2, healnet.py:242)");
   // with self_per_cross_attn == 0 no latent attention module exists (healnet.py:166-168): its head size is unused
-  HN_REQUIRE(d.latent_dim_head >= 1 && (d.self_per_cross_attn == 0 || d.latent_dim_head <= HP),
-             "hn_create: latent_dim_head must be in 1..64");
+  HN_REQUIRE(d.latent_dim_head >= 1 && (d.self_per_cross_attn == 0 || d.latent_dim_head <= MAX_DIM_HEAD),
+             "hn_create: latent_dim_head must be in 1..128");
   HN_REQUIRE(d.num_freq_bands >= 1 || !d.fourier_encode_data, "hn_create: num_freq_bands must be >= 1");
   HN_REQUIRE(!d.final_classifier_head || d.out_dims >= 1, "hn_create: out_dims must be >= 1");
   hn_handle* h = new (std::nothrow) hn_handle();
@@ -340,6 +343,8 @@ int hn_create(const hn_desc* desc, hn_handle** out) {
   h->M = d.n_modalities;
   h->I = d.x_heads * d.cross_dim_head;
   h->lI = d.l_heads * d.latent_dim_head;
+  h->hpx = head_pitch(d.cross_dim_head);
+  h->hpl = head_pitch(d.latent_dim_head);
   h->segD = round_up(d.l_d, 64);
   h->seg4D = round_up(4 * d.l_d, 64);
   for (int m = 0; m < h->M; ++m) {
@@ -426,11 +431,13 @@ int hn_pack_weights(hn_handle* h, void* cuda_stream) {
           // {norm.w, norm.b, to_q.w [lI][D], to_kv.w [2lI][D], to_out.w [D][lI], to_out.b}
           const int lh = d.l_heads, ldh = d.latent_dim_head;
           const float scale = 2.f / std::sqrt(static_cast<float>(ldh)) * LOG2E;
-          rc = pack_headpad_rows(ap.Wq, 2 * sD, 0, wa[2], D, 0, lh, ldh, D, scale, nullptr, sD, sD, st);
-          if (rc == 0) rc = pack_headpad_rows(ap.Wq, 2 * sD, lh * HP, wa[3], D, 0, lh, ldh, D, 1.f, nullptr, sD, sD, st);
+          const int hp = h->hpl;
+          rc = pack_headpad_rows(ap.Wq, 2 * sD, 0, wa[2], D, 0, lh, ldh, D, scale, nullptr, sD, sD, hp, st);
           if (rc == 0)
-            rc = pack_headpad_rows(ap.Wq, 2 * sD, 2 * lh * HP, wa[3], D, h->lI, lh, ldh, D, 1.f, nullptr, sD, sD, st);
-          if (rc == 0) rc = pack_headpad_cols(ap.Wo, 2 * lh * HP, wa[4], h->lI, D, lh, ldh, lh * HP, lh * HP, st);
+            rc = pack_headpad_rows(ap.Wq, 2 * sD, lh * hp, wa[3], D, 0, lh, ldh, D, 1.f, nullptr, sD, sD, hp, st);
+          if (rc == 0)
+            rc = pack_headpad_rows(ap.Wq, 2 * sD, 2 * lh * hp, wa[3], D, h->lI, lh, ldh, D, 1.f, nullptr, sD, sD, hp, st);
+          if (rc == 0) rc = pack_headpad_cols(ap.Wo, 2 * lh * hp, wa[4], h->lI, D, lh, ldh, lh * hp, lh * hp, hp, st);
         } else {
           // {norm.w, norm.b, norm_context.w, norm_context.b, to_q.w [I][D], to_kv.w [2I][C], to_out.w [D][I], to_out.b}
           const int H = d.x_heads, dh = d.cross_dim_head, C = ap.C;
@@ -441,14 +448,16 @@ int hn_pack_weights(hn_handle* h, void* cuda_stream) {
           }
           if (rc == 0) {
             const int sC = seg_of(C);
-            rc = pack_headpad_rows(ap.Wq, 2 * sD, 0, wa[4], D, 0, H, dh, D, scale, nullptr, sD, sD, st);
-            if (rc == 0) rc = pack_headpad_rows(ap.Wkv, 2 * sC, 0, wa[5], C, 0, H, dh, C, 1.f, wa[2], sC, sC, st);
+            const int hp = h->hpx;
+            rc = pack_headpad_rows(ap.Wq, 2 * sD, 0, wa[4], D, 0, H, dh, D, scale, nullptr, sD, sD, hp, st);
+            if (rc == 0) rc = pack_headpad_rows(ap.Wkv, 2 * sC, 0, wa[5], C, 0, H, dh, C, 1.f, wa[2], sC, sC, hp, st);
             if (rc == 0)
-              rc = pack_headpad_rows(ap.Wkv, 2 * sC, H * HP, wa[5], C, h->I, H, dh, C, 1.f, wa[2], sC, sC, st);
-            if (rc == 0) HN_CHECK_CUDA(cudaMemsetAsync(ap.bkv, 0, sizeof(float) * H * HP, st));
-            if (rc == 0) rc = fold_beta_headpad(ap.bkv, H * HP, wa[5], C, h->I, H, dh, C, wa[3], st);
+              rc = pack_headpad_rows(ap.Wkv, 2 * sC, H * hp, wa[5], C, h->I, H, dh, C, 1.f, wa[2], sC, sC, hp, st);
+            if (rc == 0) HN_CHECK_CUDA(cudaMemsetAsync(ap.bkv, 0, sizeof(float) * H * hp, st));
+            if (rc == 0) rc = fold_beta_headpad(ap.bkv, H * hp, wa[5], C, h->I, H, dh, C, wa[3], hp, st);
           }
-          if (rc == 0) rc = pack_headpad_cols(ap.Wo, 2 * H * HP, wa[6], h->I, D, H, dh, H * HP, H * HP, st);
+          if (rc == 0)
+            rc = pack_headpad_cols(ap.Wo, 2 * H * h->hpx, wa[6], h->I, D, H, dh, H * h->hpx, H * h->hpx, h->hpx, st);
         }
         if (rc != 0) return rc;
       }
@@ -572,10 +581,10 @@ int hn_forward(hn_handle* h, int batch, const void* const* modality_ptrs, const 
         const std::vector<const float*>& wf = h->w[slot_index(h, l, 2 * m + 1)];
         const AttnPacked& ap = h->attn[l * (M + 1) + m];
         const FFPacked& fp = h->ff[l * (M + 1) + m];
-        const int H = d.x_heads, ow = H * HP;
+        const int H = d.x_heads, HPx = h->hpx, ow = H * HPx;
         // PreNorm + to_q (split operands; the small-C Q' keeps its hi part only)
         HN_TRY(launch_layernorm_f16(ws.x, D, wa[0], wa[1], ws.xn, 2 * sD, sD, sD, rows, D, st));
-        const int qw = mp.small ? H * mp.zw : H * HP;
+        const int qw = mp.small ? H * mp.zw : H * HPx;
         const bool q_split = !mp.small && mp.precise;
         GemmArgs gq{ws.xn, mp.small ? ap.WqS : ap.Wq, static_cast<int>(rows), qw, D, 2 * sD, 2 * sD, EPI_F16, 0,
                     nullptr, ws.q, q_split ? 2 * qw : qw, 3, sD, sD, q_split ? qw : 0};
@@ -602,14 +611,14 @@ int hn_forward(hn_handle* h, int batch, const void* const* modality_ptrs, const 
           HN_TRY(launch_attention(aa, st));
           profile_end(h, st);
           HN_TRY(launch_combine_vproj(ws.part_acc, ws.part_ml, batch, mp.nsplit, H, L, mp.C, mp.zw,
-                                      d.cross_dim_head, ap.Wv, ap.bv, ws.o, 2 * ow, ow, st));
+                                      d.cross_dim_head, ap.Wv, ap.bv, ws.o, 2 * ow, ow, HPx, st));
         } else {
           // K/V projection of the standardised context (context LayerNorm affine folded into the weights).
           // Weights are always split (their rounding would not average out over tokens); z, K and V are split
           // only on short token axes.
           const long tok = static_cast<long>(batch) * mp.N;
           HN_REQUIRE(tok < (1L << 31), "hn_forward: batch * tokens too large for the K/V projection");
-          const int kvw = 2 * H * HP;
+          const int kvw = 2 * H * HPx;
           GemmArgs gkv{mp.z, ap.Wkv, static_cast<int>(tok), kvw, mp.C, mp.ldz, 2 * mp.segC, EPI_F16, 0, ap.bkv,
                        ws.kv, mp.precise ? 2 * kvw : kvw, mp.precise ? 3 : 2, mp.segC, mp.segC,
                        mp.precise ? kvw : 0};
@@ -617,9 +626,10 @@ int hn_forward(hn_handle* h, int batch, const void* const* modality_ptrs, const 
           aa.KV = ws.kv;
           aa.kv_ld = mp.precise ? 2 * kvw : kvw;
           aa.k_col0 = 0;
-          aa.v_col0 = H * HP;
+          aa.v_col0 = H * HPx;
           aa.shared_kv = 0;
           aa.kd = 64;
+          aa.hp = HPx;
           aa.precise = mp.precise ? 1 : 0;
           aa.q_lo_off = qw;
           aa.kv_lo_off = kvw;
@@ -627,7 +637,7 @@ int hn_forward(hn_handle* h, int batch, const void* const* modality_ptrs, const 
           if (rc != 0) return rc;
           HN_TRY(launch_attention(aa, st));
           profile_end(h, st);
-          HN_TRY(launch_combine_generic(ws.part_acc, ws.part_ml, batch, mp.nsplit, H, L, ws.o, 2 * ow, ow, st));
+          HN_TRY(launch_combine_generic(ws.part_acc, ws.part_ml, batch, mp.nsplit, H, L, ws.o, 2 * ow, ow, HPx, st));
         }
         // x = LeakyReLU(O Wo^T + bo) + x   (healnet.py:383-386, 426, 236)
         GemmArgs go{ws.o, ap.Wo, static_cast<int>(rows), D, ow, 2 * ow, 2 * ow, EPI_RES_LEAKY, 0, wa[7], ws.x, D,
@@ -642,7 +652,7 @@ int hn_forward(hn_handle* h, int batch, const void* const* modality_ptrs, const 
         const std::vector<const float*>& wf = h->w[slot_index(h, l, 2 * M + 1)];
         const AttnPacked& ap = h->attn[l * (M + 1) + M];
         const FFPacked& fp = h->ff[l * (M + 1) + M];
-        const int lh = d.l_heads, ow = lh * HP, qw = 3 * lh * HP;
+        const int lh = d.l_heads, HPl = h->hpl, ow = lh * HPl, qw = 3 * lh * HPl;
         const bool prec = ws.self_precise;
         HN_TRY(launch_layernorm_f16(ws.x, D, wa[0], wa[1], ws.xn, 2 * sD, sD, sD, rows, D, st));
         GemmArgs gq{ws.xn, ap.Wq, static_cast<int>(rows), qw, D, 2 * sD, 2 * sD, EPI_F16, 0, nullptr, ws.q,
@@ -653,10 +663,11 @@ int hn_forward(hn_handle* h, int batch, const void* const* modality_ptrs, const 
         aa.q_ld = prec ? 2 * qw : qw;
         aa.KV = ws.q;
         aa.kv_ld = aa.q_ld;
-        aa.k_col0 = lh * HP;
-        aa.v_col0 = 2 * lh * HP;
+        aa.k_col0 = lh * HPl;
+        aa.v_col0 = 2 * lh * HPl;
         aa.shared_kv = 0;
         aa.kd = 64;
+        aa.hp = HPl;
         aa.precise = prec ? 1 : 0;
         aa.q_lo_off = qw;
         aa.kv_lo_off = qw;
@@ -669,7 +680,7 @@ int hn_forward(hn_handle* h, int batch, const void* const* modality_ptrs, const 
         aa.part_acc = ws.part_acc;
         aa.part_ml = ws.part_ml;
         HN_TRY(launch_attention(aa, st));
-        HN_TRY(launch_combine_generic(ws.part_acc, ws.part_ml, batch, ws.self_nsplit, lh, L, ws.o, 2 * ow, ow, st));
+        HN_TRY(launch_combine_generic(ws.part_acc, ws.part_ml, batch, ws.self_nsplit, lh, L, ws.o, 2 * ow, ow, HPl, st));
         GemmArgs go{ws.o, ap.Wo, static_cast<int>(rows), D, ow, 2 * ow, 2 * ow, EPI_RES_LEAKY, 0, wa[5], ws.x, D,
                     3, ow, ow, 0};
         HN_TRY(launch_gemm(go, st));
@@ -699,14 +710,15 @@ struct AttnWs {
   bool prec;
   size_t bytes;
 };
-void plan_attn_ws(int batch, int n_q, long n_ctx, int qd, int cd, int heads, bool self, char* base, AttnWs& w) {
+void plan_attn_ws(int batch, int n_q, long n_ctx, int qd, int cd, int heads, int dim_head, bool self, char* base,
+                  AttnWs& w) {
   Arena ar;
   ar.base = base;
   w.sq = seg_of(qd);
   w.sc = seg_of(cd);
   w.prec = n_ctx <= PRECISE_MAX_TOKENS;
   const long rows = static_cast<long>(batch) * n_q, toks = static_cast<long>(batch) * n_ctx;
-  const int hw = heads * HP;
+  const int hw = heads * head_pitch(dim_head);
   w.xh = ar.take<__half>(rows * 2 * w.sq);
   w.ch = self ? w.xh : ar.take<__half>(toks * (w.prec ? 2 * w.sc : ctx_ld(cd)));
   w.wq = ar.take<__half>(static_cast<size_t>(hw) * 2 * w.sq);
@@ -717,7 +729,7 @@ void plan_attn_ws(int batch, int n_q, long n_ctx, int qd, int cd, int heads, boo
   w.o = ar.take<__half>(rows * 2 * hw);
   w.nsplit = attention_pick_nsplit(batch, n_q, heads, n_ctx);
   const int n_ltiles = (n_q + 127) / 128;
-  w.part_acc = ar.take<float>(static_cast<size_t>(batch) * w.nsplit * heads * n_ltiles * 128 * 64);
+  w.part_acc = ar.take<float>(static_cast<size_t>(batch) * w.nsplit * heads * n_ltiles * 128 * head_pitch(dim_head));
   w.part_ml = ar.take<float>(static_cast<size_t>(batch) * w.nsplit * heads * n_ltiles * 128 * 2);
   w.mask_bits = ar.take<uint64_t>(static_cast<size_t>(batch) * ((n_ctx + 63) / 64));
   w.bytes = ar.off + 256;
@@ -728,7 +740,7 @@ size_t hn_attention_workspace_bytes(int batch, int n_q, long n_ctx, int query_di
                                     int dim_head) {
   if (batch < 1 || n_q < 1 || n_ctx < 1 || query_dim < 1 || context_dim < 1 || heads < 1 || dim_head < 1) return 0;
   AttnWs w;
-  plan_attn_ws(batch, n_q, n_ctx, query_dim, context_dim, heads, false, nullptr, w);
+  plan_attn_ws(batch, n_q, n_ctx, query_dim, context_dim, heads, dim_head, false, nullptr, w);
   return w.bytes;
 }
 
@@ -737,7 +749,7 @@ int hn_attention_forward(int batch, int n_q, long n_ctx, int query_dim, int cont
                          const float* w_out, const float* b_out, const uint8_t* mask, float* out, void* workspace,
                          size_t workspace_bytes, void* cuda_stream) {
   HN_REQUIRE(batch >= 1 && n_q >= 1 && query_dim >= 1 && heads >= 1, "hn_attention_forward: bad shape");
-  HN_REQUIRE(dim_head >= 1 && dim_head <= HP, "hn_attention_forward: dim_head must be in 1..64");
+  HN_REQUIRE(dim_head >= 1 && dim_head <= MAX_DIM_HEAD, "hn_attention_forward: dim_head must be in 1..128");
   HN_REQUIRE(x && w_q && w_kv && w_out && b_out && out && workspace, "hn_attention_forward: null argument");
   const bool self = (context == nullptr);
   if (self) {
@@ -748,9 +760,10 @@ int hn_attention_forward(int batch, int n_q, long n_ctx, int query_dim, int cont
   HN_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "hn_attention_forward: workspace must be 256-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   AttnWs w;
-  plan_attn_ws(batch, n_q, n_ctx, query_dim, context_dim, heads, self, static_cast<char*>(workspace), w);
+  plan_attn_ws(batch, n_q, n_ctx, query_dim, context_dim, heads, dim_head, self, static_cast<char*>(workspace), w);
   HN_REQUIRE(w.bytes <= workspace_bytes, "hn_attention_forward: workspace too small");
-  const int inner = heads * dim_head, hw = heads * HP, sq = w.sq, sc = w.sc;
+  const int hp = head_pitch(dim_head);
+  const int inner = heads * dim_head, hw = heads * hp, sq = w.sq, sc = w.sc;
   const long rows = static_cast<long>(batch) * n_q, toks = static_cast<long>(batch) * n_ctx;
   HN_REQUIRE(rows < (1L << 31) && toks < (1L << 31), "hn_attention_forward: problem too large");
   const float scale = 2.f / std::sqrt(static_cast<float>(dim_head)) * LOG2E;
@@ -766,12 +779,13 @@ int hn_attention_forward(int batch, int n_q, long n_ctx, int query_dim, int cont
   if (!self)
     HN_TRY2(pack_plain(w.ch, ldc, context, context_dim, static_cast<int>(toks), context_dim, w.prec ? sc : ldc,
                        w.prec ? sc : 0, st));
-  HN_TRY2(pack_headpad_rows(w.wq, 2 * sq, 0, w_q, query_dim, 0, heads, dim_head, query_dim, scale, nullptr, sq, sq, st));
-  HN_TRY2(pack_headpad_rows(w.wkv, 2 * sc, 0, w_kv, context_dim, 0, heads, dim_head, context_dim, 1.f, nullptr, sc, sc,
+  HN_TRY2(pack_headpad_rows(w.wq, 2 * sq, 0, w_q, query_dim, 0, heads, dim_head, query_dim, scale, nullptr, sq, sq, hp,
                             st));
+  HN_TRY2(pack_headpad_rows(w.wkv, 2 * sc, 0, w_kv, context_dim, 0, heads, dim_head, context_dim, 1.f, nullptr, sc, sc,
+                            hp, st));
   HN_TRY2(pack_headpad_rows(w.wkv, 2 * sc, hw, w_kv, context_dim, inner, heads, dim_head, context_dim, 1.f, nullptr,
-                            sc, sc, st));
-  HN_TRY2(pack_headpad_cols(w.wo, 2 * hw, w_out, inner, query_dim, heads, dim_head, hw, hw, st));
+                            sc, sc, hp, st));
+  HN_TRY2(pack_headpad_cols(w.wo, 2 * hw, w_out, inner, query_dim, heads, dim_head, hw, hw, hp, st));
   GemmArgs gq{w.xh, w.wq, static_cast<int>(rows), hw, query_dim, 2 * sq, 2 * sq, EPI_F16, 0, nullptr, w.q,
               w.prec ? 2 * hw : hw, 3, sq, sq, w.prec ? hw : 0};
   HN_TRY2(launch_gemm(gq, st));
@@ -791,6 +805,7 @@ int hn_attention_forward(int batch, int n_q, long n_ctx, int query_dim, int cont
   aa.precise = w.prec ? 1 : 0;
   aa.q_lo_off = hw;
   aa.kv_lo_off = 2 * hw;
+  aa.hp = hp;
   aa.batch = batch;
   aa.L = n_q;
   aa.H = heads;
@@ -800,7 +815,7 @@ int hn_attention_forward(int batch, int n_q, long n_ctx, int query_dim, int cont
   aa.part_acc = w.part_acc;
   aa.part_ml = w.part_ml;
   HN_TRY2(launch_attention(aa, st));
-  HN_TRY2(launch_combine_generic(w.part_acc, w.part_ml, batch, w.nsplit, heads, n_q, w.o, 2 * hw, hw, st));
+  HN_TRY2(launch_combine_generic(w.part_acc, w.part_ml, batch, w.nsplit, heads, n_q, w.o, 2 * hw, hw, hp, st));
   GemmArgs go{w.o, w.wo, static_cast<int>(rows), query_dim, hw, 2 * hw, 2 * hw, EPI_LEAKY_F32, 0, b_out, out,
               query_dim, 3, hw, hw, 0};
   HN_TRY2(launch_gemm(go, st));
@@ -848,7 +863,7 @@ int hn_op_attention_nsplit(int batch, int L, int H, long N, int small_kd) {
 }
 
 int hn_op_attention(const void* Q, int q_ld, const void* KV, long kv_ld, int k_col0, int v_col0, int shared_kv,
-                    int c_ones, int batch, int L, int H, long N, int nsplit, const uint8_t* mask,
+                    int c_ones, int head_pitch_cols, int batch, int L, int H, long N, int nsplit, const uint8_t* mask,
                     void* mask_bits_scratch, float* part_acc, float* part_ml, void* cuda_stream) {
   // shared_kv: 0 generic, 1 small-context kernel (xattn_small.cu), 2 first-generation small-context kernel
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
@@ -862,6 +877,7 @@ int hn_op_attention(const void* Q, int q_ld, const void* KV, long kv_ld, int k_c
   aa.shared_kv = shared_kv ? 1 : 0;
   aa.legacy_small = shared_kv == 2 ? 1 : 0;
   aa.c_ones = c_ones;
+  aa.hp = head_pitch_cols > 0 ? head_pitch_cols : 64;
   aa.kd = shared_kv ? static_cast<int>(kv_ld) : 64;
   aa.batch = batch;
   aa.L = L;
@@ -880,12 +896,14 @@ int hn_op_attention(const void* Q, int q_ld, const void* KV, long kv_ld, int k_c
 }
 
 int hn_op_combine(const float* part_acc, const float* part_ml, int batch, int nsplit, int H, int L, int small_C,
-                  int zw, int dh, const float* Wv, const float* bv, void* O, int o_ld, void* cuda_stream) {
+                  int zw, int dh, int head_pitch_cols, const float* Wv, const float* bv, void* O, int o_ld,
+                  void* cuda_stream) {
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   if (small_C > 0)
     return launch_combine_vproj(part_acc, part_ml, batch, nsplit, H, L, small_C, zw, dh, Wv, bv,
-                                static_cast<__half*>(O), o_ld, 0, st);
-  return launch_combine_generic(part_acc, part_ml, batch, nsplit, H, L, static_cast<__half*>(O), o_ld, 0, st);
+                                static_cast<__half*>(O), o_ld, 0, head_pitch_cols, st);
+  return launch_combine_generic(part_acc, part_ml, batch, nsplit, H, L, static_cast<__half*>(O), o_ld, 0,
+                                head_pitch_cols, st);
 }
 
 }  // extern "C"

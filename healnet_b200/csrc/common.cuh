@@ -103,6 +103,7 @@ struct AttnArgs {
   int legacy_small = 0;  // shared_kv only: run the first-generation kernel (xattn.cu) instead of xattn_small.cu
   int shared_kv;  // 1 = small-C path
   int kd;         // operand width per head: 64 generic; 32 or 64 (= z row width) on the small-C path
+  int hp = 64;    // generic path: head pitch in Q / K / V columns and accumulator width, 64 or 128 (dim_head > 64)
   int batch, L, H;
   long N;
   int nsplit;
@@ -116,14 +117,14 @@ int attention_pick_nsplit(int batch, int L, int H, long N);
 int launch_small_attention(const AttnArgs& a, cudaStream_t stream);
 int small_attention_pick_nsplit(int batch, int L, int H, long N, int kd);
 
-// combine split partials. generic: O[b*L][h*64+d] = sum_s w_s acc_s[d] / sum_s w_s l_s   (fp16, ld = o_ld)
+// combine split partials. generic: O[b*L][h*hp+d] = sum_s w_s acc_s[d] / sum_s w_s l_s   (fp16, ld = o_ld)
 // (lo_seg > 0: O rows are split [hi | lo], lo at column + lo_seg)
 int launch_combine_generic(const float* part_acc, const float* part_ml, int batch, int nsplit, int H, int L,
-                           __half* O, int o_ld, int lo_seg, cudaStream_t stream);
+                           __half* O, int o_ld, int lo_seg, int hp, cudaStream_t stream);
 // small-C: u = sum_s w_s acc_s[0..C) / sum_s w_s acc_s[C];  O[b*L][h*64+d] = u . Wv[h*dh+d][:] + bv[h*dh+d]
 int launch_combine_vproj(const float* part_acc, const float* part_ml, int batch, int nsplit, int H, int L, int C,
                          int zw, int dh, const float* Wv /*[H*dh][zw]*/, const float* bv /*[H*dh]*/, __half* O,
-                         int o_ld, int lo_seg, cudaStream_t stream);
+                         int o_ld, int lo_seg, int hp, cudaStream_t stream);
 // x[b][i] = src[i]  (latent broadcast, healnet.py:225)
 int launch_broadcast_rows(const float* src, float* dst, long n, int batch, cudaStream_t stream);
 

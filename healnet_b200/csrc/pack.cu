@@ -1,7 +1,8 @@
 // pack.cu — one-time (per weight version) repacking of reference-format fp32 parameters into the fp16
 // operand layouts the tensor-core kernels consume. Runs on the device; nothing here is on the per-forward
 // path. Layout conventions:
-//   * heads are padded to 64 columns ("head-padded"): column h*64+d holds head h, dim d (zero for d >= dh)
+//   * heads are padded to a pitch hp of 64 (dim_head <= 64) or 128 columns ("head-padded"): column h*hp+d holds
+//     head h, dim d (zero for d >= dh)
 //   * softmax scale 2/sqrt(dh) (healnet.py:375,409,419) times log2(e) is folded into the Q projection
 //   * context LayerNorm affine (gamma, beta; healnet.py:310-311,318) is folded into the K/V projection
 //   * FeedForward first Linear rows are interleaved (a_j, g_j) so the gate fuses into the GEMM epilogue
@@ -17,13 +18,13 @@ __device__ __forceinline__ void put_split(__half* row, int k, int lo_off, float 
   if (lo_off > 0) row[lo_off + k] = __float2half_rn(v - __half2float(hi));
 }
 
-// dst[(dst_row0 + h*64 + d)][k] = scale * src[(src_row0 + h*dh + d)][k] * (colscale ? colscale[k] : 1)
+// dst[(dst_row0 + h*hp + d)][k] = scale * src[(src_row0 + h*dh + d)][k] * (colscale ? colscale[k] : 1)
 __global__ void pack_headpad_rows_kernel(__half* __restrict__ dst, int ld_dst, int dst_row0,
                                          const float* __restrict__ src, int ld_src, int src_row0, int n_heads,
                                          int dh, int K, float scale, const float* __restrict__ colscale, int seg,
-                                         int lo_off) {
-  const int r = blockIdx.x;  // 0 .. n_heads*64
-  const int h = r / 64, d = r % 64;
+                                         int lo_off, int hp) {
+  const int r = blockIdx.x;  // 0 .. n_heads*hp
+  const int h = r / hp, d = r % hp;
   __half* out = dst + static_cast<size_t>(dst_row0 + r) * ld_dst;
   const float* in = src + static_cast<size_t>(src_row0 + h * dh + d) * ld_src;
   for (int k = threadIdx.x; k < seg; k += blockDim.x) {
@@ -33,12 +34,12 @@ __global__ void pack_headpad_rows_kernel(__half* __restrict__ dst, int ld_dst, i
   }
 }
 
-// dst[r][h*64 + d] = src[r][h*dh + d]
+// dst[r][h*hp + d] = src[r][h*dh + d]
 __global__ void pack_headpad_cols_kernel(__half* __restrict__ dst, int ld_dst, const float* __restrict__ src,
-                                         int ld_src, int n_heads, int dh, int seg, int lo_off) {
+                                         int ld_src, int n_heads, int dh, int seg, int lo_off, int hp) {
   const int r = blockIdx.x;
   for (int c = threadIdx.x; c < seg; c += blockDim.x) {
-    const int h = c / 64, d = c % 64;
+    const int h = c / hp, d = c % hp;
     float v = 0.f;
     if (h < n_heads && d < dh) v = src[static_cast<size_t>(r) * ld_src + h * dh + d];
     put_split(dst + static_cast<size_t>(r) * ld_dst, c, lo_off, v);
@@ -65,14 +66,14 @@ __global__ void pack_plain_kernel(__half* __restrict__ dst, int ld_dst, const fl
     put_split(dst + static_cast<size_t>(r) * ld_dst, k, lo_off, k < K ? src[static_cast<size_t>(r) * ld_src + k] : 0.f);
 }
 
-// bias_dst[dst_row0 + h*64 + d] = sum_c W[(src_row0 + h*dh + d)][c] * beta[c]
+// bias_dst[dst_row0 + h*hp + d] = sum_c W[(src_row0 + h*dh + d)][c] * beta[c]
 __global__ void fold_beta_headpad_kernel(float* __restrict__ bias_dst, int dst_row0, const float* __restrict__ W,
                                          int ld, int src_row0, int n_heads, int dh, int C,
-                                         const float* __restrict__ beta) {
+                                         const float* __restrict__ beta, int hp) {
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (r >= n_heads * 64) return;
-  const int h = r / 64, d = r % 64;
+  if (r >= n_heads * hp) return;
+  const int h = r / hp, d = r % hp;
   float acc = 0.f;
   if (d < dh) {
     const float* w = W + static_cast<size_t>(src_row0 + h * dh + d) * ld;
@@ -124,16 +125,16 @@ __global__ void pack_smallc_v_kernel(float* __restrict__ Wv_dst, float* __restri
   } while (0)
 
 int pack_headpad_rows(__half* dst, int ld_dst, int dst_row0, const float* src, int ld_src, int src_row0,
-                      int n_heads, int dh, int K, float scale, const float* colscale, int seg, int lo_off,
+                      int n_heads, int dh, int K, float scale, const float* colscale, int seg, int lo_off, int hp,
                       cudaStream_t st) {
-  pack_headpad_rows_kernel<<<n_heads * 64, 128, 0, st>>>(dst, ld_dst, dst_row0, src, ld_src, src_row0, n_heads, dh, K,
-                                                        scale, colscale, seg, lo_off);
+  pack_headpad_rows_kernel<<<n_heads * hp, 128, 0, st>>>(dst, ld_dst, dst_row0, src, ld_src, src_row0, n_heads, dh, K,
+                                                        scale, colscale, seg, lo_off, hp);
   PACK_LAUNCH_CHECK();
   return 0;
 }
 int pack_headpad_cols(__half* dst, int ld_dst, const float* src, int ld_src, int rows, int n_heads, int dh, int seg,
-                      int lo_off, cudaStream_t st) {
-  pack_headpad_cols_kernel<<<rows, 128, 0, st>>>(dst, ld_dst, src, ld_src, n_heads, dh, seg, lo_off);
+                      int lo_off, int hp, cudaStream_t st) {
+  pack_headpad_cols_kernel<<<rows, 128, 0, st>>>(dst, ld_dst, src, ld_src, n_heads, dh, seg, lo_off, hp);
   PACK_LAUNCH_CHECK();
   return 0;
 }
@@ -150,9 +151,10 @@ int pack_plain(__half* dst, int ld_dst, const float* src, int ld_src, int rows, 
   return 0;
 }
 int fold_beta_headpad(float* bias_dst, int dst_row0, const float* W, int ld, int src_row0, int n_heads, int dh,
-                      int C, const float* beta, cudaStream_t st) {
-  const int rows = n_heads * 64;
-  fold_beta_headpad_kernel<<<(rows + 3) / 4, 128, 0, st>>>(bias_dst, dst_row0, W, ld, src_row0, n_heads, dh, C, beta);
+                      int C, const float* beta, int hp, cudaStream_t st) {
+  const int rows = n_heads * hp;
+  fold_beta_headpad_kernel<<<(rows + 3) / 4, 128, 0, st>>>(bias_dst, dst_row0, W, ld, src_row0, n_heads, dh, C, beta,
+                                                          hp);
   PACK_LAUNCH_CHECK();
   return 0;
 }

@@ -317,11 +317,11 @@ __global__ void pack_mask_kernel(const uint8_t* __restrict__ mask, uint64_t* __r
 }
 
 // ------------------------------------------------------------------ split combine
-// part_acc [b][s][h][L][VD], part_ml [b][s][h][L][2]; one warp per (b, l, h)
+// part_acc [b][s][h][L][hp], part_ml [b][s][h][L][2]; one warp per (b, l, h); hp = 64 | 128 accumulator columns
 __global__ void __launch_bounds__(256) combine_generic_kernel(const float* __restrict__ part_acc,
                                                               const float* __restrict__ part_ml, int batch,
                                                               int nsplit, int H, int L, __half* __restrict__ O,
-                                                              int o_ld, int lo_seg) {
+                                                              int o_ld, int lo_seg, int hp) {
   const int lane = threadIdx.x & 31;
   const long wid = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long total = static_cast<long>(batch) * L * H;
@@ -333,23 +333,27 @@ __global__ void __launch_bounds__(256) combine_generic_kernel(const float* __res
   for (int s = lane; s < nsplit; s += 32)
     M = fmaxf(M, part_ml[((((static_cast<long>(b) * nsplit + s) * H + h) * L) + l) * 2]);
   M = warp_max(M);
-  float a0 = 0.f, a1 = 0.f, den = 0.f;
+  float a[4] = {0.f, 0.f, 0.f, 0.f};
+  float den = 0.f;
+  const int nv = hp / 32;
   for (int s = 0; s < nsplit; ++s) {
     const long base = (((static_cast<long>(b) * nsplit + s) * H + h) * L) + l;
     const float m = part_ml[base * 2], ls = part_ml[base * 2 + 1];
     const float w = (m == -INFINITY) ? 0.f : exp2f(m - M);
-    a0 += w * part_acc[base * 64 + lane];
-    a1 += w * part_acc[base * 64 + 32 + lane];
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+      if (v < nv) a[v] += w * part_acc[base * hp + v * 32 + lane];
     den += w * ls;
   }
   const float inv = 1.f / den;
-  __half* o = O + (static_cast<long>(b) * L + l) * o_ld + h * 64;
-  store_split(o, lane, 0, lo_seg, a0 * inv);
-  store_split(o, lane + 32, 0, lo_seg, a1 * inv);
+  __half* o = O + (static_cast<long>(b) * L + l) * o_ld + h * hp;
+#pragma unroll
+  for (int v = 0; v < 4; ++v)
+    if (v < nv) store_split(o, v * 32 + lane, 0, lo_seg, a[v] * inv);
 }
 
 // small-C: acc rows are zw wide: [sum_t p z_c (c < C), sum_t p (col C), 0...]; then the V projection
-// O[b*L + l][h*64 + d] = (u / den) . Wv'[h*dh + d][:] + bv[h*dh + d].
+// O[b*L + l][h*hp + d] = (u / den) . Wv'[h*dh + d][:] + bv[h*dh + d], hp = 64 | 128 output columns per head.
 // Block = (32 latent rows, head, sample): warp w merges the splits of 4 rows (lane = column), the head's Wv' sits
 // transposed in shared memory so the projection reads are conflict-free broadcasts.
 __global__ void __launch_bounds__(256) combine_vproj_kernel(const float* __restrict__ part_acc,
@@ -357,12 +361,12 @@ __global__ void __launch_bounds__(256) combine_vproj_kernel(const float* __restr
                                                             int nsplit, int H, int L, int C, int zw, int dh,
                                                             const float* __restrict__ Wv,
                                                             const float* __restrict__ bv, __half* __restrict__ O,
-                                                            int o_ld, int lo_seg) {
-  __shared__ float wT[64][65];   // wT[c][d] = Wv'[h*dh + d][c]
+                                                            int o_ld, int lo_seg, int hp) {
+  __shared__ float wT[64][129];  // wT[c][d] = Wv'[h*dh + d][c]
   __shared__ float u_s[32][65];  // merged, normalised rows
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int l0 = blockIdx.x * 32, h = blockIdx.y, b = blockIdx.z;
-  for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+  for (int i = threadIdx.x; i < hp * 64; i += 256) {
     const int d = i / 64, c = i % 64;
     wT[c][d] = (d < dh && c < C) ? Wv[static_cast<long>(h * dh + d) * zw + c] : 0.f;
   }
@@ -386,16 +390,16 @@ __global__ void __launch_bounds__(256) combine_vproj_kernel(const float* __restr
     u_s[r][lane + 32] = acc1;
   }
   __syncthreads();
-  // 32 rows x 64 output columns = 2048 outputs over 256 threads
-  for (int i = threadIdx.x; i < 32 * 64; i += 256) {
-    const int r = i / 64, d = i % 64, l = l0 + r;
+  // 32 rows x hp output columns over 256 threads
+  for (int i = threadIdx.x; i < 32 * hp; i += 256) {
+    const int r = i / hp, d = i % hp, l = l0 + r;
     if (l >= L) continue;
     float out = 0.f;
     if (d < dh) {
       for (int c = 0; c < C; ++c) out += u_s[r][c] * wT[c][d];
       out = out / u_s[r][C] + bv[h * dh + d];
     }
-    __half* o = O + (static_cast<long>(b) * L + l) * o_ld + h * 64;
+    __half* o = O + (static_cast<long>(b) * L + l) * o_ld + h * hp;
     store_split(o, d, 0, lo_seg, out);
   }
 }
@@ -496,20 +500,22 @@ int launch_pack_mask(const uint8_t* mask, uint64_t* bits, int batch, long N, cud
 }
 
 int launch_combine_generic(const float* part_acc, const float* part_ml, int batch, int nsplit, int H, int L,
-                           __half* O, int o_ld, int lo_seg, cudaStream_t stream) {
+                           __half* O, int o_ld, int lo_seg, int hp, cudaStream_t stream) {
+  HN_REQUIRE(hp == 64 || hp == 128, "combine: head pitch must be 64 or 128");
   const long total = static_cast<long>(batch) * L * H;
-  combine_generic_kernel<<<static_cast<unsigned>((total + 7) / 8), 256, 0, stream>>>(part_acc, part_ml, batch,
-                                                                                      nsplit, H, L, O, o_ld, lo_seg);
+  combine_generic_kernel<<<static_cast<unsigned>((total + 7) / 8), 256, 0, stream>>>(
+      part_acc, part_ml, batch, nsplit, H, L, O, o_ld, lo_seg, hp);
   HN_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_combine_vproj(const float* part_acc, const float* part_ml, int batch, int nsplit, int H, int L, int C,
-                         int zw, int dh, const float* Wv, const float* bv, __half* O, int o_ld, int lo_seg,
+                         int zw, int dh, const float* Wv, const float* bv, __half* O, int o_ld, int lo_seg, int hp,
                          cudaStream_t stream) {
-  HN_REQUIRE((zw == 32 || zw == 64) && C <= zw - 1 && dh <= 64, "combine_vproj: C < zw and dim_head <= 64 required");
+  HN_REQUIRE((zw == 32 || zw == 64) && C <= zw - 1 && (hp == 64 || hp == 128) && dh <= hp,
+             "combine_vproj: C < zw and dim_head <= head pitch (64 | 128) required");
   combine_vproj_kernel<<<dim3((L + 31) / 32, H, batch), 256, 0, stream>>>(part_acc, part_ml, batch, nsplit, H, L, C,
-                                                                             zw, dh, Wv, bv, O, o_ld, lo_seg);
+                                                                             zw, dh, Wv, bv, O, o_ld, lo_seg, hp);
   HN_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

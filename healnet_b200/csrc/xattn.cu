@@ -52,19 +52,25 @@ struct AttnDev {
 // PREC (generic path only): operands arrive split as hi + lo fp16 pairs; S = Qh.Kh + Ql.Kh + Qh.Kl and
 // U += P.Vh + P.Vl. Used for short token axes (latent self-attention, tabular rows, small bags of patches),
 // where per-token fp16 rounding of Q/K/V would not average out under the softmax.
-template <int KD, bool SHARED, bool PREC>
-__global__ void __launch_bounds__(192, 2)
+// NA = 64-column atoms per head (generic path): 1 for dim_head <= 64, 2 for dim_head <= 128 (head pitch 128):
+// S accumulates over both atoms, U is NA * 64 columns wide (one N = 64 UMMA per atom and k-step).
+template <int KD, bool SHARED, bool PREC, int NA>
+__global__ void __launch_bounds__(192, NA == 1 ? 2 : 1)
 attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, AttnDev p) {
   static_assert(!(SHARED && PREC), "the precise mode exists on the generic path only");
-  constexpr int NSTAGE = PREC ? 2 : 4;  // K/V smem ring depth
-  constexpr int VD = KD;
-  constexpr int Q_TILE = BM * KD * 2;
-  constexpr int Q_BYTES = PREC ? 2 * Q_TILE : Q_TILE;
-  constexpr int K_BYTES = BT * KD * 2;
-  constexpr int STAGE_BYTES = SHARED ? K_BYTES : (PREC ? 4 * K_BYTES : 2 * K_BYTES);  // [K | V | K_lo | V_lo]
+  static_assert(NA == 1 || (!SHARED && KD == 64), "two atoms per head exist on the generic path only");
+  constexpr int NSTAGE = (PREC || NA == 2) ? 2 : 4;  // K/V smem ring depth
+  constexpr int VD = KD * NA;
+  constexpr int HP = KD * NA;                        // head pitch in columns
+  constexpr int Q_TILE = BM * KD * 2;                // one atom of Q
+  constexpr int Q_BYTES = (PREC ? 2 : 1) * NA * Q_TILE;   // [Q atoms | Q_lo atoms]
+  constexpr int K_BYTES = BT * KD * 2;               // one atom of K or V
+  // stage: [K atoms | V atoms | K_lo atoms | V_lo atoms]
+  constexpr int STAGE_BYTES = SHARED ? K_BYTES : (PREC ? 4 : 2) * NA * K_BYTES;
+  constexpr uint32_t TCOLS = (NA == 1) ? 256 : 512;  // S 2x64 | P 2x32 | U VD
   constexpr uint32_t LAYOUT = (KD == 64) ? SWZ_128B : SWZ_64B;
   constexpr uint32_t SBO = 8 * KD * 2;        // 8-row group pitch of a swizzled tile
-  constexpr uint32_t V_KADV = 16 * VD * 2;    // MN-major B: 16 tokens (one UMMA K step) further down
+  constexpr uint32_t V_KADV = 16 * KD * 2;    // MN-major B: 16 tokens (one UMMA K step) further down
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -112,7 +118,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     mbar_init(&acc_done, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<256>(&tmem_base_s);
+  if (warp == 1) tmem_alloc<TCOLS>(&tmem_base_s);
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -125,20 +131,27 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       tma_prefetch_desc(&tmQ);
       tma_prefetch_desc(&tmKV);
       mbar_arrive_expect_tx(&q_full, Q_BYTES);
-      tma_load_3d(sQ, &tmQ, &q_full, h * KD, lt * BM, b);
-      if (PREC) tma_load_3d(sQ + Q_TILE, &tmQ, &q_full, p.q_lo_off + h * KD, lt * BM, b);
-      const int kcol = SHARED ? 0 : p.k_col0 + h * KD;
-      const int vcol = SHARED ? 0 : p.v_col0 + h * KD;
+#pragma unroll
+      for (int a = 0; a < NA; ++a) {
+        tma_load_3d(sQ + a * Q_TILE, &tmQ, &q_full, h * HP + a * KD, lt * BM, b);
+        if (PREC) tma_load_3d(sQ + (NA + a) * Q_TILE, &tmQ, &q_full, p.q_lo_off + h * HP + a * KD, lt * BM, b);
+      }
+      const int kcol = SHARED ? 0 : p.k_col0 + h * HP;
+      const int vcol = SHARED ? 0 : p.v_col0 + h * HP;
       for (int i = 0; i < n; ++i) {
         const int s = i % NSTAGE;
         mbar_wait(&kv_empty[s], ((i / NSTAGE) & 1) ^ 1);
         mbar_arrive_expect_tx(&kv_full[s], STAGE_BYTES);
         const int tok0 = (t_begin + i) * BT;
-        tma_load_3d(sKV + s * STAGE_BYTES, &tmKV, &kv_full[s], kcol, tok0, b);
-        if (!SHARED) tma_load_3d(sKV + s * STAGE_BYTES + K_BYTES, &tmKV, &kv_full[s], vcol, tok0, b);
-        if (PREC) {
-          tma_load_3d(sKV + s * STAGE_BYTES + 2 * K_BYTES, &tmKV, &kv_full[s], p.kv_lo_off + kcol, tok0, b);
-          tma_load_3d(sKV + s * STAGE_BYTES + 3 * K_BYTES, &tmKV, &kv_full[s], p.kv_lo_off + vcol, tok0, b);
+        uint8_t* st = sKV + s * STAGE_BYTES;
+#pragma unroll
+        for (int a = 0; a < NA; ++a) {
+          tma_load_3d(st + a * K_BYTES, &tmKV, &kv_full[s], kcol + a * KD, tok0, b);
+          if (!SHARED) tma_load_3d(st + (NA + a) * K_BYTES, &tmKV, &kv_full[s], vcol + a * KD, tok0, b);
+          if (PREC) {
+            tma_load_3d(st + (2 * NA + a) * K_BYTES, &tmKV, &kv_full[s], p.kv_lo_off + kcol + a * KD, tok0, b);
+            tma_load_3d(st + (3 * NA + a) * K_BYTES, &tmKV, &kv_full[s], p.kv_lo_off + vcol + a * KD, tok0, b);
+          }
         }
       }
     }
@@ -146,7 +159,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     // ------------------------------------------------------------ UMMA issuer
     if (elect_one()) {
       constexpr uint32_t idesc_s = idesc_f16(BM, BT, false, false);  // S[128x64]  = Q[128xKD] . K[64xKD]^T
-      constexpr uint32_t idesc_u = idesc_f16(BM, VD, false, true);   // U[128xVD] += P[128x64] . V[64xVD] (MN-major B)
+      constexpr uint32_t idesc_u = idesc_f16(BM, KD, false, true);   // U[128xKD] += P[128x64] . V[64xKD] per atom (MN-major B)
       const uint32_t q0 = smem_u32(sQ);
       auto issue_s = [&](int j) {
         const int s = j % NSTAGE;
@@ -154,18 +167,21 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         fence_after_sync();
         const uint32_t k0 = smem_u32(sKV + s * STAGE_BYTES);
 #pragma unroll
-        for (int k = 0; k < KD / 16; ++k)
-          umma_ss(tS0 + (j & 1) * 64, smem_desc(q0 + k * 32, 16, SBO, LAYOUT), smem_desc(k0 + k * 32, 16, SBO, LAYOUT),
-                  idesc_s, k != 0);
-        if (PREC) {
+        for (int a = 0; a < NA; ++a) {
 #pragma unroll
-          for (int k = 0; k < KD / 16; ++k)  // Q_lo . K_hi
-            umma_ss(tS0 + (j & 1) * 64, smem_desc(q0 + Q_TILE + k * 32, 16, SBO, LAYOUT),
-                    smem_desc(k0 + k * 32, 16, SBO, LAYOUT), idesc_s, true);
+          for (int k = 0; k < KD / 16; ++k)
+            umma_ss(tS0 + (j & 1) * 64, smem_desc(q0 + a * Q_TILE + k * 32, 16, SBO, LAYOUT),
+                    smem_desc(k0 + a * K_BYTES + k * 32, 16, SBO, LAYOUT), idesc_s, (a | k) != 0);
+          if (PREC) {
 #pragma unroll
-          for (int k = 0; k < KD / 16; ++k)  // Q_hi . K_lo
-            umma_ss(tS0 + (j & 1) * 64, smem_desc(q0 + k * 32, 16, SBO, LAYOUT),
-                    smem_desc(k0 + 2 * K_BYTES + k * 32, 16, SBO, LAYOUT), idesc_s, true);
+            for (int k = 0; k < KD / 16; ++k)  // Q_lo . K_hi
+              umma_ss(tS0 + (j & 1) * 64, smem_desc(q0 + (NA + a) * Q_TILE + k * 32, 16, SBO, LAYOUT),
+                      smem_desc(k0 + a * K_BYTES + k * 32, 16, SBO, LAYOUT), idesc_s, true);
+#pragma unroll
+            for (int k = 0; k < KD / 16; ++k)  // Q_hi . K_lo
+              umma_ss(tS0 + (j & 1) * 64, smem_desc(q0 + a * Q_TILE + k * 32, 16, SBO, LAYOUT),
+                      smem_desc(k0 + (2 * NA + a) * K_BYTES + k * 32, 16, SBO, LAYOUT), idesc_s, true);
+          }
         }
         umma_commit(&s_full[j & 1]);
       };
@@ -176,15 +192,19 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         const int s = i % NSTAGE;
         mbar_wait(&p_ready[i & 1], (i >> 1) & 1);
         fence_after_sync();
-        const uint32_t v0 = smem_u32(sKV + s * STAGE_BYTES + (SHARED ? 0 : K_BYTES));
+        const uint32_t v0 = smem_u32(sKV + s * STAGE_BYTES + (SHARED ? 0 : NA * K_BYTES));
 #pragma unroll
-        for (int k = 0; k < BT / 16; ++k)
-          umma_ts(tU, tP0 + (i & 1) * 32 + k * 8, smem_desc(v0 + k * V_KADV, 16, SBO, LAYOUT), idesc_u, (i | k) != 0);
-        if (PREC) {
+        for (int a = 0; a < NA; ++a) {
 #pragma unroll
-          for (int k = 0; k < BT / 16; ++k)  // P . V_lo
-            umma_ts(tU, tP0 + (i & 1) * 32 + k * 8, smem_desc(v0 + 2 * K_BYTES + k * V_KADV, 16, SBO, LAYOUT), idesc_u,
-                    true);
+          for (int k = 0; k < BT / 16; ++k)
+            umma_ts(tU + a * KD, tP0 + (i & 1) * 32 + k * 8, smem_desc(v0 + a * K_BYTES + k * V_KADV, 16, SBO, LAYOUT),
+                    idesc_u, (i | k) != 0);
+          if (PREC) {
+#pragma unroll
+            for (int k = 0; k < BT / 16; ++k)  // P . V_lo
+              umma_ts(tU + a * KD, tP0 + (i & 1) * 32 + k * 8,
+                      smem_desc(v0 + (2 * NA + a) * K_BYTES + k * V_KADV, 16, SBO, LAYOUT), idesc_u, true);
+          }
         }
         umma_commit(&kv_empty[s]);
         umma_commit(&u_done);
@@ -292,10 +312,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<256>(tmem);
+  if (warp == 1) tmem_dealloc<TCOLS>(tmem);
 }
 
-template <int KD, bool SHARED, bool PREC>
+template <int KD, bool SHARED, bool PREC, int NA>
 int launch_t(const AttnArgs& a, cudaStream_t stream) {
   CUtensorMap tmQ, tmKV;
   const CUtensorMapSwizzle swz = KD == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -321,16 +341,14 @@ int launch_t(const AttnArgs& a, cudaStream_t stream) {
   p.mask_bits = a.mask_bits;
   p.part_acc = a.part_acc;
   p.part_ml = a.part_ml;
-  constexpr int SMEM = (PREC ? 2 : 1) * BM * KD * 2 + (PREC ? 2 * 4 : 4 * (SHARED ? 1 : 2)) * BT * KD * 2 + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    HN_CHECK_CUDA(
-        cudaFuncSetAttribute(attn_kernel<KD, SHARED, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr_set = true;
-  }
+  constexpr int NSTAGE = (PREC || NA == 2) ? 2 : 4;
+  constexpr int SMEM = (PREC ? 2 : 1) * NA * BM * KD * 2 +
+                       NSTAGE * (SHARED ? 1 : (PREC ? 4 : 2) * NA) * BT * KD * 2 + 1024;
+  HN_CHECK_CUDA(
+      cudaFuncSetAttribute(attn_kernel<KD, SHARED, PREC, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
   const long grid = static_cast<long>(p.n_ltiles) * a.H * a.batch * a.nsplit;
   HN_REQUIRE(grid > 0 && grid < 2147483647L, "attention: grid too large");
-  attn_kernel<KD, SHARED, PREC><<<static_cast<unsigned>(grid), 192, SMEM, stream>>>(tmQ, tmKV, p);
+  attn_kernel<KD, SHARED, PREC, NA><<<static_cast<unsigned>(grid), 192, SMEM, stream>>>(tmQ, tmKV, p);
   HN_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -368,14 +386,16 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
     HN_REQUIRE(a.kd == 32 || a.kd == 64, "attention: shared-context rows must be 32 or 64 wide");
     HN_REQUIRE(a.kv_ld == a.kd, "attention: shared-context rows must be dense");
     HN_REQUIRE(!a.precise, "attention: the precise mode exists on the generic path only");
-    if (a.legacy_small) return a.kd == 32 ? launch_t<32, true, false>(a, stream) : launch_t<64, true, false>(a, stream);
+    if (a.legacy_small)
+      return a.kd == 32 ? launch_t<32, true, false, 1>(a, stream) : launch_t<64, true, false, 1>(a, stream);
     return launch_small_attention(a, stream);
   }
+  HN_REQUIRE(a.hp == 64 || a.hp == 128, "attention: head pitch must be 64 or 128");
   if (a.precise) {
     HN_REQUIRE(a.q_lo_off > 0 && a.kv_lo_off > 0, "attention: precise mode needs the lo-part offsets");
-    return launch_t<64, false, true>(a, stream);
+    return a.hp == 64 ? launch_t<64, false, true, 1>(a, stream) : launch_t<64, false, true, 2>(a, stream);
   }
-  return launch_t<64, false, false>(a, stream);
+  return a.hp == 64 ? launch_t<64, false, false, 1>(a, stream) : launch_t<64, false, false, 2>(a, stream);
 }
 
 }  // namespace hn

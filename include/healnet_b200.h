@@ -42,6 +42,7 @@ typedef struct hn_desc {
   int num_freq_bands;
   int out_dims;
   int self_per_cross_attn;   /* 0 or 1 (the reference breaks for >= 2, healnet.py:242) */
+  /* cross_dim_head and latent_dim_head: 1..128 (latent_dim_head is unused when self_per_cross_attn == 0) */
   int snn;                   /* 1: a*selu(g) gate, 0: a*gelu(g) (healnet.py:323-331,342) */
   int final_classifier_head;
   int fourier_encode_data;
@@ -140,12 +141,13 @@ HN_API int hn_op_build_context(const float* raw, void* z, int ldz, int small, in
 HN_API int hn_op_attention_nsplit(int batch, int L, int H, long N, int small_kd);
 /* Streaming attention partials + combine. shared_kv != 0: small-C path (Q rows kv_ld = 32 | 64 wide per head,
  * KV = z rows whose column c_ones is 1.0; Q column c_ones must be 0); part_acc rows are kv_ld (small-C) or 64
- * (generic) floats wide. */
+ * (generic: head_pitch = 64 | 128) floats wide; head_pitch is the column pitch of one head in Q / K / V / O. */
 HN_API int hn_op_attention(const void* Q, int q_ld, const void* KV, long kv_ld, int k_col0, int v_col0, int shared_kv,
-                           int c_ones, int batch, int L, int H, long N, int nsplit, const uint8_t* mask,
+                           int c_ones, int head_pitch, int batch, int L, int H, long N, int nsplit, const uint8_t* mask,
                            void* mask_bits_scratch, float* part_acc, float* part_ml, void* cuda_stream);
 HN_API int hn_op_combine(const float* part_acc, const float* part_ml, int batch, int nsplit, int H, int L, int small_C,
-                  int zw, int dh, const float* Wv, const float* bv, void* O, int o_ld, void* cuda_stream);
+                         int zw, int dh, int head_pitch, const float* Wv, const float* bv, void* O, int o_ld,
+                         void* cuda_stream);
 /* test-only: one-tile UMMA/TMA/TMEM convention probe (probe.cu) */
 HN_API int hn_debug_probe(const void* Q, const void* K, const void* V, int kd, int vd, float* S_out, float* U_out,
                    const int* overrides, void* cuda_stream);

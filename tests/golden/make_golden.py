@@ -68,6 +68,19 @@ CASES = {
                     fourier_encode_data=False, final_classifier_head=False, self_per_cross_attn=0),
         shapes=[(2, 5, 10), (2, 9, 7, 50)], seed=3),
     # more than one 128-row latent tile, more than one 64-token tile with a ragged tail, default head sizes
+    # tuned production hyper-parameters of the reference (config/best_hyperparams.yml, ucec): one cross head of
+    # 103 dims (> 64: two 64-column atoms per head), tiny odd latent array, no latent self-attention (so the
+    # latent_dim_head of 51 is unused), max_freq 2
+    "prod_ucec": dict(
+        kwargs=dict(n_modalities=2, channel_dims=[120, 80], num_spatial_axes=[1, 1], out_dims=4, depth=2,
+                    l_c=16, l_d=65, x_heads=1, l_heads=8, cross_dim_head=103, latent_dim_head=51,
+                    self_per_cross_attn=0, max_freq=2.0),
+        shapes=[(3, 1, 120), (3, 90, 80)], seed=5),
+    # wide heads on both sides: cross 2 x 80, latent 2 x 100 (kirp / blca use latent_dim_head 113 / 127)
+    "wide_heads": dict(
+        kwargs=dict(n_modalities=2, channel_dims=[30, 3], num_spatial_axes=[1, 2], out_dims=3, depth=2,
+                    l_c=40, l_d=48, x_heads=2, l_heads=2, cross_dim_head=80, latent_dim_head=100),
+        shapes=[(2, 4, 30), (2, 9, 11, 3)], seed=6),
     "two_ltiles": dict(
         kwargs=dict(n_modalities=2, channel_dims=[5, 3], num_spatial_axes=[1, 2], out_dims=2, depth=1,
                     l_c=130, l_d=64, x_heads=2, l_heads=2, cross_dim_head=64, latent_dim_head=64),

@@ -148,11 +148,11 @@ def test_generic_attention_kernel(b, H, L, N, nsplit, masked):
     ml_v = ml.view(-1)[: b * nsplit * H * L * 2]
     bits = torch.zeros(b * ((N + 63) // 64), dtype=torch.int64, device="cuda")
     mk = mask.to(torch.uint8).contiguous() if masked else None
-    rc = lib.hn_op_attention(q.data_ptr(), H * 64, kv.data_ptr(), 2 * H * 64, 0, H * 64, 0, 0, b, L, H, N, nsplit,
+    rc = lib.hn_op_attention(q.data_ptr(), H * 64, kv.data_ptr(), 2 * H * 64, 0, H * 64, 0, 0, 64, b, L, H, N, nsplit,
                              mk.data_ptr() if masked else None, bits.data_ptr(), acc_v.data_ptr(), ml_v.data_ptr(), st)
     assert rc == 0, _lib.last_error()
     out = torch.zeros(b * L, H * 64, dtype=torch.float16, device="cuda")
-    assert lib.hn_op_combine(acc_v.data_ptr(), ml_v.data_ptr(), b, nsplit, H, L, 0, 0, 64, None, None, out.data_ptr(),
+    assert lib.hn_op_combine(acc_v.data_ptr(), ml_v.data_ptr(), b, nsplit, H, L, 0, 0, 64, 64, None, None, out.data_ptr(),
                              H * 64, st) == 0
     qh = q.float().view(b, L, H, 64).permute(0, 2, 1, 3)
     kh = kv[..., :H * 64].float().view(b, N, H, 64).permute(0, 2, 1, 3)
@@ -192,7 +192,7 @@ def test_small_context_attention_kernel(kd, C, b, H, L, N, masked):
         ml = torch.full((b * nsplit * H * n_lt * 128 * 2,), float("nan"), device="cuda")
         bits = torch.zeros(b * ((N + 63) // 64), dtype=torch.int64, device="cuda")
         mk = mask.to(torch.uint8).contiguous() if masked else None
-        rc = lib.hn_op_attention(q.data_ptr(), H * kd, z.data_ptr(), kd, 0, 0, variant, C, b, L, H, N, nsplit,
+        rc = lib.hn_op_attention(q.data_ptr(), H * kd, z.data_ptr(), kd, 0, 0, variant, C, 64, b, L, H, N, nsplit,
                                  mk.data_ptr() if masked else None, bits.data_ptr(), acc.data_ptr(), ml.data_ptr(), st)
         assert rc == 0, _lib.last_error()
         # combine with an identity V projection: Wv = I (C x C), bias 0 -> O[:, h*64 + d] = u_d / den for d < C
@@ -202,7 +202,7 @@ def test_small_context_attention_kernel(kd, C, b, H, L, N, masked):
             Wv[h * dh:(h + 1) * dh, :dh] = torch.eye(dh, device="cuda")
         bv = torch.zeros(H * dh, device="cuda")
         out = torch.zeros(b * L, H * 64, dtype=torch.float16, device="cuda")
-        assert lib.hn_op_combine(acc.data_ptr(), ml.data_ptr(), b, nsplit, H, L, C, kd, dh, Wv.data_ptr(), bv.data_ptr(),
+        assert lib.hn_op_combine(acc.data_ptr(), ml.data_ptr(), b, nsplit, H, L, C, kd, dh, 64, Wv.data_ptr(), bv.data_ptr(),
                                  out.data_ptr(), H * 64, st) == 0
         got = out.float().view(b, L, H, 64).permute(0, 2, 1, 3)[..., :dh]
         torch.testing.assert_close(got, want[..., :dh], rtol=3e-3, atol=3e-3)
@@ -227,13 +227,13 @@ def test_small_context_attention_raises_reference_max():
     nsplit = 2
     acc = torch.full((b * nsplit * H * 128 * kd,), float("nan"), device="cuda")
     ml = torch.full((b * nsplit * H * 128 * 2,), float("nan"), device="cuda")
-    assert lib.hn_op_attention(q.data_ptr(), H * kd, z.data_ptr(), kd, 0, 0, 1, C, b, L, H, N, nsplit, None, None,
+    assert lib.hn_op_attention(q.data_ptr(), H * kd, z.data_ptr(), kd, 0, 0, 1, C, 64, b, L, H, N, nsplit, None, None,
                                acc.data_ptr(), ml.data_ptr(), st) == 0
     Wv = torch.zeros(H * C, kd, device="cuda")
     for h in range(H):
         Wv[h * C:(h + 1) * C, :C] = torch.eye(C, device="cuda")
     out = torch.zeros(b * L, H * 64, dtype=torch.float16, device="cuda")
-    assert lib.hn_op_combine(acc.data_ptr(), ml.data_ptr(), b, nsplit, H, L, C, kd, C, Wv.data_ptr(),
+    assert lib.hn_op_combine(acc.data_ptr(), ml.data_ptr(), b, nsplit, H, L, C, kd, C, 64, Wv.data_ptr(),
                              torch.zeros(H * C, device="cuda").data_ptr(), out.data_ptr(), H * 64, st) == 0
     got = out.float().view(b, L, H, 64).permute(0, 2, 1, 3)[..., :C]
     assert bool(torch.isfinite(got).all())

@@ -16,7 +16,7 @@ from oracle import healnet_oracle as O
 pytestmark = pytest.mark.gpu
 RTOL, ATOL = 1e-3, 1e-4
 LAT_ATOL = 5e-4
-CASES = ["tri_small", "omic_wsi_tied", "plain_no_head", "two_ltiles"]
+CASES = ["tri_small", "omic_wsi_tied", "plain_no_head", "two_ltiles", "prod_ucec", "wide_heads"]
 
 
 def _model(meta, sd):
@@ -124,6 +124,10 @@ ORACLE_CASES = {
     "omic_wsi": (dict(n_modalities=2, channel_dims=[2000, 1024], num_spatial_axes=[1, 1], out_dims=4, l_c=256,
                       l_d=512, depth=2), [(2, 1, 2000), (2, 700, 1024)]),
     # tuned production hyper-parameters (config/best_hyperparams.yml:8-18,30): tiny odd latents, 1 head of 63
+    # long token axis with a wide head: generic streaming path, two atoms per head, non-precise
+    "wide_head_long_axis": (dict(n_modalities=1, channel_dims=[96], num_spatial_axes=[1], out_dims=4, l_c=64, l_d=96,
+                                 x_heads=2, cross_dim_head=103, l_heads=2, latent_dim_head=72, depth=2),
+                            [(2, 3000, 96)]),
     "production_odd": (dict(n_modalities=2, channel_dims=[300, 96], num_spatial_axes=[1, 1], out_dims=4, l_c=25,
                             l_d=119, x_heads=1, cross_dim_head=63, self_per_cross_attn=0),
                        [(3, 1, 300), (3, 333, 96)]),

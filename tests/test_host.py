@@ -12,7 +12,7 @@ from healnet_b200 import _lib
 from healnet_b200 import HealNet, Attention
 from conftest import ROOT
 
-CASES = ["tri_small", "omic_wsi_tied", "plain_no_head", "two_ltiles"]
+CASES = ["tri_small", "omic_wsi_tied", "plain_no_head", "two_ltiles", "prod_ucec", "wide_heads"]
 
 
 def test_library_exports_every_declared_symbol():
@@ -117,7 +117,8 @@ def test_hn_create_validation_and_workspace_sizing():
     assert lib.hn_set_weights(h, 0, 0, arr, 3) != 0
     assert lib.hn_set_weights(h, 5, 0, arr, 3) != 0
     assert lib.hn_destroy(h) == 0
-    for bad in (dict(self_per_cross_attn=2), dict(cross_dim_head=65), dict(depth=0), dict(n_modalities=17),
+    for bad in (dict(self_per_cross_attn=2), dict(cross_dim_head=129), dict(latent_dim_head=129), dict(depth=0),
+                dict(n_modalities=17),
                 dict(l_heads=0)):
         h2 = ctypes.c_void_p()
         d2 = _desc(**bad)

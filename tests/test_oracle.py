@@ -6,7 +6,7 @@ import torch
 
 from oracle import healnet_oracle as O
 
-CASES = ["tri_small", "omic_wsi_tied", "plain_no_head", "two_ltiles"]
+CASES = ["tri_small", "omic_wsi_tied", "plain_no_head", "two_ltiles", "prod_ucec", "wide_heads"]
 
 
 def _cfg(kwargs):
