@@ -520,6 +520,14 @@ int hn_profile_read(hn_handle* h, int modality, float* ms, int* launches, double
 int hn_forward(hn_handle* h, int batch, const void* const* modality_ptrs, const int* axis_sizes,
                const int* skip_latent_block, const uint8_t* mask, long mask_tokens, float* latents_out,
                float* logits_out, void* workspace, size_t workspace_bytes, void* cuda_stream) {
+  return hn_forward_ex(h, batch, modality_ptrs, nullptr, axis_sizes, skip_latent_block, mask, mask_tokens, latents_out,
+                       logits_out, workspace, workspace_bytes, cuda_stream);
+}
+
+int hn_forward_ex(hn_handle* h, int batch, const void* const* modality_ptrs, void* const* modality_ready_events,
+                  const int* axis_sizes, const int* skip_latent_block, const uint8_t* mask, long mask_tokens,
+                  float* latents_out, float* logits_out, void* workspace, size_t workspace_bytes,
+                  void* cuda_stream) {
   HN_REQUIRE(h != nullptr && modality_ptrs != nullptr && axis_sizes != nullptr, "hn_forward: null argument");
   HN_REQUIRE(batch >= 1, "hn_forward: batch must be >= 1");
   HN_REQUIRE(h->packed_valid, "hn_forward: call hn_pack_weights after registering / changing weights");
@@ -552,11 +560,15 @@ int hn_forward(hn_handle* h, int batch, const void* const* modality_ptrs, const 
   const int sD = h->segD;
   if (h->seg4D != 4 * D)  // pad columns of the split hidden rows are never written by the gate epilogue
     HN_CHECK_CUDA(cudaMemsetAsync(ws.hid, 0, sizeof(__half) * rows * 2 * h->seg4D, st));
+  // The standardised context rows of a modality are built right before its first cross-attention (layer 0), after
+  // waiting for the caller's "input ready" event if one was given — so the host-to-device copy of a large late
+  // modality (the volume) overlaps the layer-0 work on the earlier ones.
   bool mask_packed = false;
-  for (int m = 0; m < M; ++m) {
+  auto build_context = [&](int m) -> int {
     ModPlan& mp = ws.mod[m];
-    if (!mp.present) continue;
     const float* raw = static_cast<const float*>(modality_ptrs[m]);
+    if (modality_ready_events != nullptr && modality_ready_events[m] != nullptr)
+      HN_CHECK_CUDA(cudaStreamWaitEvent(st, static_cast<cudaEvent_t>(modality_ready_events[m]), 0));
     if (d.fourier_encode_data)
       HN_TRY(launch_axis_tables(mp.tab, mp.axes, mp.n_axes, d.num_freq_bands, d.max_freq, st));
     if (mp.small)
@@ -569,7 +581,8 @@ int hn_forward(hn_handle* h, int batch, const void* const* modality_ptrs, const 
       HN_TRY(launch_pack_mask(mask, ws.mask_bits, batch, mp.N, st));
       mask_packed = true;
     }
-  }
+    return 0;
+  };
   // ---- x = repeat(latents, 'n d -> b n d')   (healnet.py:225)
   HN_TRY(launch_broadcast_rows(wl[0], ws.x, static_cast<long>(L) * D, batch, st));
 
@@ -577,6 +590,10 @@ int hn_forward(hn_handle* h, int batch, const void* const* modality_ptrs, const 
     for (int m = 0; m < M; ++m) {
       ModPlan& mp = ws.mod[m];
       if (mp.present) {
+        if (l == 0) {
+          rc = build_context(m);
+          if (rc != 0) return rc;
+        }
         const std::vector<const float*>& wa = h->w[slot_index(h, l, 2 * m)];
         const std::vector<const float*>& wf = h->w[slot_index(h, l, 2 * m + 1)];
         const AttnPacked& ap = h->attn[l * (M + 1) + m];

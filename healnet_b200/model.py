@@ -263,11 +263,13 @@ class HealNet(nn.Module):
         self._weights_sig = None
         self._staged = []       # keeps staged fp32 device copies alive while the handle borrows them
         self._workspace = None
+        self._copy_stream = None
         self.last_launch_count = 0
         self._warned = set()
 
     # ------------------------------------------------------------------------------------------------ native
-    _NATIVE_DEFAULTS = dict(_handle=None, _handle_dev=None, _weights_sig=None, _staged=(), _workspace=None)
+    _NATIVE_DEFAULTS = dict(_handle=None, _handle_dev=None, _weights_sig=None, _staged=(), _workspace=None,
+                            _copy_stream=None)
 
     def __getstate__(self):
         """copy.deepcopy / pickle / torch.save(model): the native handle, staged weights and workspace are
@@ -387,6 +389,7 @@ class HealNet(nn.Module):
         batch = None
         ret_dev, ret_dtype = None, None
         staged: List[Optional[torch.Tensor]] = [None] * M
+        ready: List[Optional[torch.cuda.Event]] = [None] * M   # per-modality "copy finished" events (host inputs)
         axis_sizes = (ctypes.c_int * (HN_MAX_MODALITIES * HN_MAX_AXES))()
         for i in range(min(n_given, M)):
             data = tensors[i]
@@ -404,7 +407,7 @@ class HealNet(nn.Module):
                 continue
             if len(axis) > HN_MAX_AXES:
                 raise ValueError(f"at most {HN_MAX_AXES} spatial axes per modality are supported")
-            staged[i] = data.detach().to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+            staged[i], ready[i] = self._stage_input(data.detach(), dev)
             for a, s in enumerate(axis):
                 axis_sizes[i * HN_MAX_AXES + a] = int(s)
         if batch is None:
@@ -442,13 +445,34 @@ class HealNet(nn.Module):
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             self._sync_native(dev, stream)
-            out = self._launch(lib, staged, axis_sizes, skip_self, mask_dev, mask_tokens, batch, want_latents, dev,
-                               stream)
+            out = self._launch(lib, staged, ready, axis_sizes, skip_self, mask_dev, mask_tokens, batch, want_latents,
+                               dev, stream)
         if ret_dtype is not None and not ret_dtype.is_floating_point:
             ret_dtype = torch.float32
         return out.to(device=ret_dev, dtype=ret_dtype)
 
-    def _launch(self, lib, staged, axis_sizes, skip_self, mask_dev, mask_tokens, batch, want_latents, dev, stream):
+    def _stage_input(self, data: torch.Tensor, dev: torch.device):
+        """-> (fp32 contiguous device tensor, event or None). Pinned host tensors are copied on a side stream and
+        the forward waits for each modality's copy only where it first reads it (hn_forward_ex), so the transfer
+        of a large late modality overlaps the work on the earlier ones."""
+        if data.device == dev:
+            return data.to(dtype=torch.float32).contiguous(), None
+        if data.device.type == "cpu" and data.is_pinned() and data.dtype == torch.float32 and data.is_contiguous():
+            if self._copy_stream is None or self._copy_stream.device != dev:
+                self._copy_stream = torch.cuda.Stream(device=dev)
+            cur = torch.cuda.current_stream(dev)
+            out = torch.empty(data.shape, dtype=torch.float32, device=dev)   # allocated on the compute stream
+            self._copy_stream.wait_stream(cur)                              # ...whose earlier users must be done
+            with torch.cuda.stream(self._copy_stream):
+                out.copy_(data, non_blocking=True)
+                out.record_stream(self._copy_stream)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+            return out, ev
+        return data.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous(), None
+
+    def _launch(self, lib, staged, ready, axis_sizes, skip_self, mask_dev, mask_tokens, batch, want_latents, dev,
+                stream):
         hp = self._hparams
         M = self.modalities
         ptrs = (ctypes.c_void_p * HN_MAX_MODALITIES)()
@@ -471,7 +495,12 @@ class HealNet(nn.Module):
             out = torch.empty(batch, hp["out_dims"], device=dev, dtype=torch.float32)
             lat_ptr, log_ptr = None, out.data_ptr()
         skip = (ctypes.c_int * HN_MAX_MODALITIES)(*[1 if f else 0 for f in skip_self]) if any(skip_self) else None
-        check(lib.hn_forward(self._handle, batch, ptrs, sizes, skip,
+        events = None
+        if any(e is not None for e in ready):
+            events = (ctypes.c_void_p * HN_MAX_MODALITIES)()
+            for i in range(M):
+                events[i] = ready[i].cuda_event if (ready[i] is not None and staged[i] is not None) else None
+        check(lib.hn_forward_ex(self._handle, batch, ptrs, events, sizes, skip,
                              mask_dev.data_ptr() if mask_dev is not None else None,
                              mask_tokens, lat_ptr, log_ptr, self._workspace.data_ptr(), self._workspace.numel(),
                              stream), "hn_forward")

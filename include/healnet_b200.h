@@ -98,6 +98,15 @@ HN_API int hn_forward(hn_handle* h, int batch, const void* const* modality_ptrs,
                       const int* skip_latent_block, const uint8_t* mask, long mask_tokens, float* latents_out,
                       float* logits_out, void* workspace, size_t workspace_bytes, void* cuda_stream);
 
+/* hn_forward with per-modality "input ready" events: modality_ready_events[m] (a cudaEvent_t, or NULL) is waited on
+ * by the forward's stream right before modality m's buffer is first read (just ahead of its layer-0 cross-attention),
+ * so a caller can copy a large late modality host-to-device on another stream while the earlier modalities are
+ * already being processed (healnet/main.py:415 copies all features up front). modality_ready_events may be NULL. */
+HN_API int hn_forward_ex(hn_handle* h, int batch, const void* const* modality_ptrs, void* const* modality_ready_events,
+                         const int* axis_sizes, const int* skip_latent_block, const uint8_t* mask, long mask_tokens,
+                         float* latents_out, float* logits_out, void* workspace, size_t workspace_bytes,
+                         void* cuda_stream);
+
 /* Number of kernels hn_forward enqueued on its last call for this handle (for bench accounting). */
 HN_API int hn_last_launch_count(const hn_handle* h);
 
