@@ -172,7 +172,7 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint8_t* sQ = smem;
   uint8_t* sZ = smem + G * Q_TILE;
   __shared__ uint64_t q_full, z_full[NST], z_empty[NST];
-  __shared__ uint64_t s_full[MAXG][2], p_ready[MAXG], u_done[MAXG], acc_done[MAXG];
+  __shared__ uint64_t s_full[MAXG][2], p_ready[MAXG][2], u_done[MAXG], acc_done[MAXG];
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -212,7 +212,8 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     for (int g = 0; g < MAXG; ++g) {
       mbar_init(&s_full[g][0], 1);
       mbar_init(&s_full[g][1], 1);
-      mbar_init(&p_ready[g], 4);
+      mbar_init(&p_ready[g][0], 4);
+      mbar_init(&p_ready[g][1], 4);
       mbar_init(&u_done[g], 1);
       mbar_init(&acc_done[g], 1);
     }
@@ -266,7 +267,9 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       issue_s(0);
       if (n > 1) issue_s(1);
       for (int i = 0; i < n; ++i) {
-        mbar_wait_sleepy(&p_ready[g], i & 1, 20000);  // all four warps: S(i) consumed, P(i) in TMEM, Q' fold up to date
+        // all four warps: S(i) consumed, P(i) in TMEM, Q' fold up to date. Two alternating barriers: a warp may run
+        // one tile ahead of its group but never two, so it cannot arrive twice in one phase of either.
+        mbar_wait_sleepy(&p_ready[g][i & 1], (i >> 1) & 1, 20000);
         fence_after_sync();
         const int s = i % NST;
         const uint32_t z0 = smem_u32(sZ + s * Z_BYTES);
@@ -323,7 +326,9 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float x0 = __uint_as_float(s[2 * j]), x1 = __uint_as_float(s[2 * j + 1]);
-              if (PMODE >= 5 && poly_pair<PMODE>(j)) {
+              if (PMODE == 9) {  // timing experiment only: no exponentials at all (skeleton cost)
+                pk[c * 16 + j] = pack_half2(x0, x1) & 0x3FFF3FFFu;
+              } else if (PMODE >= 5 && poly_pair<PMODE>(j)) {
                 pk[c * 16 + j] = ex2_pair_h2(x0, x1);
               } else {
                 const float e0 = (PMODE < 5 && poly_slot<PMODE>(2 * j)) ? ex2_poly(x0) : ex2_mufu(x0);
@@ -408,12 +413,7 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         tmem_wait_st();
         fence_before_sync();
         __syncwarp();
-        if (lane == 0) {
-          // a warp may run one tile ahead of its group (S is double-buffered) but must not arrive twice in one
-          // barrier phase: phase i-1 has to be complete before the arrival for tile i
-          if (i > 0) mbar_wait(&p_ready[g], (i - 1) & 1);
-          mbar_arrive(&p_ready[g]);
-        }
+        if (lane == 0) mbar_arrive(&p_ready[g][buf]);
         __syncwarp();
         if (exact) {  // the buffer S(i+2) will land in carries the current reference
           if (buf) m_in1 = (m_ref == -INFINITY) ? 0.f : m_ref; else m_in0 = (m_ref == -INFINITY) ? 0.f : m_ref;
@@ -524,6 +524,7 @@ int launch_small_attention(const AttnArgs& a, cudaStream_t stream) {
   if (pmode < 0) {
     const char* e = getenv("HN_POLY_MODE");
     pmode = (e != nullptr && e[0] >= '0' && e[0] <= '8') ? e[0] - '0' : 5;
+    if (e != nullptr && e[0] == '9') pmode = 9;
   }
   switch (pmode) {
     case 0: return launch_small_t<32, 3, 0>(a, stream);
@@ -534,6 +535,7 @@ int launch_small_attention(const AttnArgs& a, cudaStream_t stream) {
     case 8: return launch_small_t<32, 3, 8>(a, stream);
     case 1: return launch_small_t<32, 3, 1>(a, stream);
     case 6: return launch_small_t<32, 3, 6>(a, stream);
+    case 9: return launch_small_t<32, 3, 9>(a, stream);
     default: return launch_small_t<32, 3, 5>(a, stream);
   }
 }
