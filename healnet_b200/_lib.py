@@ -55,6 +55,7 @@ SIGNATURES = {
     "hn_forward_ex": (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int), POINTER(c_int),
                               c_void_p, c_long, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "hn_last_launch_count": (c_int, [c_void_p]),
+    "hn_set_attention_export": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "hn_profile_enable": (c_int, [c_void_p, c_int]),
     "hn_profile_read": (c_int, [c_void_p, c_int, POINTER(c_float), POINTER(c_int), POINTER(ctypes.c_double),
                                 POINTER(ctypes.c_double)]),

@@ -87,6 +87,8 @@ struct hn_handle {
   int launches = 0;
   // optional per-launch timing of the cross-attention kernels (bench.py roofline): CUDA event pairs on the
   // forward's own stream, one pair per (layer, modality), read back after the caller synchronises
+  // opt-in attention-weight export buffers, index layer * (M + 1) + module (M = latent self-attention); null = off
+  std::vector<float*> export_ptrs;
   bool profile = false;
   std::vector<cudaEvent_t> ev;          // 2 per slot
   std::vector<int> ev_mod;              // modality of each recorded slot in the last forward
@@ -357,6 +359,7 @@ int hn_create(const hn_desc* desc, hn_handle** out) {
   }
   h->slots_per_layer = 2 * h->M + 2;
   h->w.assign(static_cast<size_t>(d.depth + 1) * h->slots_per_layer, std::vector<const float*>());
+  h->export_ptrs.assign(static_cast<size_t>(d.depth) * (h->M + 1), nullptr);
   *out = h;
   return 0;
 }
@@ -493,6 +496,14 @@ size_t hn_workspace_bytes(const hn_handle* h, int batch, const int* axis_sizes) 
 
 int hn_last_launch_count(const hn_handle* h) { return h ? h->launches : 0; }
 
+int hn_set_attention_export(hn_handle* h, int layer, int module, float* dev_out) {
+  HN_REQUIRE(h != nullptr, "hn_set_attention_export: null handle");
+  HN_REQUIRE(layer >= 0 && layer < h->d.depth && module >= 0 && module <= h->M, "hn_set_attention_export: bad index");
+  HN_REQUIRE(module < h->M || h->d.self_per_cross_attn, "hn_set_attention_export: model has no latent self-attention");
+  h->export_ptrs[layer * (h->M + 1) + module] = dev_out;
+  return 0;
+}
+
 int hn_profile_enable(hn_handle* h, int on) {
   HN_REQUIRE(h != nullptr, "hn_profile_enable: null handle");
   h->profile = on != 0;
@@ -627,6 +638,7 @@ int hn_forward_ex(hn_handle* h, int batch, const void* const* modality_ptrs, voi
           if (rc != 0) return rc;
           HN_TRY(launch_attention(aa, st));
           profile_end(h, st);
+          if (h->export_ptrs[l * (M + 1) + m] != nullptr) HN_TRY(launch_attn_export(aa, h->export_ptrs[l * (M + 1) + m], st));
           HN_TRY(launch_combine_vproj(ws.part_acc, ws.part_ml, batch, mp.nsplit, H, L, mp.C, mp.zw,
                                       d.cross_dim_head, ap.Wv, ap.bv, ws.o, 2 * ow, ow, HPx, st));
         } else {
@@ -654,6 +666,7 @@ int hn_forward_ex(hn_handle* h, int batch, const void* const* modality_ptrs, voi
           if (rc != 0) return rc;
           HN_TRY(launch_attention(aa, st));
           profile_end(h, st);
+          if (h->export_ptrs[l * (M + 1) + m] != nullptr) HN_TRY(launch_attn_export(aa, h->export_ptrs[l * (M + 1) + m], st));
           HN_TRY(launch_combine_generic(ws.part_acc, ws.part_ml, batch, mp.nsplit, H, L, ws.o, 2 * ow, ow, HPx, st));
         }
         // x = LeakyReLU(O Wo^T + bo) + x   (healnet.py:383-386, 426, 236)
@@ -697,6 +710,7 @@ int hn_forward_ex(hn_handle* h, int batch, const void* const* modality_ptrs, voi
         aa.part_acc = ws.part_acc;
         aa.part_ml = ws.part_ml;
         HN_TRY(launch_attention(aa, st));
+        if (h->export_ptrs[l * (M + 1) + M] != nullptr) HN_TRY(launch_attn_export(aa, h->export_ptrs[l * (M + 1) + M], st));
         HN_TRY(launch_combine_generic(ws.part_acc, ws.part_ml, batch, ws.self_nsplit, lh, L, ws.o, 2 * ow, ow, HPl, st));
         GemmArgs go{ws.o, ap.Wo, static_cast<int>(rows), D, ow, 2 * ow, 2 * ow, EPI_RES_LEAKY, 0, wa[5], ws.x, D,
                     3, ow, ow, 0};

@@ -125,6 +125,9 @@ int launch_combine_generic(const float* part_acc, const float* part_ml, int batc
 int launch_combine_vproj(const float* part_acc, const float* part_ml, int batch, int nsplit, int H, int L, int C,
                          int zw, int dh, const float* Wv /*[H*dh][zw]*/, const float* bv /*[H*dh]*/, __half* O,
                          int o_ld, int lo_seg, int hp, cudaStream_t stream);
+// opt-in export of attn = softmax(...) of one attention call, out[(b*H + h)][l][n] fp32; call after the attention
+// kernel (needs its partials' row statistics), before the buffers are reused
+int launch_attn_export(const AttnArgs& a, float* out, cudaStream_t stream);
 // x[b][i] = src[i]  (latent broadcast, healnet.py:225)
 int launch_broadcast_rows(const float* src, float* dst, long n, int batch, cudaStream_t stream);
 

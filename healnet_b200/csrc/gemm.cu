@@ -244,11 +244,8 @@ int launch_t(const GemmArgs& a, cudaStream_t stream) {
   GemmDev p{a.M, a.N, a.K, a.epi, a.act, a.bias, a.out, a.ldo, vec_ok, a.terms, a.a_seg, a.b_seg,
             half_out ? a.out_seg : 0};
   constexpr int SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    HN_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr_set = true;
-  }
+  // per device and cheap: set on every launch so a process driving several GPUs never misses it
+  HN_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
   dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM);
   gemm_kernel<BN, STAGES><<<grid, 192, SMEM, stream>>>(tmA, tmB, p);
   HN_CHECK_CUDA(cudaGetLastError());

@@ -412,6 +412,85 @@ __global__ void broadcast_rows_kernel(const float* __restrict__ src, float* __re
   }
 }
 
+// ------------------------------------------------------------------ attention-weight export (opt-in)
+// Materialises attn = softmax(2 q k^T / sqrt(dh)) of one Attention call — what the reference keeps in
+// `Attention.attn_weights` (healnet.py:420) and hands out through get_attention_weights() (:252-262) — from the
+// same fp16 operands the streaming kernel used, normalised with the row statistics of the split partials, so
+// the exported matrix is the one the fused forward actually applied. out[(b*H + h)][l][n], fp32.
+// Block: 16 query rows x 256 tokens of one (sample, head); thread = token.
+template <int KW>  // operand width per head in fp16 elements (32, 64 or 128)
+__global__ void __launch_bounds__(256) attn_export_kernel(
+    const __half* __restrict__ Q, int q_ld, int q_col0, int q_lo_off, const __half* __restrict__ K, long k_ld,
+    int k_col0, int k_lo_off, int q_pitch, int k_pitch, int batch, int H, int L, long N, int nsplit,
+    const float* __restrict__ part_acc, const float* __restrict__ part_ml, int acc_w, int den_col,
+    const uint64_t* __restrict__ mask_bits, float* __restrict__ out) {
+  __shared__ float q_s[16][KW];
+  __shared__ float m_s[16], inv_s[16];
+  const int bh = blockIdx.z, b = bh / H, h = bh % H;
+  const int l0 = blockIdx.y * 16;
+  const long n = static_cast<long>(blockIdx.x) * 256 + threadIdx.x;
+  for (int i = threadIdx.x; i < 16 * KW; i += 256) {
+    const int r = i / KW, c = i % KW, l = l0 + r;
+    float v = 0.f;
+    if (l < L) {
+      const __half* qr = Q + (static_cast<long>(b) * L + l) * q_ld + q_col0 + h * q_pitch + c;
+      v = __half2float(qr[0]);
+      if (q_lo_off > 0) v += __half2float(qr[q_lo_off]);
+    }
+    q_s[r][c] = v;
+  }
+  if (threadIdx.x < 16) {
+    const int l = l0 + threadIdx.x;
+    float M = -INFINITY, den = 0.f;
+    if (l < L) {
+      for (int s = 0; s < nsplit; ++s)
+        M = fmaxf(M, part_ml[((((static_cast<long>(b) * nsplit + s) * H + h) * L) + l) * 2]);
+      for (int s = 0; s < nsplit; ++s) {
+        const long base = (((static_cast<long>(b) * nsplit + s) * H + h) * L) + l;
+        const float m = part_ml[base * 2];
+        const float w = (m == -INFINITY) ? 0.f : exp2f(m - M);
+        den += w * (den_col >= 0 ? part_acc[base * acc_w + den_col] : part_ml[base * 2 + 1]);
+      }
+    }
+    m_s[threadIdx.x] = M;
+    inv_s[threadIdx.x] = 1.f / den;
+  }
+  __syncthreads();
+  if (n >= N) return;
+  float k[KW];
+  const __half* kr = K + (static_cast<long>(b) * N + n) * k_ld + k_col0 + h * k_pitch;
+#pragma unroll
+  for (int c = 0; c < KW; c += 8) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(kr + c);
+    const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h2[j]);
+      k[c + 2 * j] = f.x;
+      k[c + 2 * j + 1] = f.y;
+    }
+    if (k_lo_off > 0) {
+      const uint4 rawl = *reinterpret_cast<const uint4*>(kr + k_lo_off + c);
+      const __half2* l2 = reinterpret_cast<const __half2*>(&rawl);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(l2[j]);
+        k[c + 2 * j] += f.x;
+        k[c + 2 * j + 1] += f.y;
+      }
+    }
+  }
+  bool keep = true;
+  if (mask_bits != nullptr) keep = (mask_bits[static_cast<long>(b) * ((N + 63) / 64) + n / 64] >> (n % 64)) & 1ull;
+  for (int r = 0; r < 16 && l0 + r < L; ++r) {
+    float sdot = 0.f;
+#pragma unroll
+    for (int c = 0; c < KW; ++c) sdot += q_s[r][c] * k[c];
+    const float p = keep ? exp2f(sdot - m_s[r]) * inv_s[r] : 0.f;
+    out[(static_cast<long>(bh) * L + l0 + r) * N + n] = p;
+  }
+}
+
 AxisInfo make_axis(const int* sizes, int n_axes) {
   AxisInfo ax{};
   ax.n_axes = n_axes;
@@ -516,6 +595,31 @@ int launch_combine_vproj(const float* part_acc, const float* part_ml, int batch,
              "combine_vproj: C < zw and dim_head <= head pitch (64 | 128) required");
   combine_vproj_kernel<<<dim3((L + 31) / 32, H, batch), 256, 0, stream>>>(part_acc, part_ml, batch, nsplit, H, L, C,
                                                                              zw, dh, Wv, bv, O, o_ld, lo_seg, hp);
+  HN_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_attn_export(const AttnArgs& a, float* out, cudaStream_t stream) {
+  HN_REQUIRE(out != nullptr, "attention export: null output");
+  const dim3 grid(static_cast<unsigned>((a.N + 255) / 256), (a.L + 15) / 16, a.batch * a.H);
+  const int q_lo = a.precise ? a.q_lo_off : 0, k_lo = a.precise ? a.kv_lo_off : 0;
+  // small-context path: Q' heads are kd columns apart, every head reads the same z row, the denominator is the
+  // accumulator column that met z's 1.0; generic path: heads hp apart in Q and K, denominator = tracked row sum
+  const int kw = a.shared_kv ? a.kd : a.hp;
+  const int q_pitch = kw, k_pitch = a.shared_kv ? 0 : a.hp;
+  const int k_col0 = a.shared_kv ? 0 : a.k_col0;
+  const int den_col = a.shared_kv ? a.c_ones : -1;
+#define HN_EXPORT(KW)                                                                                              \
+  attn_export_kernel<KW><<<grid, 256, 0, stream>>>(a.Q, a.q_ld, 0, q_lo, a.KV, a.kv_ld, k_col0, k_lo, q_pitch,      \
+                                                   k_pitch, a.batch, a.H, a.L, a.N, a.nsplit, a.part_acc,          \
+                                                   a.part_ml, kw, den_col, a.mask_bits, out)
+  if (kw == 32)
+    HN_EXPORT(32);
+  else if (kw == 64)
+    HN_EXPORT(64);
+  else
+    HN_EXPORT(128);
+#undef HN_EXPORT
   HN_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

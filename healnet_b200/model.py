@@ -264,12 +264,17 @@ class HealNet(nn.Module):
         self._staged = []       # keeps staged fp32 device copies alive while the handle borrows them
         self._workspace = None
         self._copy_stream = None
+        self._export_registered = False
+        # opt-in: materialise every Attention module's softmax matrix on each forward (reference: always on,
+        # healnet.py:420). Off by default: (b*h, L, N) fp32 is 9.87 GB per sample and layer at the README shapes.
+        self.export_attention_weights = False
+        self.export_attention_max_bytes = 16 << 30
         self.last_launch_count = 0
         self._warned = set()
 
     # ------------------------------------------------------------------------------------------------ native
     _NATIVE_DEFAULTS = dict(_handle=None, _handle_dev=None, _weights_sig=None, _staged=(), _workspace=None,
-                            _copy_stream=None)
+                            _copy_stream=None, _export_registered=False)
 
     def __getstate__(self):
         """copy.deepcopy / pickle / torch.save(model): the native handle, staged weights and workspace are
@@ -495,6 +500,7 @@ class HealNet(nn.Module):
             out = torch.empty(batch, hp["out_dims"], device=dev, dtype=torch.float32)
             lat_ptr, log_ptr = None, out.data_ptr()
         skip = (ctypes.c_int * HN_MAX_MODALITIES)(*[1 if f else 0 for f in skip_self]) if any(skip_self) else None
+        exported = self._register_attention_export(lib, staged, skip_self, batch, dev)
         events = None
         if any(e is not None for e in ready):
             events = (ctypes.c_void_p * HN_MAX_MODALITIES)()
@@ -505,6 +511,50 @@ class HealNet(nn.Module):
                              mask_tokens, lat_ptr, log_ptr, self._workspace.data_ptr(), self._workspace.numel(),
                              stream), "hn_forward")
         self.last_launch_count = lib.hn_last_launch_count(self._handle)
+        for module, tensor in exported:   # later calls of a tied / repeated module win, as in the reference
+            module.attn_weights = tensor
+        return out
+
+    def _register_attention_export(self, lib, staged, skip_self, batch, dev):
+        """Allocates and registers the export buffers (hn_set_attention_export) when `export_attention_weights` is
+        on; returns [(Attention module, tensor)] in call order. Shapes follow the reference: (b*h, L, N)."""
+        hp = self._hparams
+        M, L = self.modalities, hp["l_c"]
+        if not self.export_attention_weights:
+            if self._export_registered:
+                for l in range(hp["depth"]):
+                    for m in range(M + (1 if self.self_per_cross_attn > 0 else 0)):
+                        check(lib.hn_set_attention_export(self._handle, l, m, None), "hn_set_attention_export")
+                self._export_registered = False
+            return []
+        plan, total = [], 0
+        for l, layer in enumerate(self.layers):
+            last_self = None
+            for m in range(M):
+                if staged[m] is not None:
+                    n_tok = staged[m].numel() // (batch * staged[m].shape[-1])
+                    plan.append((l, m, layer[2 * m].fn, (batch * hp["x_heads"], L, n_tok)))
+                if self.self_per_cross_attn > 0 and not skip_self[m]:
+                    last_self = (l, M, layer[-1][0].fn, (batch * hp["l_heads"], L, L))
+            if last_self is not None:
+                plan.append(last_self)
+        for _, _, _, shape in plan:
+            total += 4 * shape[0] * shape[1] * shape[2]
+        if total > self.export_attention_max_bytes:
+            raise MemoryError(f"export_attention_weights needs {total / 2**30:.1f} GiB for these shapes "
+                              f"(limit export_attention_max_bytes = {self.export_attention_max_bytes / 2**30:.1f} GiB)")
+        out = []
+        registered = set()
+        for l, m, module, shape in plan:
+            t = torch.empty(shape, device=dev, dtype=torch.float32)
+            check(lib.hn_set_attention_export(self._handle, l, m, t.data_ptr()), "hn_set_attention_export")
+            registered.add((l, m))
+            out.append((module, t))
+        for l in range(hp["depth"]):   # modules that do not run this time must not write into stale buffers
+            for m in range(M + (1 if self.self_per_cross_attn > 0 else 0)):
+                if (l, m) not in registered:
+                    check(lib.hn_set_attention_export(self._handle, l, m, None), "hn_set_attention_export")
+        self._export_registered = True
         return out
 
     # ------------------------------------------------------------------------------------------- measurement
@@ -526,7 +576,7 @@ class HealNet(nn.Module):
         return dict(ms=ms.value, launches=n.value, flops=fl.value, exps=ex.value)
 
     def get_attention_weights(self) -> List[Optional[torch.Tensor]]:
-        """One entry per Attention module, in module order (healnet.py:252-262). The streaming kernels never
-        materialise the (b*h, L, N) attention matrices, so the entries are None (as in the reference before
-        its first forward)."""
+        """One entry per Attention module, in module order (healnet.py:252-262): the (b*h, L, N) softmax matrix of
+        the module's last call when `export_attention_weights` was on for that forward, else None (the streaming
+        kernels do not materialise it; the reference always keeps it, healnet.py:420)."""
         return [m.attn_weights for m in self.modules() if isinstance(m, Attention)]

@@ -110,6 +110,15 @@ HN_API int hn_forward_ex(hn_handle* h, int batch, const void* const* modality_pt
 /* Number of kernels hn_forward enqueued on its last call for this handle (for bench accounting). */
 HN_API int hn_last_launch_count(const hn_handle* h);
 
+/* Opt-in replacement for `Attention.attn_weights` (healnet.py:420) / HealNet.get_attention_weights() (:252-262).
+ * Registers (dev_out != NULL) or clears a caller-owned fp32 device buffer of shape (batch * heads, l_c, N) for the
+ * attention call of `module` in `layer`: module m < n_modalities = cross-attention of modality m (N = its token
+ * count, heads = x_heads); module == n_modalities = latent self-attention (N = l_c, heads = l_heads; it runs once
+ * per modality and the buffer keeps the last call, as the reference's attribute does). Subsequent hn_forward calls
+ * fill it with the softmax matrix actually applied. The streaming kernels never materialise this matrix (9.87 GB per
+ * sample and layer at the README shapes), so export is off by default and the caller sizes the buffers. */
+HN_API int hn_set_attention_export(hn_handle* h, int layer, int module, float* dev_out);
+
 /* Measurement hook (bench.py roofline): when enabled, hn_forward brackets every cross-attention kernel launch
  * with CUDA events on its own stream. After the caller has synchronised the stream, hn_profile_read sums, for one
  * modality, the device time of those launches in the LAST forward, their count, the tensor-core FLOPs they executed

@@ -214,3 +214,59 @@ def test_pinned_host_inputs_overlap_path():
         assert torch.equal(got, want.cpu())
     miss = model([host[0], None, host[2]])
     assert torch.equal(miss, model([host[0].cuda(), None, host[2].cuda()]).cpu())
+
+
+@pytest.mark.parametrize("name", ["tri_small", "wide_heads", "omic_wsi_tied"])
+def test_attention_weight_export(golden, name):
+    """Opt-in replacement of the reference's retained `attn_weights` (healnet.py:420, :252-262; consumed by
+    explainer.py:102-104): one (b*h, L, N) matrix per Attention module, in module order, last call wins."""
+    meta, sd, ins, outs, _ = golden(name)
+    kw = meta["kwargs"]
+    m = _model(meta, sd)
+    x = _inputs(ins, kw["n_modalities"])
+    assert all(w is None for w in m.get_attention_weights())
+    m.export_attention_weights = True
+    logits = m(list(x))
+    got = m.get_attention_weights()
+    # oracle: attention matrices in call order -> keep the last call of every module (tying, repeated self-attn)
+    calls = []
+    O.forward(sd, _cfg(kw), [t.cpu() for t in x], collect_weights=calls)
+    M, depth, spc = kw["n_modalities"], kw.get("depth", 3), kw.get("self_per_cross_attn", 1)
+    per_module = {}
+    it = iter(calls)
+    for l in range(depth):
+        for i in range(M):
+            per_module[id(m.layers[l][2 * i].fn)] = next(it)
+            if spc:
+                per_module[id(m.layers[l][-1][0].fn)] = next(it)
+    mods = [mod for mod in m.modules() if isinstance(mod, Attention)]
+    assert len(got) == len(mods)
+    for mod, w in zip(mods, got):
+        want = per_module[id(mod)]
+        assert w is not None and tuple(w.shape) == tuple(want.shape)
+        torch.testing.assert_close(w.cpu(), want, rtol=5e-3, atol=1e-5)
+        torch.testing.assert_close(w.sum(-1).cpu(), torch.ones(w.shape[:2]), rtol=1e-3, atol=1e-3)
+    # export must not change the result, and switching it off stops refreshing the tensors
+    m.export_attention_weights = False
+    torch.testing.assert_close(m(list(x)), logits, rtol=0, atol=0)
+
+
+def test_attention_weight_export_long_axis_and_mask():
+    """Small-context streaming path (N > 2048) with a mask: exported rows are the applied softmax, zeros at masked tokens."""
+    torch.manual_seed(3)
+    kw = dict(n_modalities=1, channel_dims=[3], num_spatial_axes=[2], out_dims=2, depth=1, l_c=40, l_d=64, x_heads=2,
+              cross_dim_head=32, self_per_cross_attn=0)
+    m = HealNet(**kw).eval().cuda()
+    x = torch.rand(2, 50, 60, 3, device="cuda")
+    mask = torch.rand(2, 3000, device="cuda") > 0.3
+    m.export_attention_weights = True
+    m([x], mask=mask)
+    (w,) = m.get_attention_weights()
+    calls = []
+    O.forward({k: v.cpu() for k, v in m.state_dict().items()}, _cfg(kw), [x.cpu()], mask=mask.cpu(), collect_weights=calls)
+    assert tuple(w.shape) == (4, 40, 3000)
+    torch.testing.assert_close(w.cpu(), calls[0], rtol=5e-3, atol=1e-6)
+    assert bool((w[:2][:, :, ~mask[0]] == 0).all())
+    m.export_attention_max_bytes = 1000
+    with pytest.raises(MemoryError):
+        m([x])
