@@ -18,6 +18,8 @@
 // fp16), warp 1 = single-thread UMMA issuer (+ TMEM allocator), warps 2..5 = epilogue (each thread owns
 // one accumulator row = one TMEM lane). M/N/K tails are handled by TMA out-of-bounds zero fill plus
 // guards in the epilogue, so any shape whose row pitches are multiples of 8 elements is legal.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "tc05.cuh"
 
@@ -263,7 +265,18 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   if (a.terms >= 2) HN_REQUIRE(a.b_seg % 64 == 0 && a.b_seg >= a.K, "gemm: B lo segment must start at a multiple of 64 >= K");
   if (a.terms == 3) HN_REQUIRE(a.a_seg % 64 == 0 && a.a_seg >= a.K, "gemm: A lo segment must start at a multiple of 64 >= K");
   // wide tiles once the grid would still cover the 148 SMs, narrow ones otherwise
-  const long tiles128 = static_cast<long>((a.N + 127) / 128) * ((a.M + BM - 1) / BM);
+  const long mt = (a.M + BM - 1) / BM;
+  const long tiles128 = static_cast<long>((a.N + 127) / 128) * mt;
+  static int force = -1;  // tuning knob: HN_GEMM_BN=64|128|256
+  if (force < 0) {
+    const char* e = getenv("HN_GEMM_BN");
+    force = e ? atoi(e) : 0;
+  }
+  if (force == 256) return launch_t<256, 3>(a, stream);
+  if (force == 128) return launch_t<128, 3>(a, stream);
+  if (force == 64) return launch_t<64, 4>(a, stream);
+  if (force == 648) return launch_t<64, 8>(a, stream);
+  if (force == 1286) return launch_t<128, 6>(a, stream);
   if (tiles128 >= 148) return launch_t<128, 3>(a, stream);
   return launch_t<64, 4>(a, stream);
 }
