@@ -14,10 +14,19 @@
 // A_hi.(B_hi + B_lo) (exact weights, fp16 activations) for the wide-context K/V projection, whose per-token
 // activation rounding averages out under the softmax while weight rounding would not.
 //
-// One CTA computes a 128 x BN output tile: warp 0 = TMA producer (128B-swizzled K-major tiles of 64
-// fp16), warp 1 = single-thread UMMA issuer (+ TMEM allocator), warps 2..5 = epilogue (each thread owns
-// one accumulator row = one TMEM lane). M/N/K tails are handled by TMA out-of-bounds zero fill plus
-// guards in the epilogue, so any shape whose row pitches are multiples of 8 elements is legal.
+// Persistent kernel, one CTA per SM, static round-robin over the 128 x BN output tiles (m fastest, so CTAs that run
+// side by side read the same weight tile): warp 0 = TMA producer, warp 1 = single-thread UMMA issuer (+ TMEM
+// allocator), warps 2..5 = epilogue (each thread owns one accumulator row = one TMEM lane). These GEMMs have few rows
+// (M = batch * L = 2048 at cfg 1), so they are bound by the bytes an SM has to pull in from L2 per k-tile, not by the
+// tensor pipe. Hence:
+//   * every distinct operand tile is loaded ONCE per k-tile — a stage holds [A_hi | A_lo | B_hi | B_lo] and feeds the
+//     three UMMA terms (the first version re-read A_hi and B_hi in separate passes: 6 tile loads instead of 4);
+//   * the ring uses the whole shared memory of the SM (up to 8 stages) to cover L2 latency;
+//   * two accumulators in TMEM (2 x BN columns): the epilogue of tile j overlaps the main loop of tile j+1, and the
+//     per-CTA set-up (barriers, TMEM allocation, descriptor fetch) is paid once per SM instead of once per tile;
+//   * BN = 256 whenever that still gives every SM a tile (halves the A bytes per FLOP).
+// M/N/K tails are handled by TMA out-of-bounds zero fill plus guards in the epilogue, so any shape whose row pitches
+// are multiples of 8 elements is legal.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -37,9 +46,10 @@ struct GemmDev {
   void* out;
   int ldo;
   int vec_ok;  // output rows are 16-byte aligned -> vector stores allowed
-  int terms;   // 1, 2 or 3 passes over the K tiles (see header comment)
+  int terms;   // 1, 2 or 3 UMMA terms per k-tile (see header comment)
   int a_seg, b_seg;  // column offset of the lo segment of A / B (elements)
   int out_seg;       // fp16 outputs: > 0 -> also store lo = fp16(v - hi) at column + out_seg
+  int stages;        // depth of the operand ring (host: as many as fit the SM's shared memory, <= 8)
 };
 
 __device__ __forceinline__ void split_half(float v, __half& hi, __half& lo) {
@@ -63,76 +73,106 @@ __device__ __forceinline__ float selu_f(float x) {
 __device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float leaky_f(float x) { return x > 0.f ? x : 0.01f * x; }
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(192) gemm_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                   const __grid_constant__ CUtensorMap tmB, GemmDev p) {
+constexpr int MAX_STAGES = 8;
+constexpr int SMEM_BUDGET = 220 * 1024;
+
+template <int BN, int BK>
+__global__ void __launch_bounds__(192, 1) gemm_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                      const __grid_constant__ CUtensorMap tmB, GemmDev p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int A_BYTES = BM * BK * 2;
   constexpr int B_BYTES = BN * BK * 2;
-  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], acc_bar;
+  constexpr uint32_t LAYOUT = (BK == 64) ? SWZ_128B : SWZ_64B;
+  constexpr uint32_t SBO = 8 * BK * 2;
+  __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
-  const int k_tiles_1 = (p.K + BK - 1) / BK;
-  const int k_tiles = k_tiles_1 * p.terms;
+  const int n_a = p.terms == 3 ? 2 : 1, n_b = p.terms >= 2 ? 2 : 1;  // distinct A / B tiles per k-tile
+  const int stage_bytes = n_a * A_BYTES + n_b * B_BYTES;
+  const int stages = p.stages;
+  const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
+  const int n_tiles = tiles_m * tiles_n;
+  const int k_tiles = (p.K + BK - 1) / BK;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(&acc_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 4);
+    }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<BN>(&tmem_base_s);
+  if (warp == 1) tmem_alloc<2 * BN>(&tmem_base_s);
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  const uint32_t tD = tmem_base_s;
+  const uint32_t tmem = tmem_base_s;
 
   if (warp == 0) {
     if (elect_one()) {
       tma_prefetch_desc(&tmA);
       tma_prefetch_desc(&tmB);
-      for (int kt = 0; kt < k_tiles; ++kt) {
-        const int s = kt % STAGES;
-        mbar_wait(&empty_bar[s], ((kt / STAGES) & 1) ^ 1);
-        mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
-        const int pass = kt / k_tiles_1, k0 = (kt - pass * k_tiles_1) * BK;
-        // pass 0: A_hi.B_hi; terms == 3: pass 1 = A_lo.B_hi, pass 2 = A_hi.B_lo; terms == 2: pass 1 = A_hi.B_lo
-        const int a_col = k0 + ((p.terms == 3 && pass == 1) ? p.a_seg : 0);
-        const int b_col = k0 + ((pass == p.terms - 1 && pass > 0) ? p.b_seg : 0);
-        tma_load_2d(smem + s * STAGE_BYTES, &tmA, &full_bar[s], a_col, m0);
-        tma_load_2d(smem + s * STAGE_BYTES + A_BYTES, &tmB, &full_bar[s], b_col, n0);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+        for (int kt = 0; kt < k_tiles; ++kt, ++it) {
+          const int s = it % stages;
+          mbar_wait(&empty_bar[s], ((it / stages) & 1) ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+          uint8_t* st = smem + s * stage_bytes;
+          const int k0 = kt * BK;
+          tma_load_2d(st, &tmA, &full_bar[s], k0, m0);
+          if (n_a == 2) tma_load_2d(st + A_BYTES, &tmA, &full_bar[s], k0 + p.a_seg, m0);
+          tma_load_2d(st + n_a * A_BYTES, &tmB, &full_bar[s], k0, n0);
+          if (n_b == 2) tma_load_2d(st + n_a * A_BYTES + B_BYTES, &tmB, &full_bar[s], k0 + p.b_seg, n0);
+        }
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {
       constexpr uint32_t idesc = idesc_f16(BM, BN, false, false);
-      for (int kt = 0; kt < k_tiles; ++kt) {
-        const int s = kt % STAGES;
-        mbar_wait(&full_bar[s], (kt / STAGES) & 1);
+      int it = 0, j = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+        const int acc = j & 1;
+        mbar_wait(&acc_empty[acc], ((j >> 1) & 1) ^ 1);  // epilogue of tile j-2 has drained this accumulator
         fence_after_sync();
-        const uint32_t a0 = smem_u32(smem + s * STAGE_BYTES);
-        const uint32_t b0 = a0 + A_BYTES;
+        const uint32_t tD = tmem + acc * BN;
+        for (int kt = 0; kt < k_tiles; ++kt, ++it) {
+          const int s = it % stages;
+          mbar_wait(&full_bar[s], (it / stages) & 1);
+          fence_after_sync();
+          const uint32_t a_hi = smem_u32(smem + s * stage_bytes);
+          const uint32_t a_lo = a_hi + A_BYTES;
+          const uint32_t b_hi = a_hi + n_a * A_BYTES;
+          const uint32_t b_lo = b_hi + B_BYTES;
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          umma_ss(tD, smem_desc(a0 + k * 32, 16, 1024, SWZ_128B), smem_desc(b0 + k * 32, 16, 1024, SWZ_128B),
-                  idesc, (kt | k) != 0);
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t dah = smem_desc(a_hi + k * 32, 16, SBO, LAYOUT), dbh = smem_desc(b_hi + k * 32, 16, SBO, LAYOUT);
+            umma_ss(tD, dah, dbh, idesc, (kt | k) != 0);
+            if (p.terms == 3) umma_ss(tD, smem_desc(a_lo + k * 32, 16, SBO, LAYOUT), dbh, idesc, true);
+            if (p.terms >= 2) umma_ss(tD, dah, smem_desc(b_lo + k * 32, 16, SBO, LAYOUT), idesc, true);
+          }
+          umma_commit(&empty_bar[s]);
         }
-        umma_commit(&empty_bar[s]);
+        umma_commit(&acc_full[acc]);
       }
-      umma_commit(&acc_bar);
     }
   } else {
     // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
     const uint32_t lane_base = (warp & 3) * 32;
+    int j = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+    const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+    const int acc = j & 1;
+    const uint32_t tD = tmem + acc * BN;
     const int row = m0 + lane_base + lane;
     const bool row_ok = row < p.M;
-    mbar_wait(&acc_bar, 0);
+    mbar_wait_sleepy(&acc_full[acc], (j >> 1) & 1, 2000);
     fence_after_sync();
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
@@ -222,34 +262,48 @@ __global__ void __launch_bounds__(192) gemm_kernel(const __grid_constant__ CUten
       }  // row_ok
       __syncwarp();
     }
+    // accumulator drained (every tcgen05.ld above has completed): hand it back to the issuer
+    fence_before_sync();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&acc_empty[acc]);
+    }  // tile
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<BN>(tD);
+  if (warp == 1) tmem_dealloc<2 * BN>(tmem);
 }
 
-template <int BN, int STAGES>
+template <int BN, int BK>
 int launch_t(const GemmArgs& a, cudaStream_t stream) {
   CUtensorMap tmA, tmB;
   // single-segment operands rely on TMA zero fill beyond column K; split operands declare hi|lo and keep
   // explicit zeros in the pad columns [K, seg) of both segments
   const uint64_t a_cols = a.terms == 3 ? static_cast<uint64_t>(a.a_seg) + a.K : a.K;
   const uint64_t b_cols = a.terms >= 2 ? static_cast<uint64_t>(a.b_seg) + a.K : a.K;
-  if (!make_tmap_2d_f16(&tmA, a.A, a.M, a_cols, static_cast<uint64_t>(a.lda) * 2, BM, BK, CU_TENSOR_MAP_SWIZZLE_128B) ||
-      !make_tmap_2d_f16(&tmB, a.B, a.N, b_cols, static_cast<uint64_t>(a.ldb) * 2, BN, BK, CU_TENSOR_MAP_SWIZZLE_128B)) {
+  const CUtensorMapSwizzle swz = BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  if (!make_tmap_2d_f16(&tmA, a.A, a.M, a_cols, static_cast<uint64_t>(a.lda) * 2, BM, BK, swz) ||
+      !make_tmap_2d_f16(&tmB, a.B, a.N, b_cols, static_cast<uint64_t>(a.ldb) * 2, BN, BK, swz)) {
     set_error("gemm: cuTensorMapEncodeTiled failed");
     return -2;
   }
   const bool half_out = (a.epi == EPI_F16 || a.epi == EPI_GATE_F16);
   const int vec_ok = ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0) && (a.ldo % (half_out ? 8 : 4) == 0) &&
                      (a.out_seg % 8 == 0);
+  const int stage_bytes = ((a.terms == 3 ? 2 : 1) * BM + (a.terms >= 2 ? 2 : 1) * BN) * BK * 2;
+  int stages = SMEM_BUDGET / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
   GemmDev p{a.M, a.N, a.K, a.epi, a.act, a.bias, a.out, a.ldo, vec_ok, a.terms, a.a_seg, a.b_seg,
-            half_out ? a.out_seg : 0};
-  constexpr int SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024;
+            half_out ? a.out_seg : 0, stages};
+  const int smem = stages * stage_bytes + 1024;
+  int dev = 0, sms = 0;
+  HN_CHECK_CUDA(cudaGetDevice(&dev));
+  HN_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   // per device and cheap: set on every launch so a process driving several GPUs never misses it
-  HN_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-  dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM);
-  gemm_kernel<BN, STAGES><<<grid, 192, SMEM, stream>>>(tmA, tmB, p);
+  HN_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     SMEM_BUDGET + 1024));
+  const long n_tiles = static_cast<long>((a.N + BN - 1) / BN) * ((a.M + BM - 1) / BM);
+  const unsigned grid = static_cast<unsigned>(n_tiles < sms ? n_tiles : sms);
+  gemm_kernel<BN, BK><<<grid, 192, smem, stream>>>(tmA, tmB, p);
   HN_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -264,21 +318,22 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   HN_REQUIRE(a.terms >= 1 && a.terms <= 3, "gemm: terms must be 1, 2 or 3");
   if (a.terms >= 2) HN_REQUIRE(a.b_seg % 64 == 0 && a.b_seg >= a.K, "gemm: B lo segment must start at a multiple of 64 >= K");
   if (a.terms == 3) HN_REQUIRE(a.a_seg % 64 == 0 && a.a_seg >= a.K, "gemm: A lo segment must start at a multiple of 64 >= K");
-  // wide tiles once the grid would still cover the 148 SMs, narrow ones otherwise
+  // widest tile that still gives (nearly) every SM one; k-tiles of 32 for the four-operand stages
   const long mt = (a.M + BM - 1) / BM;
+  const long tiles256 = static_cast<long>((a.N + 255) / 256) * mt;
   const long tiles128 = static_cast<long>((a.N + 127) / 128) * mt;
-  static int force = -1;  // tuning knob: HN_GEMM_BN=64|128|256
+  static int force = -1, force_bk = -1;  // tuning knobs: HN_GEMM_BN=64|128|256, HN_GEMM_BK=32|64
   if (force < 0) {
     const char* e = getenv("HN_GEMM_BN");
     force = e ? atoi(e) : 0;
+    const char* k = getenv("HN_GEMM_BK");
+    force_bk = k ? atoi(k) : 0;
   }
-  if (force == 256) return launch_t<256, 3>(a, stream);
-  if (force == 128) return launch_t<128, 3>(a, stream);
-  if (force == 64) return launch_t<64, 4>(a, stream);
-  if (force == 648) return launch_t<64, 8>(a, stream);
-  if (force == 1286) return launch_t<128, 6>(a, stream);
-  if (tiles128 >= 148) return launch_t<128, 3>(a, stream);
-  return launch_t<64, 4>(a, stream);
+  const int bn = force ? force : (tiles256 >= 120 ? 256 : tiles128 >= 120 ? 128 : 64);
+  const int bk = force_bk ? force_bk : (a.terms == 3 ? 32 : 64);
+  if (bn == 256) return bk == 64 ? launch_t<256, 64>(a, stream) : launch_t<256, 32>(a, stream);
+  if (bn == 128) return bk == 64 ? launch_t<128, 64>(a, stream) : launch_t<128, 32>(a, stream);
+  return bk == 64 ? launch_t<64, 64>(a, stream) : launch_t<64, 32>(a, stream);
 }
 
 }  // namespace hn

@@ -53,6 +53,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// waiter off the critical path: let the hardware suspend the thread (try_wait with a suspend-time hint)
+// instead of spinning through issue slots other warps need
+__device__ __forceinline__ void mbar_wait_sleepy(uint64_t* bar, uint32_t parity, unsigned hint_ns) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+        : "memory");
+  } while (!ok);
+}
 // generic-proxy smem writes -> visible to the async proxy (UMMA / TMA reads of smem)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -129,21 +129,6 @@ template <int PMODE>
 __device__ __forceinline__ constexpr bool poly_pair(int j) {
   return PMODE == 5 ? (j % 3) == 1 : PMODE == 6 ? (j % 2) == 1 : PMODE == 7 ? (j % 3) != 1 : PMODE == 8 ? (j % 4) != 1 : false;
 }
-// waiter off the critical path: let the hardware suspend the thread (try_wait with a long suspend-time hint)
-// instead of spinning through issue slots the softmax warps need
-__device__ __forceinline__ void mbar_wait_sleepy(uint64_t* bar, uint32_t parity, unsigned hint_ns) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
-        : "memory");
-  } while (!ok);
-}
-
 // byte offset of element (row, col) inside a TMA-swizzled [rows][KD] fp16 tile (64-byte rows -> SWIZZLE_64B,
 // 128-byte rows -> SWIZZLE_128B): the 16-byte chunk index is XORed with the low bits of (row-pair | row)
 template <int KD>
