@@ -56,12 +56,24 @@ struct SmallDev {
   int L, H, batch, nsplit, n_ltiles, n_rb;  // n_rb = H * n_ltiles row blocks per (sample, split)
   int ctas_per_stream;                       // ceil(n_rb / G)
   int tiles_total;
+  int mask_words;  // 64-token mask words per sample
+  long long* trace;  // debug timeline buffer or null
   int c_ones;  // column of z that is 1.0 (= context width C): Q' carries -m_ref there
   long N;
   const uint64_t* mask_bits;
   float* part_acc;
   float* part_ml;
 };
+
+// Debug timeline (tools/trace_attn.py): CTA 0 records clock64() at a few points of tiles [TR_T0, TR_T0 + TR_NT) for
+// the first softmax warp and the issuer of every group. Compiled into separate TRACE instantiations only.
+constexpr int TR_T0 = 64, TR_NT = 48, TR_NP = 8;
+long long* g_trace_buf = nullptr;  // set through hn_debug_set_trace (debug only)
+#define HN_TR(slot, tile, k)                                                                              \
+  do {                                                                                                    \
+    if (TRACE && p.trace != nullptr && blockIdx.x == 0 && lane == 0 && (tile) >= TR_T0 && (tile) < TR_T0 + TR_NT) \
+      p.trace[(static_cast<long>(slot) * TR_NT + ((tile) - TR_T0)) * TR_NP + (k)] = clock64();            \
+  } while (0)
 
 __device__ __forceinline__ float ex2_mufu(float x) {
   float y;
@@ -138,7 +150,7 @@ __device__ __forceinline__ uint32_t swizzled_off(int row, int col) {
   return row * 128 + ((chunk ^ (static_cast<uint32_t>(row) & 7u)) << 4) + within;
 }
 
-template <int KD, int G, int PMODE>
+template <int KD, int G, int PMODE, bool TRACE = false>
 __global__ void __launch_bounds__((5 * G + 1) * 32, 1)
 attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmZ, SmallDev p) {
   constexpr int VD = KD;
@@ -254,7 +266,9 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       for (int i = 0; i < n; ++i) {
         // all four warps: S(i) consumed, P(i) in TMEM, Q' fold up to date. Two alternating barriers: a warp may run
         // one tile ahead of its group but never two, so it cannot arrive twice in one phase of either.
+        HN_TR(MAXG + g, i, 0);
         mbar_wait_sleepy(&p_ready[g][i & 1], (i >> 1) & 1, 20000);
+        HN_TR(MAXG + g, i, 1);
         fence_after_sync();
         const int s = i % NST;
         const uint32_t z0 = smem_u32(sZ + s * Z_BYTES);
@@ -264,7 +278,9 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                   (i | k) != 0);
         umma_commit(&z_empty[s]);
         umma_commit(&u_done[g]);
+        HN_TR(MAXG + g, i, 2);
         if (i + 2 < n) issue_s(i + 2);
+        HN_TR(MAXG + g, i, 3);
         if (i + 1 == n) umma_commit(&acc_done[g]);
       }
     }
@@ -275,8 +291,6 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const int rb = rb0 + g, h = rb / p.n_ltiles, lt = rb % p.n_ltiles;
       const uint32_t lane_base = (warp & 3) * 32;
       const int trow = lane_base + lane;  // row inside the 128-row block
-      const int row = lt * BM + trow;
-      const long part_row = ((static_cast<long>(b) * p.nsplit + split) * p.H + h) * p.L + row;
       const uint32_t tG = tmem + g * GCOLS;  // group columns (lane field 0)
       const uint32_t tL = tmem_addr(tG, lane_base, 0);
       const uint32_t tU = tL + 128;
@@ -293,7 +307,9 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         const int buf = i & 1;
         const uint32_t tS = tL + buf * 64;
 
+        if ((warp & 3) == 0) HN_TR(g, i, 0);
         mbar_wait(&s_full[g][buf], (i >> 1) & 1);
+        if ((warp & 3) == 0) HN_TR(g, i, 1);
         fence_after_sync();
 
         // steady state needs: a full unmasked tile whose folded offset is the current reference (all warp-uniform)
@@ -308,6 +324,7 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             uint32_t s[32];
             tmem_ld32(tS + c * 32, s);
             tmem_wait_ld();
+            if ((warp & 3) == 0 && c == 0) HN_TR(g, i, 5);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float x0 = __uint_as_float(s[2 * j]), x1 = __uint_as_float(s[2 * j + 1]);
@@ -394,17 +411,22 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             }
           }
         }
+        if ((warp & 3) == 0) HN_TR(g, i, 2);
         tmem_st32(tS, pk);  // P(i) over S columns 0..31 (this thread has read all 64 of them)
         tmem_wait_st();
+        if ((warp & 3) == 0) HN_TR(g, i, 3);
         fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_ready[g][buf]);
         __syncwarp();
+        if ((warp & 3) == 0) HN_TR(g, i, 4);
         if (exact) {  // the buffer S(i+2) will land in carries the current reference
           if (buf) m_in1 = (m_ref == -INFINITY) ? 0.f : m_ref; else m_in0 = (m_ref == -INFINITY) ? 0.f : m_ref;
         }
       }
       // ---- epilogue: un-normalised accumulator rows + reference max
+      const int row = lt * BM + trow;
+      const long part_row = ((static_cast<long>(b) * p.nsplit + split) * p.H + h) * p.L + row;
       mbar_wait(&acc_done[g], 0);
       fence_after_sync();
 #pragma unroll
@@ -431,6 +453,7 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   __syncthreads();
   if (warp == PRODUCER_WARP) tmem_dealloc<512>(tmem);
 }
+
 
 template <int KD, int G, int PMODE>
 int launch_small_t(const AttnArgs& a, cudaStream_t stream) {
@@ -464,11 +487,27 @@ int launch_small_t(const AttnArgs& a, cudaStream_t stream) {
       cudaFuncSetAttribute(attn_small_kernel<KD, G, PMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
   const long grid = static_cast<long>(p.ctas_per_stream) * a.batch * a.nsplit;
   HN_REQUIRE(grid > 0 && grid < 2147483647L, "attention: grid too large");
+  p.mask_words = p.tiles_total;
+  p.trace = g_trace_buf;
+  if (g_trace_buf != nullptr && (PMODE == 5 || PMODE == 9)) {
+    HN_CHECK_CUDA(cudaFuncSetAttribute(attn_small_kernel<KD, G, PMODE, true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attn_small_kernel<KD, G, PMODE, true><<<static_cast<unsigned>(grid), (5 * G + 1) * 32, SMEM, stream>>>(tmQ, tmZ, p);
+  } else
   attn_small_kernel<KD, G, PMODE><<<static_cast<unsigned>(grid), (5 * G + 1) * 32, SMEM, stream>>>(tmQ, tmZ, p);
   HN_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 }  // namespace
+
+static int poly_mode() {
+  static int pmode = -1;  // tuning knob (HN_POLY_MODE=0..9): share of the exponentials on the FMA pipe
+  if (pmode < 0) {
+    const char* e = getenv("HN_POLY_MODE");
+    pmode = (e != nullptr && e[0] >= '0' && e[0] <= '9') ? e[0] - '0' : 5;
+  }
+  return pmode;
+}
 
 int small_attention_groups(int kd) { return kd == 32 ? 3 : 2; }
 
@@ -488,13 +527,20 @@ int small_attention_pick_nsplit(int batch, int L, int H, long N, int kd) {
     const long ctas = base * s;
     const long waves = (ctas + slots - 1) / slots;
     const long per = (tiles + s - 1) / s;
-    const double cost = static_cast<double>(waves) * (per + 8.0);
+    // every extra split also costs a set of partials (written here, re-read by the combine kernel)
+    const double cost = static_cast<double>(waves) * (per + 8.0) * (1.0 + 0.001 * s);
     if (cost < best_cost * 0.999) {
       best_cost = cost;
       best = s;
     }
   }
   return static_cast<int>(best);
+}
+
+template <int PMODE>
+static int launch_small_variant(const AttnArgs& a, cudaStream_t stream) {
+  if (a.kd == 64) return launch_small_t<64, 2, PMODE>(a, stream);
+  return launch_small_t<32, 3, PMODE>(a, stream);
 }
 
 int launch_small_attention(const AttnArgs& a, cudaStream_t stream) {
@@ -504,25 +550,18 @@ int launch_small_attention(const AttnArgs& a, cudaStream_t stream) {
   HN_REQUIRE(a.q_ld % 8 == 0, "attention: row pitches must be multiples of 8 elements");
   HN_REQUIRE(a.N < (1L << 31), "attention: token axis too long");
   HN_REQUIRE(a.c_ones >= 1 && a.c_ones < a.kd, "attention: ones column must lie inside the context row");
-  if (a.kd == 64) return launch_small_t<64, 2, 5>(a, stream);
-  static int pmode = -1;  // tuning knob (HN_POLY_MODE=0..8); default 5: every third column pair on the FMA pipe (half2); 5 and 6 measured equal and best
-  if (pmode < 0) {
-    const char* e = getenv("HN_POLY_MODE");
-    pmode = (e != nullptr && e[0] >= '0' && e[0] <= '8') ? e[0] - '0' : 5;
-    if (e != nullptr && e[0] == '9') pmode = 9;
-  }
-  switch (pmode) {
-    case 0: return launch_small_t<32, 3, 0>(a, stream);
-    case 2: return launch_small_t<32, 3, 2>(a, stream);
-    case 3: return launch_small_t<32, 3, 3>(a, stream);
-    case 4: return launch_small_t<32, 3, 4>(a, stream);
-    case 7: return launch_small_t<32, 3, 7>(a, stream);
-    case 8: return launch_small_t<32, 3, 8>(a, stream);
-    case 1: return launch_small_t<32, 3, 1>(a, stream);
-    case 6: return launch_small_t<32, 3, 6>(a, stream);
-    case 9: return launch_small_t<32, 3, 9>(a, stream);
-    default: return launch_small_t<32, 3, 5>(a, stream);
+  switch (poly_mode()) {
+    case 0: return launch_small_variant<0>(a, stream);
+    case 6: return launch_small_variant<6>(a, stream);
+    case 7: return launch_small_variant<7>(a, stream);
+    case 9: return launch_small_variant<9>(a, stream);
+    default: return launch_small_variant<5>(a, stream);
   }
 }
 
 }  // namespace hn
+
+// debug hook (not part of include/healnet_b200.h): timeline buffer for tools/trace_attn.py, 2*MAXG*TR_NT*TR_NP int64
+extern "C" __attribute__((visibility("default"))) void hn_debug_set_trace(void* dev_buf) {
+  hn::g_trace_buf = static_cast<long long*>(dev_buf);
+}
