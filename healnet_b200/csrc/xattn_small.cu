@@ -17,10 +17,11 @@
 //     sits on the critical path;
 //   * softmax threads own one latent row (one TMEM lane) and work in 32-column chunks (S -> P in place of
 //     registers, ~80 regs/thread);
-//   * a third of the exponentials are evaluated on the FMA / ALU pipes, two at a time in half2 arithmetic (Cody-Waite
+//   * half of the exponentials are evaluated on the FMA / ALU pipes, two at a time in half2 arithmetic (Cody-Waite
 //     range reduction + degree-3 minimax polynomial + integer exponent insert, 12 instructions per column pair
 //     incl. the fp16 pack) so MUFU only sees the rest (pipe microbenchmark: 23 elem/clk/SM for a 3/8 fp32
-//     mix vs 16 for MUFU alone, tools/microbench/mb_pipes.cu; HN_POLY_MODE sweeps the share, 1/3 .. 1/2 measured best);
+//     mix vs 16 for MUFU alone, tools/microbench/mb_pipes.cu; HN_POLY_MODE sweeps the share; 1/2 measured best once the
+//     per-tile bookkeeping was taken off the serial path, tools/microbench/mb_softmax.cu gives the no-sync bound);
 //   * the running max is a lazily raised reference: the steady state does no max pass at all — it only tracks
 //     the max of the packed fp16 P words (VIMNMX3.U16x2, a quarter of an instruction per element) and falls
 //     back to the exact two-pass path when a P exceeds 2^8 (or on the first / a masked / the ragged last tile);
@@ -32,6 +33,7 @@
 // stretched that warp's tile and with it the whole group's; last warp = TMA producer (Q' tiles once, z tiles
 // through an 8-stage mbarrier ring). TMEM per group: S/P buffer 0 (64) | S/P buffer 1 (64) | U (KD).
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 #include "tc05.cuh"
@@ -139,7 +141,7 @@ __device__ __forceinline__ uint32_t ex2_pair_h2(float x0, float x1) {
 // PMODE >= 5: which column PAIRS take the half2 polynomial: 5 = 1/3, 6 = 1/2, 7 = 2/3, 8 = 3/4
 template <int PMODE>
 __device__ __forceinline__ constexpr bool poly_pair(int j) {
-  return PMODE == 5 ? (j % 3) == 1 : PMODE == 6 ? (j % 2) == 1 : PMODE == 7 ? (j % 3) != 1 : PMODE == 8 ? (j % 4) != 1 : false;
+  return PMODE == 5 ? (j % 3) == 1 : PMODE == 6 ? (j % 2) == 1 : PMODE == 7 ? (j % 3) != 1 : false;
 }
 // byte offset of element (row, col) inside a TMA-swizzled [rows][KD] fp16 tile (64-byte rows -> SWIZZLE_64B,
 // 128-byte rows -> SWIZZLE_128B): the 16-byte chunk index is XORed with the low bits of (row-pair | row)
@@ -298,23 +300,29 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       float m_ref = -INFINITY;  // reference max (log2 units), always exactly representable in fp16
       float m_in0 = 0.f, m_in1 = 0.f;  // offset baked into S buffer 0 / 1 by the fold (0: none)
 
-      // tiles [0, n_full) of this CTA's range are complete 64-token tiles; only the globally last tile can be ragged
+      // tiles [0, n_steady) can take the steady-state path (complete, unmasked 64-token tiles; only the globally last
+      // tile of the token axis can be ragged)
       const int n_full = (t_end == p.tiles_total && (p.N % BT) != 0) ? n - 1 : n;
       const bool has_mask = p.mask_bits != nullptr;
-      int stale = 0;  // warp-uniform: > 0 while the S buffer about to be read was computed before the last raise
+      const int n_steady = has_mask ? 0 : n_full;
+      // warp-uniform: true while the S buffer about to be read was computed before the last raise (and for tile 0,
+      // which has no reference yet)
+      bool stale = true;
+      bool ready = false;  // s_full of the tile about to start was already seen complete (tested inside the previous tile)
 
-      for (int i = 0; i < n; ++i) {
-        const int buf = i & 1;
+      // One tile; BUF is a compile-time constant (the loop below is unrolled by two) so that every barrier / TMEM
+      // address is an immediate offset and the per-tile bookkeeping stays off the serial path.
+      auto tile = [&](const int i, auto buf_c, const uint32_t ph) {
+        constexpr int buf = decltype(buf_c)::value;
         const uint32_t tS = tL + buf * 64;
-
         if ((warp & 3) == 0) HN_TR(g, i, 0);
-        mbar_wait(&s_full[g][buf], (i >> 1) & 1);
+        if (!ready) mbar_wait(&s_full[g][buf], ph);
         if ((warp & 3) == 0) HN_TR(g, i, 1);
         fence_after_sync();
+        ready = false;
 
-        // steady state needs: a full unmasked tile whose folded offset is the current reference (all warp-uniform)
-        bool exact = has_mask || i >= n_full || i == 0 || stale > 0;
-        stale = 0;
+        bool exact = stale || i >= n_steady;
+        stale = false;
         uint32_t pk[32];  // P(i) as packed fp16 pairs; stored over S columns 0..31 once the whole row is known good
         if (!exact) {
           // ---------------- steady state: P = 2^S chunk by chunk; no max pass, no subtraction, no mask
@@ -339,6 +347,9 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
               }
               pmax = vmaxu2(pmax, pk[c * 16 + j]);
             }
+            // S(i+1) has normally been complete for most of a tile: test its barrier here, where the ~100 clk of the
+            // try_wait hide behind the second half's exponentials, instead of opening the next tile with it
+            if (c == 0) ready = mbar_try_wait(&s_full[g][buf ^ 1], buf ? (ph ^ 1) : ph);
           }
           const bool big = ((pmax & 0xFFFFu) > P_RAISE_BITS) || ((pmax >> 16) > P_RAISE_BITS);
           exact = __any_sync(0xffffffffu, big);  // some P above 2^8 (or inf / garbage): redo with a raised reference
@@ -346,10 +357,10 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         if (exact) {
           // ---------------- exact path (first tiles, masked / ragged tile, stale fold, or the reference max has
           // to be raised): max pass, rescale, exp pass. TMEM holds s - m_in (nothing has been overwritten yet).
-          const int tile = t_begin + i;
+          const int tile_idx = t_begin + i;
           uint64_t bits = ~0ull;
-          if (has_mask) bits = p.mask_bits[static_cast<long>(b) * p.tiles_total + tile];
-          const long rem = p.N - static_cast<long>(tile) * BT;
+          if (has_mask) bits = p.mask_bits[static_cast<long>(b) * p.tiles_total + tile_idx];
+          const long rem = p.N - static_cast<long>(tile_idx) * BT;
           if (rem < BT) bits &= (1ull << rem) - 1ull;
           const float m_in = buf ? m_in1 : m_in0;
           float mx = -INFINITY;
@@ -367,7 +378,7 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             }
           }
           mx += m_in;  // true row max of this tile (-inf stays -inf)
-          // raise lazily: keep the reference while the tile stays within 2^8 of it
+          // raise lazily: keep the reference while the tile stays within 2^5 of it
           const bool raise = __any_sync(0xffffffffu, mx > m_ref + RESCALE_THRESHOLD);
           if (raise) {
             // round the new reference to fp16 so that the folded offset IS the reference
@@ -389,14 +400,18 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
               }
             }
             // S(i+1) may still be reading Q': wait for it before changing the folded offset
-            if (i + 1 < n) mbar_wait(&s_full[g][buf ^ 1], ((i + 1) >> 1) & 1);
+            if (i + 1 < n) {
+              mbar_wait(&s_full[g][buf ^ 1], buf ? (ph ^ 1) : ph);
+              ready = true;
+            }
             m_ref = m_new;
             const float fold = (m_ref == -INFINITY) ? 0.f : -m_ref;
             *reinterpret_cast<__half*>(qrow_fold + swizzled_off<KD>(trow, p.c_ones)) = __float2half_rn(fold);
             fence_proxy_async_smem();
-            stale = 1;  // S(i+1) was computed with the previous offset
+            stale = true;  // S(i+1) was computed with the previous offset
           }
-          const float delta = m_in - ((m_ref == -INFINITY) ? 0.f : m_ref);
+          const float m_cur = (m_ref == -INFINITY) ? 0.f : m_ref;
+          const float delta = m_in - m_cur;
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             uint32_t s[32];
@@ -410,6 +425,8 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
               pk[c * 16 + j] = pack_half2(ex2_mufu(a + delta), ex2_mufu(bb + delta));
             }
           }
+          // the tile S(i+2) that will land in this buffer carries the current reference
+          if (buf) m_in1 = m_cur; else m_in0 = m_cur;
         }
         if ((warp & 3) == 0) HN_TR(g, i, 2);
         tmem_st32(tS, pk);  // P(i) over S columns 0..31 (this thread has read all 64 of them)
@@ -420,9 +437,15 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         if (lane == 0) mbar_arrive(&p_ready[g][buf]);
         __syncwarp();
         if ((warp & 3) == 0) HN_TR(g, i, 4);
-        if (exact) {  // the buffer S(i+2) will land in carries the current reference
-          if (buf) m_in1 = (m_ref == -INFINITY) ? 0.f : m_ref; else m_in0 = (m_ref == -INFINITY) ? 0.f : m_ref;
+      };
+      {
+        int i = 0;
+        uint32_t ph = 0;
+        for (; i + 1 < n; i += 2, ph ^= 1) {
+          tile(i, std::integral_constant<int, 0>{}, ph);
+          tile(i + 1, std::integral_constant<int, 1>{}, ph);
         }
+        if (i < n) tile(i, std::integral_constant<int, 0>{}, ph);
       }
       // ---- epilogue: un-normalised accumulator rows + reference max
       const int row = lt * BM + trow;
@@ -489,7 +512,7 @@ int launch_small_t(const AttnArgs& a, cudaStream_t stream) {
   HN_REQUIRE(grid > 0 && grid < 2147483647L, "attention: grid too large");
   p.mask_words = p.tiles_total;
   p.trace = g_trace_buf;
-  if (g_trace_buf != nullptr && (PMODE == 5 || PMODE == 9)) {
+  if (g_trace_buf != nullptr && (PMODE == 6 || PMODE == 9)) {
     HN_CHECK_CUDA(cudaFuncSetAttribute(attn_small_kernel<KD, G, PMODE, true>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attn_small_kernel<KD, G, PMODE, true><<<static_cast<unsigned>(grid), (5 * G + 1) * 32, SMEM, stream>>>(tmQ, tmZ, p);
@@ -504,7 +527,7 @@ static int poly_mode() {
   static int pmode = -1;  // tuning knob (HN_POLY_MODE=0..9): share of the exponentials on the FMA pipe
   if (pmode < 0) {
     const char* e = getenv("HN_POLY_MODE");
-    pmode = (e != nullptr && e[0] >= '0' && e[0] <= '9') ? e[0] - '0' : 5;
+    pmode = (e != nullptr && e[0] >= '0' && e[0] <= '9') ? e[0] - '0' : 6;
   }
   return pmode;
 }
@@ -552,10 +575,10 @@ int launch_small_attention(const AttnArgs& a, cudaStream_t stream) {
   HN_REQUIRE(a.c_ones >= 1 && a.c_ones < a.kd, "attention: ones column must lie inside the context row");
   switch (poly_mode()) {
     case 0: return launch_small_variant<0>(a, stream);
-    case 6: return launch_small_variant<6>(a, stream);
+    case 5: return launch_small_variant<5>(a, stream);
     case 7: return launch_small_variant<7>(a, stream);
     case 9: return launch_small_variant<9>(a, stream);
-    default: return launch_small_variant<5>(a, stream);
+    default: return launch_small_variant<6>(a, stream);
   }
 }
 
