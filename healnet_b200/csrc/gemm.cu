@@ -16,7 +16,7 @@
 //
 // Persistent kernel, one CTA per SM, static round-robin over the 128 x BN output tiles (m fastest, so CTAs that run
 // side by side read the same weight tile): warp 0 = TMA producer, warp 1 = single-thread UMMA issuer (+ TMEM
-// allocator), warps 2..5 = epilogue (each thread owns one accumulator row = one TMEM lane). These GEMMs have few rows
+// allocator), warps 2..9 = epilogue (each thread owns one accumulator row = one TMEM lane, two warps per quadrant). These GEMMs have few rows
 // (M = batch * L = 2048 at cfg 1), so they are bound by the bytes an SM has to pull in from L2 per k-tile, not by the
 // tensor pipe. Hence:
 //   * every distinct operand tile is loaded ONCE per k-tile — a stage holds [A_hi | A_lo | B_hi | B_lo] and feeds the
@@ -50,6 +50,7 @@ struct GemmDev {
   int a_seg, b_seg;  // column offset of the lo segment of A / B (elements)
   int out_seg;       // fp16 outputs: > 0 -> also store lo = fp16(v - hi) at column + out_seg
   int stages;        // depth of the operand ring (host: as many as fit the SM's shared memory, <= 8)
+  int bias_vec;      // bias is 16-byte aligned -> float4 loads
 };
 
 __device__ __forceinline__ void split_half(float v, __half& hi, __half& lo) {
@@ -76,8 +77,10 @@ __device__ __forceinline__ float leaky_f(float x) { return x > 0.f ? x : 0.01f *
 constexpr int MAX_STAGES = 8;
 constexpr int SMEM_BUDGET = 220 * 1024;
 
+constexpr int EPI_WARPS = 8;  // two per TMEM lane quadrant: each takes every other 32-column chunk of the tile
+
 template <int BN, int BK>
-__global__ void __launch_bounds__(192, 1) gemm_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__((2 + EPI_WARPS) * 32, 1) gemm_kernel(const __grid_constant__ CUtensorMap tmA,
                                                       const __grid_constant__ CUtensorMap tmB, GemmDev p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -103,7 +106,7 @@ __global__ void __launch_bounds__(192, 1) gemm_kernel(const __grid_constant__ CU
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], 4);
+      mbar_init(&acc_empty[a], EPI_WARPS);
     }
     fence_mbar_init();
   }
@@ -163,8 +166,11 @@ __global__ void __launch_bounds__(192, 1) gemm_kernel(const __grid_constant__ CU
       }
     }
   } else {
-    // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
+    // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32); the two warps of a quadrant interleave
+    // the 32-column chunks (a single warp per scheduler advances at ~0.2 IPC on this dependent code: the FF1 gate
+    // epilogue, not the tensor pipe, used to bound that GEMM)
     const uint32_t lane_base = (warp & 3) * 32;
+    const int chunk0 = (warp - 2) >> 2;
     int j = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
     const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
@@ -175,7 +181,7 @@ __global__ void __launch_bounds__(192, 1) gemm_kernel(const __grid_constant__ CU
     mbar_wait_sleepy(&acc_full[acc], (j >> 1) & 1, 2000);
     fence_after_sync();
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = chunk0; c < BN / 32; c += EPI_WARPS / 4) {
       uint32_t r[32];
       tmem_ld32(tmem_addr(tD, lane_base, c * 32), r);
       tmem_wait_ld();
@@ -183,11 +189,22 @@ __global__ void __launch_bounds__(192, 1) gemm_kernel(const __grid_constant__ CU
       if (nb >= p.N) continue;
       const bool full = (nb + 32 <= p.N) && p.vec_ok;
       float v[32];
+      if (p.bias_vec && nb + 32 <= p.N) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float b = 0.f;
-        if (p.bias != nullptr && nb + j < p.N) b = __ldg(p.bias + nb + j);
-        v[j] = __uint_as_float(r[j]) + b;
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
+          v[j] = __uint_as_float(r[j]) + b4.x;
+          v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
+          v[j + 2] = __uint_as_float(r[j + 2]) + b4.z;
+          v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float b = 0.f;
+          if (p.bias != nullptr && nb + j < p.N) b = __ldg(p.bias + nb + j);
+          v[j] = __uint_as_float(r[j]) + b;
+        }
       }
       if (row_ok) {
       if (p.epi == EPI_F16) {
@@ -293,7 +310,8 @@ int launch_t(const GemmArgs& a, cudaStream_t stream) {
   int stages = SMEM_BUDGET / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   GemmDev p{a.M, a.N, a.K, a.epi, a.act, a.bias, a.out, a.ldo, vec_ok, a.terms, a.a_seg, a.b_seg,
-            half_out ? a.out_seg : 0, stages};
+            half_out ? a.out_seg : 0, stages,
+            (a.bias != nullptr && (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0) ? 1 : 0};
   const int smem = stages * stage_bytes + 1024;
   int dev = 0, sms = 0;
   HN_CHECK_CUDA(cudaGetDevice(&dev));
@@ -303,7 +321,7 @@ int launch_t(const GemmArgs& a, cudaStream_t stream) {
                                      SMEM_BUDGET + 1024));
   const long n_tiles = static_cast<long>((a.N + BN - 1) / BN) * ((a.M + BM - 1) / BM);
   const unsigned grid = static_cast<unsigned>(n_tiles < sms ? n_tiles : sms);
-  gemm_kernel<BN, BK><<<grid, 192, smem, stream>>>(tmA, tmB, p);
+  gemm_kernel<BN, BK><<<grid, (2 + EPI_WARPS) * 32, smem, stream>>>(tmA, tmB, p);
   HN_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -318,7 +336,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   HN_REQUIRE(a.terms >= 1 && a.terms <= 3, "gemm: terms must be 1, 2 or 3");
   if (a.terms >= 2) HN_REQUIRE(a.b_seg % 64 == 0 && a.b_seg >= a.K, "gemm: B lo segment must start at a multiple of 64 >= K");
   if (a.terms == 3) HN_REQUIRE(a.a_seg % 64 == 0 && a.a_seg >= a.K, "gemm: A lo segment must start at a multiple of 64 >= K");
-  // widest tile that still gives (nearly) every SM one; k-tiles of 32 for the four-operand stages
+  // widest tile that still gives (nearly) every SM one
   const long mt = (a.M + BM - 1) / BM;
   const long tiles256 = static_cast<long>((a.N + 255) / 256) * mt;
   const long tiles128 = static_cast<long>((a.N + 127) / 128) * mt;
@@ -330,7 +348,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     force_bk = k ? atoi(k) : 0;
   }
   const int bn = force ? force : (tiles256 >= 120 ? 256 : tiles128 >= 120 ? 128 : 64);
-  const int bk = force_bk ? force_bk : (a.terms == 3 ? 32 : 64);
+  const int bk = force_bk ? force_bk : 64;  // 128-byte operand rows: half the L2 requests of BK = 32 (measured faster for every shape)
   if (bn == 256) return bk == 64 ? launch_t<256, 64>(a, stream) : launch_t<256, 32>(a, stream);
   if (bn == 128) return bk == 64 ? launch_t<128, 64>(a, stream) : launch_t<128, 32>(a, stream);
   return bk == 64 ? launch_t<64, 64>(a, stream) : launch_t<64, 32>(a, stream);
