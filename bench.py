@@ -223,14 +223,19 @@ def run_gpu_arm(args):
 
     torch.manual_seed(0)
     model = HealNet(**kwargs).eval().to(dev)
-    g = torch.Generator().manual_seed(rank)
+    token_shard = args.shard == "tokens" and world > 1
+    # batch sharding (default): every rank owns its own samples; token sharding: every rank sees the SAME samples and
+    # streams 1/world of each long token axis (strong scaling of a batch too small to spread over the GPUs)
+    g = torch.Generator().manual_seed(0 if token_shard else rank)
     host = [torch.rand((batch,) + tuple(s), generator=g).pin_memory() for s in shapes]
     resident = [t.to(dev) for t in host]
-    global_batch = batch * world
+    global_batch = batch if token_shard else batch * world
+    if token_shard:
+        model.enable_token_sharding(min_tokens=8192, max_batch=batch)
 
     def step_resident():
         out = model(list(resident))
-        return gather_rows(out, global_batch) if world > 1 else out
+        return gather_rows(out, global_batch) if (world > 1 and not token_shard) else out
 
     def step_e2e():
         out = model(list(host))          # pinned host tensors in, host logits out (H2D + D2H inside)
@@ -290,11 +295,13 @@ def run_gpu_arm(args):
         exp_rate = kt["exps"] / max(kt["ms"], 1e-9) / 1e-3
         line = dict(
             metric=METRIC, value=value, unit="samples/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
-            ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+            ms_per_step=ms_per_step, higher_is_better=True, scaling="strong" if token_shard else "weak",
+            vs_baseline=None, dtype="f32",
             data="synthetic",
             config=dict(workload=args.workload, batch_per_gpu=batch, global_batch=global_batch,
                         shapes=[list(s) for s in shapes], depth=cfg.depth, l_c=cfg.l_c, l_d=cfg.l_d,
-                        parallelism=f"batch-sharded x{world}", operands="fp16 (split hi/lo on the latent side), fp32 accumulate",
+                        parallelism=(f"token-axis sharded x{world} (partials merged over NVLink peer memory)"
+                                     if token_shard else f"batch-sharded x{world}"), operands="fp16 (split hi/lo on the latent side), fp32 accumulate",
                         l2="per-step working set (standardised context rows + inputs) exceeds the 126 MB L2"),
             clocks=dict(sm_mhz=csum["sm_mhz"], sm_max_mhz=csum["sm_max_mhz"], reasons=csum["reasons"]),
             e2e=dict(value=global_batch * args.steps / e2e_s, unit="samples/s",
@@ -304,7 +311,7 @@ def run_gpu_arm(args):
                           frac=achieved / peaks["tflops"],
                           traffic=load_traffic() if args.workload == "cfg1" and batch == 4 else None,
                           peak_source=peaks["src"],
-                          kernel="attn_small_kernel<32,3,1> (volume cross-attention, xattn_small.cu)", kernel_ms=k_ms,
+                          kernel="attn_small_kernel<32,3,6> (volume cross-attention, xattn_small.cu)", kernel_ms=k_ms,
                           kernel_share_of_step=kt["ms"] / ms_per_step if ms_per_step > 0 else None,
                           flops="executed (reassociated small-context form, padded tiles)",
                           exp_per_s=exp_rate, exp_frac_of_mufu=exp_rate / (148 * 16 * sm_hz)),
@@ -330,6 +337,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg1", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
+    ap.add_argument("--shard", default="batch", choices=["batch", "tokens"],
+                    help="multi-GPU partitioning: batch (weak scaling, default) or tokens (strong scaling of one batch)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline sample")
     args = ap.parse_args()

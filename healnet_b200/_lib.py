@@ -54,6 +54,17 @@ SIGNATURES = {
                            c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "hn_forward_ex": (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int), POINTER(c_int),
                               c_void_p, c_long, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "hn_exchange_bytes": (c_size_t, [c_void_p, c_int]),
+    "hn_exchange_alloc": (c_int, [c_size_t, POINTER(c_void_p), c_void_p]),
+    "hn_exchange_open": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "hn_exchange_close": (c_int, [c_void_p]),
+    "hn_exchange_free": (c_int, [c_void_p]),
+    "hn_set_exchange": (c_int, [c_void_p, c_int, c_int, POINTER(c_void_p), c_size_t]),
+    "hn_exchange_error": (c_int, [c_void_p, POINTER(c_int)]),
+    "hn_workspace_bytes_split": (c_size_t, [c_void_p, c_int, POINTER(c_int), POINTER(c_long)]),
+    "hn_forward_split": (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int), POINTER(c_long),
+                                 POINTER(c_long), POINTER(c_int), c_void_p, c_long, c_void_p, c_void_p, c_void_p,
+                                 c_size_t, c_void_p]),
     "hn_last_launch_count": (c_int, [c_void_p]),
     "hn_set_attention_export": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "hn_profile_enable": (c_int, [c_void_p, c_int]),

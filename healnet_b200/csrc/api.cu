@@ -94,6 +94,11 @@ struct hn_handle {
   std::vector<int> ev_mod;              // modality of each recorded slot in the last forward
   std::vector<double> ev_flops;         // tensor-core FLOPs the launch executed (padded tiles included)
   std::vector<double> ev_exps;          // softmax exponentials the launch evaluated
+  // token-axis sharding across GPUs (hn_set_exchange): peer-mapped exchange buffers, own rank included
+  int x_rank = 0, x_world = 0;
+  char* x_bufs[HN_MAX_PEERS] = {};
+  size_t x_bytes = 0;
+  unsigned long long x_seq = 0;         // exchanges published so far (all ranks advance in lock step)
 };
 
 namespace {
@@ -174,7 +179,10 @@ struct ModPlan {
   int segC = 0;
   int C = 0, c_raw = 0, n_axes = 0;
   int axes[HN_MAX_AXES];
-  long N = 0;
+  long N = 0;       // tokens of the modality (decides the path, so every rank of a token-sharded run agrees)
+  long Nl = 0;      // tokens held by this rank (== N unless the token axis is sharded across GPUs)
+  long tok0 = 0;    // first local token on the full axis
+  bool sharded = false;
   int nsplit = 1;
   bool masked = false;
   float* tab = nullptr;
@@ -200,7 +208,7 @@ struct Workspace {
 
 // Lays the forward workspace out over `base` (null: sizing pass). present[m] tells which modalities are given.
 int plan_workspace(const hn_handle* h, int batch, const int* axis_sizes, const bool* present, long mask_tokens,
-                   char* base, Workspace& ws) {
+                   char* base, Workspace& ws, const long* tok_begin = nullptr, const long* tok_count = nullptr) {
   const hn_desc& d = h->d;
   const int M = h->M, L = d.l_c, D = d.l_d;
   Arena ar;
@@ -233,33 +241,41 @@ int plan_workspace(const hn_handle* h, int batch, const int* axis_sizes, const b
       mp.N *= mp.axes[a];
     }
     HN_REQUIRE(mp.N < (1L << 31), "hn_forward: token axis too long");
+    mp.Nl = mp.N;
+    if (tok_count != nullptr && tok_count[m] > 0 && tok_count[m] < mp.N) {
+      mp.sharded = true;
+      mp.Nl = tok_count[m];
+      mp.tok0 = tok_begin != nullptr ? tok_begin[m] : 0;
+      HN_REQUIRE(mp.tok0 >= 0 && mp.tok0 + mp.Nl <= mp.N, "hn_forward_split: token range outside the modality");
+      HN_REQUIRE(mp.N > PRECISE_MAX_TOKENS, "hn_forward_split: short token axes are replicated, not sharded");
+    }
     mp.small = mp.C <= 63 && mp.N > PRECISE_MAX_TOKENS;
-    mp.masked = (mask_tokens > 0 && mask_tokens == mp.N);
+    mp.masked = (mask_tokens > 0 && mask_tokens == mp.Nl);
     int axsum = 0;
     for (int a = 0; a < mp.n_axes; ++a) axsum += mp.axes[a];
     mp.tab = ar.take<float>(static_cast<size_t>(axsum) * (2 * d.num_freq_bands + 1));
     const int vd = mp.small ? (mp.C <= 31 ? 32 : 64) : h->hpx;
     if (mp.small) {
       mp.zw = vd;
-      mp.z = ar.take<__half>(static_cast<size_t>(batch) * mp.N * mp.zw);
+      mp.z = ar.take<__half>(static_cast<size_t>(batch) * mp.Nl * mp.zw);
       qw = qw > d.x_heads * mp.zw ? qw : d.x_heads * mp.zw;
     } else {
       mp.precise = mp.N <= PRECISE_MAX_TOKENS;
       mp.segC = seg_of(mp.C);
       mp.ldz = mp.precise ? 2 * mp.segC : ctx_ld(mp.C);
-      mp.z = ar.take<__half>(static_cast<size_t>(batch) * mp.N * mp.ldz);
-      const size_t kv = static_cast<size_t>(batch) * mp.N * 2 * d.x_heads * h->hpx * (mp.precise ? 2 : 1);
+      mp.z = ar.take<__half>(static_cast<size_t>(batch) * mp.Nl * mp.ldz);
+      const size_t kv = static_cast<size_t>(batch) * mp.Nl * 2 * d.x_heads * h->hpx * (mp.precise ? 2 : 1);
       kv_elems = kv > kv_elems ? kv : kv_elems;
       qw = qw > d.x_heads * h->hpx ? qw : d.x_heads * h->hpx;
     }
     ow = ow > d.x_heads * h->hpx ? ow : d.x_heads * h->hpx;
-    mp.nsplit = mp.small ? small_attention_pick_nsplit(batch, L, d.x_heads, mp.N, vd)
-                         : attention_pick_nsplit(batch, L, d.x_heads, mp.N);
+    mp.nsplit = mp.small ? small_attention_pick_nsplit(batch, L, d.x_heads, mp.Nl, vd)
+                         : attention_pick_nsplit(batch, L, d.x_heads, mp.Nl);
     const size_t pa = static_cast<size_t>(batch) * mp.nsplit * d.x_heads * n_ltiles * 128 * vd;
     const size_t pm = static_cast<size_t>(batch) * mp.nsplit * d.x_heads * n_ltiles * 128 * 2;
     part_acc_elems = pa > part_acc_elems ? pa : part_acc_elems;
     part_ml_elems = pm > part_ml_elems ? pm : part_ml_elems;
-    if (mp.masked) mask_words = static_cast<size_t>(batch) * ((mp.N + 63) / 64);
+    if (mp.masked) mask_words = static_cast<size_t>(batch) * ((mp.Nl + 63) / 64);
   }
   ws.q = ar.take<__half>(rows * 2 * (qw > 8 ? qw : 8));
   ws.o = ar.take<__half>(rows * 2 * (ow > 8 ? ow : 8));
@@ -494,6 +510,23 @@ size_t hn_workspace_bytes(const hn_handle* h, int batch, const int* axis_sizes) 
   return ws.bytes + static_cast<size_t>(batch) * ((mask_tokens + 63) / 64) * 8 + 256;
 }
 
+size_t hn_workspace_bytes_split(const hn_handle* h, int batch, const int* axis_sizes, const long* tok_count) {
+  if (h == nullptr || batch < 1 || axis_sizes == nullptr || tok_count == nullptr) {
+    set_error("hn_workspace_bytes_split: bad argument");
+    return 0;
+  }
+  Workspace ws;
+  long mask_tokens = 0;
+  for (int m = 0; m < h->M; ++m) {
+    long n = 1;
+    for (int a = 0; a < h->d.num_spatial_axes[m]; ++a) n *= axis_sizes[m * HN_MAX_AXES + a];
+    if (tok_count[m] > 0 && tok_count[m] < n) n = tok_count[m];
+    mask_tokens = n > mask_tokens ? n : mask_tokens;
+  }
+  if (plan_workspace(h, batch, axis_sizes, nullptr, 0, nullptr, ws, nullptr, tok_count) != 0) return 0;
+  return ws.bytes + static_cast<size_t>(batch) * ((mask_tokens + 63) / 64) * 8 + 256;
+}
+
 int hn_last_launch_count(const hn_handle* h) { return h ? h->launches : 0; }
 
 int hn_set_attention_export(hn_handle* h, int layer, int module, float* dev_out) {
@@ -535,10 +568,128 @@ int hn_forward(hn_handle* h, int batch, const void* const* modality_ptrs, const 
                        logits_out, workspace, workspace_bytes, cuda_stream);
 }
 
+static int forward_impl(hn_handle* h, int batch, const void* const* modality_ptrs, void* const* modality_ready_events,
+                        const int* axis_sizes, const long* tok_begin, const long* tok_count,
+                        const int* skip_latent_block, const uint8_t* mask, long mask_tokens, float* latents_out,
+                        float* logits_out, void* workspace, size_t workspace_bytes, void* cuda_stream);
+
 int hn_forward_ex(hn_handle* h, int batch, const void* const* modality_ptrs, void* const* modality_ready_events,
                   const int* axis_sizes, const int* skip_latent_block, const uint8_t* mask, long mask_tokens,
                   float* latents_out, float* logits_out, void* workspace, size_t workspace_bytes,
                   void* cuda_stream) {
+  return forward_impl(h, batch, modality_ptrs, modality_ready_events, axis_sizes, nullptr, nullptr, skip_latent_block,
+                      mask, mask_tokens, latents_out, logits_out, workspace, workspace_bytes, cuda_stream);
+}
+
+int hn_forward_split(hn_handle* h, int batch, const void* const* modality_ptrs, void* const* modality_ready_events,
+                     const int* axis_sizes, const long* tok_begin, const long* tok_count,
+                     const int* skip_latent_block, const uint8_t* mask, long mask_tokens, float* latents_out,
+                     float* logits_out, void* workspace, size_t workspace_bytes, void* cuda_stream) {
+  HN_REQUIRE(tok_begin != nullptr && tok_count != nullptr, "hn_forward_split: token ranges required");
+  return forward_impl(h, batch, modality_ptrs, modality_ready_events, axis_sizes, tok_begin, tok_count,
+                      skip_latent_block, mask, mask_tokens, latents_out, logits_out, workspace, workspace_bytes,
+                      cuda_stream);
+}
+
+// bytes of one exchange slot (un-normalised accumulators + (max, sum) per (sample, head, latent row)), 256-aligned
+static size_t xchg_slot_bytes(const hn_handle* h, int batch) {
+  const size_t rows = static_cast<size_t>(batch) * h->d.x_heads * h->d.l_c;
+  const size_t w = h->hpx > 64 ? 128 : 64;  // widest accumulator row of any path (small-context rows are <= 64)
+  return ((rows * (w + 2) * sizeof(float)) + 255) & ~size_t(255);
+}
+
+size_t hn_exchange_bytes(const hn_handle* h, int batch) {
+  if (h == nullptr || batch < 1) return 0;
+  return sizeof(XchgHeader) + 2 * xchg_slot_bytes(h, batch);
+}
+
+int hn_exchange_alloc(size_t bytes, void** dev_ptr, unsigned char* ipc_handle_out) {
+  HN_REQUIRE(dev_ptr != nullptr && ipc_handle_out != nullptr && bytes >= sizeof(XchgHeader), "hn_exchange_alloc: bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+  void* p = nullptr;
+  HN_CHECK_CUDA(cudaMalloc(&p, bytes));
+  HN_CHECK_CUDA(cudaMemset(p, 0, bytes));
+  cudaIpcMemHandle_t hd;
+  cudaError_t e = cudaIpcGetMemHandle(&hd, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    set_error(std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+    return -10;
+  }
+  memcpy(ipc_handle_out, &hd, 64);
+  *dev_ptr = p;
+  return 0;
+}
+
+int hn_exchange_open(const unsigned char* ipc_handle, void** peer_ptr) {
+  HN_REQUIRE(ipc_handle != nullptr && peer_ptr != nullptr, "hn_exchange_open: null argument");
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, ipc_handle, 64);
+  HN_CHECK_CUDA(cudaIpcOpenMemHandle(peer_ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+
+int hn_exchange_close(void* peer_ptr) {
+  if (peer_ptr != nullptr) HN_CHECK_CUDA(cudaIpcCloseMemHandle(peer_ptr));
+  return 0;
+}
+
+int hn_exchange_free(void* dev_ptr) {
+  if (dev_ptr != nullptr) HN_CHECK_CUDA(cudaFree(dev_ptr));
+  return 0;
+}
+
+int hn_set_exchange(hn_handle* h, int rank, int world, void* const* bufs, size_t bytes) {
+  HN_REQUIRE(h != nullptr, "hn_set_exchange: null handle");
+  if (world <= 1 || bufs == nullptr) {
+    h->x_world = 0;
+    return 0;
+  }
+  HN_REQUIRE(world <= HN_MAX_PEERS && rank >= 0 && rank < world, "hn_set_exchange: at most 8 ranks");
+  for (int r = 0; r < world; ++r) {
+    HN_REQUIRE(bufs[r] != nullptr && (reinterpret_cast<uintptr_t>(bufs[r]) & 255) == 0,
+               "hn_set_exchange: exchange buffers must be 256-byte aligned device pointers");
+    h->x_bufs[r] = static_cast<char*>(bufs[r]);
+  }
+  h->x_rank = rank;
+  h->x_world = world;
+  h->x_bytes = bytes;
+  h->x_seq = 0;
+  return 0;
+}
+
+int hn_exchange_error(const hn_handle* h, int* error_out) {
+  HN_REQUIRE(h != nullptr && error_out != nullptr && h->x_world > 1, "hn_exchange_error: no exchange registered");
+  const XchgHeader* hdr = reinterpret_cast<const XchgHeader*>(h->x_bufs[h->x_rank]);
+  HN_CHECK_CUDA(cudaMemcpy(error_out, &hdr->error, sizeof(int), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// Publishes this rank's partials of one cross-attention pass and fills the peer table the combine kernel reads.
+static int exchange_partials(hn_handle* h, const Workspace& ws, int batch, int nsplit, int H, int L, int w,
+                             PeerParts& pp, cudaStream_t st) {
+  HN_REQUIRE(h->x_world > 1, "hn_forward_split: hn_set_exchange has not been called");
+  const size_t slot = xchg_slot_bytes(h, batch);
+  HN_REQUIRE(sizeof(XchgHeader) + 2 * slot <= h->x_bytes, "hn_forward_split: exchange buffer too small (hn_exchange_bytes)");
+  const unsigned long long seq = ++h->x_seq;
+  const size_t off = sizeof(XchgHeader) + (seq & 1) * slot;
+  const size_t rows = static_cast<size_t>(batch) * H * L;
+  pp.world = h->x_world;
+  pp.rank = h->x_rank;
+  pp.seq = seq;
+  for (int r = 0; r < h->x_world; ++r) {
+    pp.hdr[r] = reinterpret_cast<XchgHeader*>(h->x_bufs[r]);
+    pp.acc[r] = reinterpret_cast<const float*>(h->x_bufs[r] + off);
+    pp.ml[r] = pp.acc[r] + rows * w;
+  }
+  float* my_acc = reinterpret_cast<float*>(h->x_bufs[h->x_rank] + off);
+  return launch_merge_signal(ws.part_acc, ws.part_ml, batch, nsplit, H, L, w, my_acc, my_acc + rows * w, pp, st);
+}
+
+static int forward_impl(hn_handle* h, int batch, const void* const* modality_ptrs, void* const* modality_ready_events,
+                        const int* axis_sizes, const long* tok_begin, const long* tok_count,
+                        const int* skip_latent_block, const uint8_t* mask, long mask_tokens, float* latents_out,
+                        float* logits_out, void* workspace, size_t workspace_bytes, void* cuda_stream) {
   HN_REQUIRE(h != nullptr && modality_ptrs != nullptr && axis_sizes != nullptr, "hn_forward: null argument");
   HN_REQUIRE(batch >= 1, "hn_forward: batch must be >= 1");
   HN_REQUIRE(h->packed_valid, "hn_forward: call hn_pack_weights after registering / changing weights");
@@ -559,7 +710,8 @@ int hn_forward_ex(hn_handle* h, int batch, const void* const* modality_ptrs, voi
   for (int m = 0; m < M; ++m) present[m] = modality_ptrs[m] != nullptr;
   if (mask == nullptr) mask_tokens = 0;
   Workspace ws;
-  int rc = plan_workspace(h, batch, axis_sizes, present, mask_tokens, static_cast<char*>(workspace), ws);
+  int rc = plan_workspace(h, batch, axis_sizes, present, mask_tokens, static_cast<char*>(workspace), ws, tok_begin,
+                          tok_count);
   if (rc != 0) return rc;
   HN_REQUIRE(ws.bytes <= workspace_bytes, "hn_forward: workspace too small (see hn_workspace_bytes)");
   h->launches = 0;
@@ -583,13 +735,13 @@ int hn_forward_ex(hn_handle* h, int batch, const void* const* modality_ptrs, voi
     if (d.fourier_encode_data)
       HN_TRY(launch_axis_tables(mp.tab, mp.axes, mp.n_axes, d.num_freq_bands, d.max_freq, st));
     if (mp.small)
-      HN_TRY(launch_build_z_small(raw, mp.z, mp.zw, batch, mp.N, mp.c_raw, mp.n_axes, mp.axes, d.num_freq_bands,
-                                  mp.tab, d.fourier_encode_data, st));
+      HN_TRY(launch_build_z_small(raw, mp.z, mp.zw, batch, mp.Nl, mp.c_raw, mp.n_axes, mp.axes, d.num_freq_bands,
+                                  mp.tab, d.fourier_encode_data, st, mp.tok0));
     else
-      HN_TRY(launch_build_z_large(raw, mp.z, mp.ldz, mp.precise ? mp.segC : 0, batch, mp.N, mp.c_raw, mp.n_axes,
-                                  mp.axes, d.num_freq_bands, mp.tab, d.fourier_encode_data, st));
+      HN_TRY(launch_build_z_large(raw, mp.z, mp.ldz, mp.precise ? mp.segC : 0, batch, mp.Nl, mp.c_raw, mp.n_axes,
+                                  mp.axes, d.num_freq_bands, mp.tab, d.fourier_encode_data, st, mp.tok0));
     if (mp.masked && !mask_packed) {
-      HN_TRY(launch_pack_mask(mask, ws.mask_bits, batch, mp.N, st));
+      HN_TRY(launch_pack_mask(mask, ws.mask_bits, batch, mp.Nl, st));
       mask_packed = true;
     }
     return 0;
@@ -623,7 +775,11 @@ int hn_forward_ex(hn_handle* h, int batch, const void* const* modality_ptrs, voi
         aa.batch = batch;
         aa.L = L;
         aa.H = H;
-        aa.N = mp.N;
+        aa.N = mp.Nl;
+        PeerParts pp;
+        if (mp.sharded)
+          HN_REQUIRE(h->export_ptrs[l * (M + 1) + m] == nullptr,
+                     "hn_forward_split: attention-weight export is not available on a sharded token axis");
         aa.nsplit = mp.nsplit;
         aa.mask_bits = mp.masked ? ws.mask_bits : nullptr;
         aa.part_acc = ws.part_acc;
@@ -639,13 +795,15 @@ int hn_forward_ex(hn_handle* h, int batch, const void* const* modality_ptrs, voi
           HN_TRY(launch_attention(aa, st));
           profile_end(h, st);
           if (h->export_ptrs[l * (M + 1) + m] != nullptr) HN_TRY(launch_attn_export(aa, h->export_ptrs[l * (M + 1) + m], st));
+          if (mp.sharded) HN_TRY(exchange_partials(h, ws, batch, mp.nsplit, H, L, mp.zw, pp, st));
           HN_TRY(launch_combine_vproj(ws.part_acc, ws.part_ml, batch, mp.nsplit, H, L, mp.C, mp.zw,
-                                      d.cross_dim_head, ap.Wv, ap.bv, ws.o, 2 * ow, ow, HPx, st));
+                                      d.cross_dim_head, ap.Wv, ap.bv, ws.o, 2 * ow, ow, HPx, st,
+                                      mp.sharded ? &pp : nullptr));
         } else {
           // K/V projection of the standardised context (context LayerNorm affine folded into the weights).
           // Weights are always split (their rounding would not average out over tokens); z, K and V are split
           // only on short token axes.
-          const long tok = static_cast<long>(batch) * mp.N;
+          const long tok = static_cast<long>(batch) * mp.Nl;
           HN_REQUIRE(tok < (1L << 31), "hn_forward: batch * tokens too large for the K/V projection");
           const int kvw = 2 * H * HPx;
           GemmArgs gkv{mp.z, ap.Wkv, static_cast<int>(tok), kvw, mp.C, mp.ldz, 2 * mp.segC, EPI_F16, 0, ap.bkv,
@@ -667,7 +825,9 @@ int hn_forward_ex(hn_handle* h, int batch, const void* const* modality_ptrs, voi
           HN_TRY(launch_attention(aa, st));
           profile_end(h, st);
           if (h->export_ptrs[l * (M + 1) + m] != nullptr) HN_TRY(launch_attn_export(aa, h->export_ptrs[l * (M + 1) + m], st));
-          HN_TRY(launch_combine_generic(ws.part_acc, ws.part_ml, batch, mp.nsplit, H, L, ws.o, 2 * ow, ow, HPx, st));
+          if (mp.sharded) HN_TRY(exchange_partials(h, ws, batch, mp.nsplit, H, L, HPx, pp, st));
+          HN_TRY(launch_combine_generic(ws.part_acc, ws.part_ml, batch, mp.nsplit, H, L, ws.o, 2 * ow, ow, HPx, st,
+                                        mp.sharded ? &pp : nullptr));
         }
         // x = LeakyReLU(O Wo^T + bo) + x   (healnet.py:383-386, 426, 236)
         GemmArgs go{ws.o, ap.Wo, static_cast<int>(rows), D, ow, 2 * ow, 2 * ow, EPI_RES_LEAKY, 0, wa[7], ws.x, D,

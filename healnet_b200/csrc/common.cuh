@@ -71,13 +71,14 @@ int launch_layernorm_f16(const float* x, int ldx, const float* gamma, const floa
 int launch_axis_tables(float* tab, const int* axis_sizes, int n_axes, int n_bands, float max_freq,
                        cudaStream_t stream);
 // standardised context rows, small-C layout: z[b][N][zw] fp16 = [(v-mean)*rstd (C values), 1, 0...], zw = 32 | 64
+// (tok0: index of the first token of this buffer on the modality's full token axis; N = tokens in the buffer)
 int launch_build_z_small(const float* raw, __half* z, int zw, int batch, long N, int c_raw, int n_axes,
                          const int* axis_sizes /*host*/, int n_bands, const float* tab, int fourier,
-                         cudaStream_t stream);
+                         cudaStream_t stream, long tok0 = 0);
 // standardised context rows, generic layout: z[b*N][ldz] fp16 (pad cols zero); lo_seg > 0: split [hi | lo]
 int launch_build_z_large(const float* raw, __half* z, int ldz, int lo_seg, int batch, long N, int c_raw, int n_axes,
                          const int* axis_sizes /*host*/, int n_bands, const float* tab, int fourier,
-                         cudaStream_t stream);
+                         cudaStream_t stream, long tok0 = 0);
 // pooled head: logits[b][o] = LN(mean_L x[b]) . W[o] + bias[o]
 // (pooled: batch * D floats of scratch)
 int launch_head(const float* x, int batch, int L, int D, const float* ln_w, const float* ln_b, const float* W,
@@ -117,14 +118,39 @@ int attention_pick_nsplit(int batch, int L, int H, long N);
 int launch_small_attention(const AttnArgs& a, cudaStream_t stream);
 int small_attention_pick_nsplit(int batch, int L, int H, long N, int kd);
 
+// Token-axis sharding across GPUs: every rank reduces its own splits to ONE partial per
+// (sample, head, latent row) in its exchange buffer (peer-mapped through CUDA IPC) and raises a flag in every peer's
+// buffer; the combine kernels then read all ranks' partials straight over NVLink, in rank order on every rank, so all
+// ranks hold bit-identical latents afterwards. Exchange buffer: [XchgHeader | slot 0 | slot 1], slot = acc | ml.
+constexpr int HN_MAX_PEERS = 8;
+struct XchgHeader {
+  unsigned long long flags[HN_MAX_PEERS];  // flags[r] = sequence number of the last exchange rank r has published
+  unsigned int blocks_done;                // merge kernel: last-block-signals counter
+  int error;                               // set when a wait timed out
+  unsigned int pad[46];
+};
+static_assert(sizeof(XchgHeader) == 256, "exchange header is one 256-byte line");
+struct PeerParts {
+  int world = 0;  // 0: plain local partials
+  int rank = 0;
+  const float* acc[HN_MAX_PEERS];  // slot of every rank for this exchange (own rank included)
+  const float* ml[HN_MAX_PEERS];
+  XchgHeader* hdr[HN_MAX_PEERS];   // header of every rank's buffer (own: hdr[rank])
+  unsigned long long seq = 0;
+};
+// local splits -> one partial in this rank's slot, then flag every peer (last block signals)
+int launch_merge_signal(const float* part_acc, const float* part_ml, int batch, int nsplit, int H, int L, int w,
+                        float* slot_acc, float* slot_ml, const PeerParts& peers, cudaStream_t stream);
+
 // combine split partials. generic: O[b*L][h*hp+d] = sum_s w_s acc_s[d] / sum_s w_s l_s   (fp16, ld = o_ld)
 // (lo_seg > 0: O rows are split [hi | lo], lo at column + lo_seg)
 int launch_combine_generic(const float* part_acc, const float* part_ml, int batch, int nsplit, int H, int L,
-                           __half* O, int o_ld, int lo_seg, int hp, cudaStream_t stream);
+                           __half* O, int o_ld, int lo_seg, int hp, cudaStream_t stream,
+                           const PeerParts* peers = nullptr);
 // small-C: u = sum_s w_s acc_s[0..C) / sum_s w_s acc_s[C];  O[b*L][h*64+d] = u . Wv[h*dh+d][:] + bv[h*dh+d]
 int launch_combine_vproj(const float* part_acc, const float* part_ml, int batch, int nsplit, int H, int L, int C,
                          int zw, int dh, const float* Wv /*[H*dh][zw]*/, const float* bv /*[H*dh]*/, __half* O,
-                         int o_ld, int lo_seg, int hp, cudaStream_t stream);
+                         int o_ld, int lo_seg, int hp, cudaStream_t stream, const PeerParts* peers = nullptr);
 // opt-in export of attn = softmax(...) of one attention call, out[(b*H + h)][l][n] fp32; call after the attention
 // kernel (needs its partials' row statistics), before the buffers are reused
 int launch_attn_export(const AttnArgs& a, float* out, cudaStream_t stream);

@@ -139,10 +139,10 @@ __global__ void axis_tables_kernel(float* __restrict__ tab, AxisInfo ax, int B, 
 template <int ZW>
 __global__ void __launch_bounds__(256) build_z_small_kernel(const float* __restrict__ raw, __half* __restrict__ z,
                                                             long tokens_total, long N, int c_raw, AxisInfo ax,
-                                                            int F, const float* __restrict__ tab) {
+                                                            int F, const float* __restrict__ tab, long tok0) {
   const long t = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= tokens_total) return;
-  const long n = t % N;
+  const long n = t % N + tok0;
   float v[ZW];
   const float* r = raw + t * c_raw;
 #pragma unroll
@@ -208,11 +208,11 @@ __global__ void __launch_bounds__(256) build_z_small_kernel(const float* __restr
 __global__ void __launch_bounds__(256) build_z_large_kernel(const float* __restrict__ raw, __half* __restrict__ z,
                                                             int ldz, int seg, int lo_seg, long tokens_total, long N,
                                                             int c_raw, AxisInfo ax, int F,
-                                                            const float* __restrict__ tab) {
+                                                            const float* __restrict__ tab, long tok0) {
   const int lane = threadIdx.x & 31;
   const long t = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= tokens_total) return;
-  const long n = t % N;
+  const long n = t % N + tok0;
   const float* r = raw + t * c_raw;
   const int n_feat = F * ax.n_axes;
   const int C = c_raw + n_feat;
@@ -316,12 +316,96 @@ __global__ void pack_mask_kernel(const uint8_t* __restrict__ mask, uint64_t* __r
   bits[w] = v;
 }
 
+// ------------------------------------------------------------------ token-axis sharding across GPUs (peer memory)
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// Block-wide wait until every rank has published exchange `seq` (its flag in OUR header, written by the peer over
+// NVLink). Bounded: after ~2 s the block gives up, records the error and carries on, so a dead peer can never hang
+// the GPU. Call with all threads of the block.
+__device__ __forceinline__ void peers_wait(const PeerParts& pp) {
+  if (pp.world == 0) return;
+  if (threadIdx.x < pp.world) {
+    const unsigned long long* f = &pp.hdr[pp.rank]->flags[threadIdx.x];
+    const long long t0 = clock64();
+    while (ld_acquire_sys(f) < pp.seq) {
+      if (clock64() - t0 > 4000000000LL) {
+        pp.hdr[pp.rank]->error = 1;
+        break;
+      }
+      __nanosleep(200);
+    }
+  }
+  __syncthreads();
+}
+// split s of row (b, h, l): local layout [b][nsplit][H][L], peer layout = one partial per rank
+__device__ __forceinline__ long part_row(const PeerParts& pp, int b, int s, int nsplit, int H, int h, int L, int l) {
+  return pp.world ? ((static_cast<long>(b) * H + h) * L + l) : ((((static_cast<long>(b) * nsplit + s) * H + h) * L) + l);
+}
+
+// one warp per (b, h, l): merges the local splits into this rank's slot (un-normalised accumulator at the merged
+// max, merged max, merged row sum); the last block to finish publishes the exchange to every peer
+__global__ void __launch_bounds__(256) merge_signal_kernel(const float* __restrict__ part_acc,
+                                                           const float* __restrict__ part_ml, int batch, int nsplit,
+                                                           int H, int L, int w, float* __restrict__ slot_acc,
+                                                           float* __restrict__ slot_ml, PeerParts pp) {
+  const int lane = threadIdx.x & 31;
+  const long wid = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long total = static_cast<long>(batch) * H * L;
+  if (wid < total) {
+    const int l = static_cast<int>(wid % L);
+    const int h = static_cast<int>((wid / L) % H);
+    const int b = static_cast<int>(wid / (static_cast<long>(L) * H));
+    float M = -INFINITY;
+    for (int s = lane; s < nsplit; s += 32)
+      M = fmaxf(M, part_ml[((((static_cast<long>(b) * nsplit + s) * H + h) * L) + l) * 2]);
+    M = warp_max(M);
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    float den = 0.f;
+    const int nv = w / 32;
+    for (int s = 0; s < nsplit; ++s) {
+      const long base = (((static_cast<long>(b) * nsplit + s) * H + h) * L) + l;
+      const float m = part_ml[base * 2], ls = part_ml[base * 2 + 1];
+      const float wgt = (m == -INFINITY) ? 0.f : exp2f(m - M);
+#pragma unroll
+      for (int v = 0; v < 4; ++v)
+        if (v < nv) a[v] += wgt * part_acc[base * w + v * 32 + lane];
+      den += wgt * ls;
+    }
+    const long orow = (static_cast<long>(b) * H + h) * L + l;
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+      if (v < nv) slot_acc[orow * w + v * 32 + lane] = a[v];
+    if (lane == 0) {
+      slot_ml[orow * 2] = M;
+      slot_ml[orow * 2 + 1] = den;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    XchgHeader* mine = pp.hdr[pp.rank];
+    __threadfence();
+    const unsigned int prev = atomicAdd(&mine->blocks_done, 1u);
+    if (prev == gridDim.x - 1) {
+      mine->blocks_done = 0;
+      __threadfence_system();
+      for (int r = 0; r < pp.world; ++r) st_release_sys(&pp.hdr[r]->flags[pp.rank], pp.seq);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ split combine
 // part_acc [b][s][h][L][hp], part_ml [b][s][h][L][2]; one warp per (b, l, h); hp = 64 | 128 accumulator columns
 __global__ void __launch_bounds__(256) combine_generic_kernel(const float* __restrict__ part_acc,
                                                               const float* __restrict__ part_ml, int batch,
                                                               int nsplit, int H, int L, __half* __restrict__ O,
-                                                              int o_ld, int lo_seg, int hp) {
+                                                              int o_ld, int lo_seg, int hp, PeerParts pp) {
+  peers_wait(pp);
   const int lane = threadIdx.x & 31;
   const long wid = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long total = static_cast<long>(batch) * L * H;
@@ -331,18 +415,20 @@ __global__ void __launch_bounds__(256) combine_generic_kernel(const float* __res
   const int b = static_cast<int>(wid / (static_cast<long>(H) * L));
   float M = -INFINITY;
   for (int s = lane; s < nsplit; s += 32)
-    M = fmaxf(M, part_ml[((((static_cast<long>(b) * nsplit + s) * H + h) * L) + l) * 2]);
+    M = fmaxf(M, (pp.world ? pp.ml[s] : part_ml)[part_row(pp, b, s, nsplit, H, h, L, l) * 2]);
   M = warp_max(M);
   float a[4] = {0.f, 0.f, 0.f, 0.f};
   float den = 0.f;
   const int nv = hp / 32;
   for (int s = 0; s < nsplit; ++s) {
-    const long base = (((static_cast<long>(b) * nsplit + s) * H + h) * L) + l;
-    const float m = part_ml[base * 2], ls = part_ml[base * 2 + 1];
+    const long base = part_row(pp, b, s, nsplit, H, h, L, l);
+    const float* pml = pp.world ? pp.ml[s] : part_ml;
+    const float* pac = pp.world ? pp.acc[s] : part_acc;
+    const float m = pml[base * 2], ls = pml[base * 2 + 1];
     const float w = (m == -INFINITY) ? 0.f : exp2f(m - M);
 #pragma unroll
     for (int v = 0; v < 4; ++v)
-      if (v < nv) a[v] += w * part_acc[base * hp + v * 32 + lane];
+      if (v < nv) a[v] += w * pac[base * hp + v * 32 + lane];
     den += w * ls;
   }
   const float inv = 1.f / den;
@@ -361,7 +447,7 @@ __global__ void __launch_bounds__(256) combine_vproj_kernel(const float* __restr
                                                             int nsplit, int H, int L, int C, int zw, int dh,
                                                             const float* __restrict__ Wv,
                                                             const float* __restrict__ bv, __half* __restrict__ O,
-                                                            int o_ld, int lo_seg, int hp) {
+                                                            int o_ld, int lo_seg, int hp, PeerParts pp) {
   __shared__ float wT[64][129];  // wT[c][d] = Wv'[h*dh + d][c]
   __shared__ float u_s[32][65];  // merged, normalised rows
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -370,20 +456,23 @@ __global__ void __launch_bounds__(256) combine_vproj_kernel(const float* __restr
     const int d = i / 64, c = i % 64;
     wT[c][d] = (d < dh && c < C) ? Wv[static_cast<long>(h * dh + d) * zw + c] : 0.f;
   }
+  peers_wait(pp);  // (after the weight tile is on its way: the wait overlaps those loads)
   for (int r = w; r < 32; r += 8) {
     const int l = l0 + r;
     float acc0 = 0.f, acc1 = 0.f;
     if (l < L) {
       float M = -INFINITY;
       for (int s = lane; s < nsplit; s += 32)
-        M = fmaxf(M, part_ml[((((static_cast<long>(b) * nsplit + s) * H + h) * L) + l) * 2]);
+        M = fmaxf(M, (pp.world ? pp.ml[s] : part_ml)[part_row(pp, b, s, nsplit, H, h, L, l) * 2]);
       M = warp_max(M);
       for (int s = 0; s < nsplit; ++s) {
-        const long base = (((static_cast<long>(b) * nsplit + s) * H + h) * L) + l;
-        const float m = part_ml[base * 2];
+        const long base = part_row(pp, b, s, nsplit, H, h, L, l);
+        const float* pml = pp.world ? pp.ml[s] : part_ml;
+        const float* pac = pp.world ? pp.acc[s] : part_acc;
+        const float m = pml[base * 2];
         const float wgt = (m == -INFINITY) ? 0.f : exp2f(m - M);
-        acc0 += wgt * part_acc[base * zw + lane];
-        if (zw > 32) acc1 += wgt * part_acc[base * zw + 32 + lane];
+        acc0 += wgt * pac[base * zw + lane];
+        if (zw > 32) acc1 += wgt * pac[base * zw + 32 + lane];
       }
     }
     u_s[r][lane] = acc0;
@@ -532,7 +621,8 @@ int launch_axis_tables(float* tab, const int* axis_sizes, int n_axes, int n_band
 }
 
 int launch_build_z_small(const float* raw, __half* z, int zw, int batch, long N, int c_raw, int n_axes,
-                         const int* axis_sizes, int n_bands, const float* tab, int fourier, cudaStream_t stream) {
+                         const int* axis_sizes, int n_bands, const float* tab, int fourier, cudaStream_t stream,
+                         long tok0) {
   const int F = fourier ? 2 * n_bands + 1 : 0;
   const int C = c_raw + F * n_axes;
   HN_REQUIRE(zw == 32 || zw == 64, "small-C context rows are 32 or 64 wide");
@@ -541,22 +631,23 @@ int launch_build_z_small(const float* raw, __half* z, int zw, int batch, long N,
   const long total = static_cast<long>(batch) * N;
   const unsigned grid = static_cast<unsigned>((total + 255) / 256);
   if (zw == 32)
-    build_z_small_kernel<32><<<grid, 256, 0, stream>>>(raw, z, total, N, c_raw, ax, F, tab);
+    build_z_small_kernel<32><<<grid, 256, 0, stream>>>(raw, z, total, N, c_raw, ax, F, tab, tok0);
   else
-    build_z_small_kernel<64><<<grid, 256, 0, stream>>>(raw, z, total, N, c_raw, ax, F, tab);
+    build_z_small_kernel<64><<<grid, 256, 0, stream>>>(raw, z, total, N, c_raw, ax, F, tab, tok0);
   HN_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_build_z_large(const float* raw, __half* z, int ldz, int lo_seg, int batch, long N, int c_raw, int n_axes,
-                         const int* axis_sizes, int n_bands, const float* tab, int fourier, cudaStream_t stream) {
+                         const int* axis_sizes, int n_bands, const float* tab, int fourier, cudaStream_t stream,
+                         long tok0) {
   const int F = fourier ? 2 * n_bands + 1 : 0;
   const int seg = lo_seg > 0 ? lo_seg : ldz;
   HN_REQUIRE(seg >= c_raw + F * n_axes && ldz >= lo_seg + seg, "build_z_large: bad output layout");
   AxisInfo ax = make_axis(axis_sizes, n_axes);
   const long total = static_cast<long>(batch) * N;
   const unsigned grid = static_cast<unsigned>((total + 7) / 8);
-  build_z_large_kernel<<<grid, 256, 0, stream>>>(raw, z, ldz, seg, lo_seg, total, N, c_raw, ax, F, tab);
+  build_z_large_kernel<<<grid, 256, 0, stream>>>(raw, z, ldz, seg, lo_seg, total, N, c_raw, ax, F, tab, tok0);
   HN_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -579,22 +670,37 @@ int launch_pack_mask(const uint8_t* mask, uint64_t* bits, int batch, long N, cud
 }
 
 int launch_combine_generic(const float* part_acc, const float* part_ml, int batch, int nsplit, int H, int L,
-                           __half* O, int o_ld, int lo_seg, int hp, cudaStream_t stream) {
+                           __half* O, int o_ld, int lo_seg, int hp, cudaStream_t stream, const PeerParts* peers) {
   HN_REQUIRE(hp == 64 || hp == 128, "combine: head pitch must be 64 or 128");
   const long total = static_cast<long>(batch) * L * H;
+  PeerParts pp;
+  if (peers != nullptr) pp = *peers;
   combine_generic_kernel<<<static_cast<unsigned>((total + 7) / 8), 256, 0, stream>>>(
-      part_acc, part_ml, batch, nsplit, H, L, O, o_ld, lo_seg, hp);
+      part_acc, part_ml, batch, pp.world ? pp.world : nsplit, H, L, O, o_ld, lo_seg, hp, pp);
   HN_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_combine_vproj(const float* part_acc, const float* part_ml, int batch, int nsplit, int H, int L, int C,
                          int zw, int dh, const float* Wv, const float* bv, __half* O, int o_ld, int lo_seg, int hp,
-                         cudaStream_t stream) {
+                         cudaStream_t stream, const PeerParts* peers) {
   HN_REQUIRE((zw == 32 || zw == 64) && C <= zw - 1 && (hp == 64 || hp == 128) && dh <= hp,
              "combine_vproj: C < zw and dim_head <= head pitch (64 | 128) required");
-  combine_vproj_kernel<<<dim3((L + 31) / 32, H, batch), 256, 0, stream>>>(part_acc, part_ml, batch, nsplit, H, L, C,
-                                                                             zw, dh, Wv, bv, O, o_ld, lo_seg, hp);
+  PeerParts pp;
+  if (peers != nullptr) pp = *peers;
+  combine_vproj_kernel<<<dim3((L + 31) / 32, H, batch), 256, 0, stream>>>(
+      part_acc, part_ml, batch, pp.world ? pp.world : nsplit, H, L, C, zw, dh, Wv, bv, O, o_ld, lo_seg, hp, pp);
+  HN_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_merge_signal(const float* part_acc, const float* part_ml, int batch, int nsplit, int H, int L, int w,
+                        float* slot_acc, float* slot_ml, const PeerParts& peers, cudaStream_t stream) {
+  HN_REQUIRE(peers.world >= 1 && peers.world <= HN_MAX_PEERS, "merge: bad peer table");
+  HN_REQUIRE(w == 32 || w == 64 || w == 128, "merge: accumulator rows are 32, 64 or 128 wide");
+  const long total = static_cast<long>(batch) * H * L;
+  merge_signal_kernel<<<static_cast<unsigned>((total + 7) / 8), 256, 0, stream>>>(part_acc, part_ml, batch, nsplit, H,
+                                                                                  L, w, slot_acc, slot_ml, peers);
   HN_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

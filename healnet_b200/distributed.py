@@ -22,6 +22,31 @@ def shard_bounds(batch: int, world_size: int, rank: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def token_shard_bounds(n_tokens: int, world_size: int, rank: int, align: int = 64) -> Tuple[int, int]:
+    """Token-axis sharding: contiguous slice [lo, hi) of a modality's flattened token axis
+    owned by `rank`, cut at multiples of `align` tokens (the streaming kernel's tile) so only the last rank sees a
+    ragged tile. Slices may be empty only when there are fewer tiles than ranks."""
+    tiles = -(-n_tokens // align)
+    base, extra = divmod(tiles, world_size)
+    t_lo = rank * base + min(rank, extra)
+    t_hi = t_lo + base + (1 if rank < extra else 0)
+    return min(t_lo * align, n_tokens), min(t_hi * align, n_tokens)
+
+
+def merge_softmax_partials(maxes, sums, accs) -> torch.Tensor:
+    """Host restatement of what the combine kernels do with the ranks' partials of one attention row block
+    (rowops.cu: merge_signal_kernel / combine_*_kernel): partial r holds the running max m_r, the row sum l_r and the
+    un-normalised accumulator A_r of softmax(s) v over rank r's tokens; merged in rank order so every rank gets the
+    same bits.  out = sum_r e^(m_r - M) A_r / sum_r e^(m_r - M) l_r,  M = max_r m_r."""
+    big = torch.stack(list(maxes)).amax(dim=0)
+    num, den = 0, 0
+    for m, l, a in zip(maxes, sums, accs):
+        w = torch.where(torch.isinf(m) & (m < 0), torch.zeros_like(m), torch.exp(m - big))
+        num = num + w[..., None] * a
+        den = den + w * l
+    return num / den[..., None]
+
+
 def shard_batch(tensors: Sequence[Optional[torch.Tensor]], world_size: int, rank: int):
     """Slices every present modality (and nothing else) along the batch axis."""
     batch = next(t.shape[0] for t in tensors if t is not None)

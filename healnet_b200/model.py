@@ -19,6 +19,7 @@ import torch
 from torch import nn
 
 from . import _lib
+from .distributed import token_shard_bounds
 from ._lib import HN_MAX_AXES, HN_MAX_MODALITIES, check, hn_desc, load_library
 
 
@@ -265,6 +266,9 @@ class HealNet(nn.Module):
         self._workspace = None
         self._copy_stream = None
         self._export_registered = False
+        # token-axis sharding across GPUs (enable_token_sharding): (rank, world, min_tokens) or None
+        self._token_shard = None
+        self._exchange = None   # (own device ptr, [peer ptrs], bytes, max batch)
         # opt-in: materialise every Attention module's softmax matrix on each forward (reference: always on,
         # healnet.py:420). Off by default: (b*h, L, N) fp32 is 9.87 GB per sample and layer at the README shapes.
         self.export_attention_weights = False
@@ -292,6 +296,14 @@ class HealNet(nn.Module):
             pass
 
     def _release(self):
+        if getattr(self, "_exchange", None) is not None:
+            lib = load_library()
+            mine, bufs = self._exchange[0], self._exchange[1]
+            for p in bufs:
+                if p != mine:
+                    lib.hn_exchange_close(p)
+            lib.hn_exchange_free(mine)
+            self._exchange = None
         if getattr(self, "_handle", None) is not None:
             load_library().hn_destroy(self._handle)
             self._handle = None
@@ -396,6 +408,10 @@ class HealNet(nn.Module):
         staged: List[Optional[torch.Tensor]] = [None] * M
         ready: List[Optional[torch.cuda.Event]] = [None] * M   # per-modality "copy finished" events (host inputs)
         axis_sizes = (ctypes.c_int * (HN_MAX_MODALITIES * HN_MAX_AXES))()
+        axis_tokens = [0] * M   # full token count of every given modality
+        tok_begin = tok_count = None
+        if self._token_shard is not None:
+            tok_begin, tok_count = [0] * M, [0] * M
         for i in range(min(n_given, M)):
             data = tensors[i]
             if data is None:
@@ -412,9 +428,18 @@ class HealNet(nn.Module):
                 continue
             if len(axis) > HN_MAX_AXES:
                 raise ValueError(f"at most {HN_MAX_AXES} spatial axes per modality are supported")
-            staged[i], ready[i] = self._stage_input(data.detach(), dev)
+            axis_tokens[i] = 1
             for a, s in enumerate(axis):
                 axis_sizes[i * HN_MAX_AXES + a] = int(s)
+                axis_tokens[i] *= int(s)
+            data = data.detach()
+            if self._token_shard is not None and axis_tokens[i] >= self._token_shard[2]:
+                # token-axis sharding: stage only this rank's slice of a long modality (positions stay global)
+                rank, world, _ = self._token_shard
+                lo, hi = token_shard_bounds(axis_tokens[i], world, rank)
+                tok_begin[i], tok_count[i] = lo, hi - lo
+                data = data.reshape(b, axis_tokens[i], c)[:, lo:hi]
+            staged[i], ready[i] = self._stage_input(data, dev)
         if batch is None:
             # reference: `b` is unbound -> UnboundLocalError at :225
             raise UnboundLocalError("cannot infer the batch size: every modality is missing")
@@ -435,6 +460,14 @@ class HealNet(nn.Module):
             if mask_dev.shape[0] != batch:
                 raise ValueError("mask must have the batch dimension of the inputs")
             mask_tokens = int(mask_dev.shape[1])
+            if tok_count is not None:
+                # a mask addresses one token axis: cut it like the (single) sharded modality of that length
+                cuts = {(tok_begin[i], tok_count[i]) for i, t in enumerate(staged)
+                        if t is not None and tok_count[i] > 0 and axis_tokens[i] == mask_tokens}
+                if len(cuts) == 1:
+                    lo, cnt = cuts.pop()
+                    mask_dev = mask_dev[:, lo:lo + cnt].contiguous()
+                    mask_tokens = cnt
             for i, t in enumerate(staged):
                 if t is not None:
                     n_tok = t.numel() // (batch * t.shape[-1])
@@ -451,7 +484,7 @@ class HealNet(nn.Module):
             stream = torch.cuda.current_stream(dev).cuda_stream
             self._sync_native(dev, stream)
             out = self._launch(lib, staged, ready, axis_sizes, skip_self, mask_dev, mask_tokens, batch, want_latents,
-                               dev, stream)
+                               dev, stream, tok_begin, tok_count)
         if ret_dtype is not None and not ret_dtype.is_floating_point:
             ret_dtype = torch.float32
         return out.to(device=ret_dev, dtype=ret_dtype)
@@ -462,14 +495,20 @@ class HealNet(nn.Module):
         of a large late modality overlaps the work on the earlier ones."""
         if data.device == dev:
             return data.to(dtype=torch.float32).contiguous(), None
-        if data.device.type == "cpu" and data.is_pinned() and data.dtype == torch.float32 and data.is_contiguous():
+        # (a token-sharded slice of a pinned tensor is contiguous per sample: copied sample by sample, still async)
+        per_sample = data.dim() == 3 and not data.is_contiguous() and all(data[i].is_contiguous() for i in range(data.shape[0]))
+        if data.device.type == "cpu" and data.is_pinned() and data.dtype == torch.float32 and (data.is_contiguous() or per_sample):
             if self._copy_stream is None or self._copy_stream.device != dev:
                 self._copy_stream = torch.cuda.Stream(device=dev)
             cur = torch.cuda.current_stream(dev)
             out = torch.empty(data.shape, dtype=torch.float32, device=dev)   # allocated on the compute stream
             self._copy_stream.wait_stream(cur)                              # ...whose earlier users must be done
             with torch.cuda.stream(self._copy_stream):
-                out.copy_(data, non_blocking=True)
+                if per_sample:
+                    for i in range(data.shape[0]):
+                        out[i].copy_(data[i], non_blocking=True)
+                else:
+                    out.copy_(data, non_blocking=True)
                 out.record_stream(self._copy_stream)
                 ev = torch.cuda.Event()
                 ev.record(self._copy_stream)
@@ -477,7 +516,7 @@ class HealNet(nn.Module):
         return data.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous(), None
 
     def _launch(self, lib, staged, ready, axis_sizes, skip_self, mask_dev, mask_tokens, batch, want_latents, dev,
-                stream):
+                stream, tok_begin=None, tok_count=None):
         hp = self._hparams
         M = self.modalities
         ptrs = (ctypes.c_void_p * HN_MAX_MODALITIES)()
@@ -487,7 +526,14 @@ class HealNet(nn.Module):
             if staged[i] is None:
                 for a in range(HN_MAX_AXES):   # sizing needs sane extents for absent modalities too
                     sizes[i * HN_MAX_AXES + a] = max(1, sizes[i * HN_MAX_AXES + a])
-        need = lib.hn_workspace_bytes(self._handle, batch, sizes)
+        split = tok_count is not None and any(c > 0 for c in tok_count)
+        if split:
+            tb = (ctypes.c_long * HN_MAX_MODALITIES)(*tok_begin)
+            tc = (ctypes.c_long * HN_MAX_MODALITIES)(*tok_count)
+            self._ensure_exchange(lib, batch)
+            need = lib.hn_workspace_bytes_split(self._handle, batch, sizes, tc)
+        else:
+            need = lib.hn_workspace_bytes(self._handle, batch, sizes)
         if need == 0:
             raise _lib.HealNetLibraryError(f"hn_workspace_bytes failed: {_lib.last_error()}")
         if self._workspace is None or self._workspace.device != dev or self._workspace.numel() < need:
@@ -506,14 +552,63 @@ class HealNet(nn.Module):
             events = (ctypes.c_void_p * HN_MAX_MODALITIES)()
             for i in range(M):
                 events[i] = ready[i].cuda_event if (ready[i] is not None and staged[i] is not None) else None
-        check(lib.hn_forward_ex(self._handle, batch, ptrs, events, sizes, skip,
-                             mask_dev.data_ptr() if mask_dev is not None else None,
-                             mask_tokens, lat_ptr, log_ptr, self._workspace.data_ptr(), self._workspace.numel(),
-                             stream), "hn_forward")
+        if split:
+            check(lib.hn_forward_split(self._handle, batch, ptrs, events, sizes, tb, tc, skip,
+                                       mask_dev.data_ptr() if mask_dev is not None else None,
+                                       mask_tokens, lat_ptr, log_ptr, self._workspace.data_ptr(),
+                                       self._workspace.numel(), stream), "hn_forward_split")
+        else:
+            check(lib.hn_forward_ex(self._handle, batch, ptrs, events, sizes, skip,
+                                    mask_dev.data_ptr() if mask_dev is not None else None,
+                                    mask_tokens, lat_ptr, log_ptr, self._workspace.data_ptr(), self._workspace.numel(),
+                                    stream), "hn_forward")
         self.last_launch_count = lib.hn_last_launch_count(self._handle)
         for module, tensor in exported:   # later calls of a tied / repeated module win, as in the reference
             module.attn_weights = tensor
         return out
+
+    # ------------------------------------------------------------------------------ token-axis sharding (row f4)
+    def enable_token_sharding(self, group=None, min_tokens: int = 8192, max_batch: int = 8) -> None:
+        """Shards the token axis of every modality with at least `min_tokens` tokens across the ranks of `group`
+        (one process per GPU of ONE node): each rank streams its slice and the per-row softmax partials are merged
+        over peer memory (hn_forward_split). Every rank must then call forward() with the same full inputs and gets
+        the same (bit-identical) result. For batches too small to fill the GPUs by batch sharding."""
+        import torch.distributed as dist
+        if not dist.is_initialized() or dist.get_world_size(group) == 1:
+            self._token_shard = None
+            return
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if world > 8:
+            raise ValueError("token sharding covers the GPUs of one node (<= 8 ranks)")
+        self._token_shard = (rank, world, max(int(min_tokens), 2049 * 1))
+        self._exchange_group, self._exchange_max_batch = group, int(max_batch)
+
+    def _ensure_exchange(self, lib, batch: int) -> None:
+        """Allocates this rank's exchange buffer, swaps CUDA IPC handles with the peers (one all-gather of 64 bytes
+        per rank on the host side) and registers the peer-mapped pointers with the native handle."""
+        import torch.distributed as dist
+        if self._exchange is not None and self._exchange[3] >= batch and self._exchange[4] is self._handle:
+            return
+        rank, world, _ = self._token_shard
+        cap = max(batch, self._exchange_max_batch)
+        nbytes = lib.hn_exchange_bytes(self._handle, cap)
+        mine = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        check(lib.hn_exchange_alloc(nbytes, ctypes.byref(mine), handle), "hn_exchange_alloc")
+        gathered = [None] * world
+        dist.all_gather_object(gathered, bytes(handle), group=self._exchange_group)
+        bufs = (ctypes.c_void_p * world)()
+        for r in range(world):
+            if r == rank:
+                bufs[r] = mine.value
+            else:
+                peer = ctypes.c_void_p()
+                raw = (ctypes.c_ubyte * 64).from_buffer_copy(gathered[r])
+                check(lib.hn_exchange_open(raw, ctypes.byref(peer)), "hn_exchange_open")
+                bufs[r] = peer.value
+        check(lib.hn_set_exchange(self._handle, rank, world, bufs, nbytes), "hn_set_exchange")
+        dist.barrier(group=self._exchange_group)   # nobody publishes before everybody has mapped everybody
+        self._exchange = (mine.value, [bufs[r] for r in range(world)], nbytes, cap, self._handle)
 
     def _register_attention_export(self, lib, staged, skip_self, batch, dev):
         """Allocates and registers the export buffers (hn_set_attention_export) when `export_attention_weights` is

@@ -107,6 +107,34 @@ HN_API int hn_forward_ex(hn_handle* h, int batch, const void* const* modality_pt
                          float* latents_out, float* logits_out, void* workspace, size_t workspace_bytes,
                          void* cuda_stream);
 
+/* Token-axis ("split-N") sharding of one forward across the GPUs of a node — SURVEY.md section 8 row f4; the
+ * reference has no distributed code (its only multi-sample axis is the batch, healnet/main.py:415-432). Every rank
+ * holds the whole (small) batch and, for each long modality, only tokens [tok_begin[m], tok_begin[m] + tok_count[m])
+ * of its row-major flattened token axis: modality_ptrs[m] is then fp32 (batch, tok_count[m], channel_dims[m]) while
+ * axis_sizes still describes the FULL modality (positions are global). tok_count[m] <= 0 or == the full count means
+ * "replicated" (short axes, <= 2048 tokens, must be). Each rank runs the streaming attention over its tokens; the
+ * per-row partials (running max, un-normalised accumulator, denominator) are exchanged through peer-mapped buffers
+ * (CUDA IPC over NVLink) and merged by the combine kernel in rank order, so every rank ends up with bit-identical
+ * latents / logits. mask (if any) covers the local tokens: (batch, mask_tokens == tok_count[m]).
+ * Set-up, once per process group:  bytes = hn_exchange_bytes(h, max_batch); hn_exchange_alloc(bytes, &mine, handle);
+ * all-gather the 64-byte handles; hn_exchange_open() the peers'; hn_set_exchange(h, rank, world, bufs, bytes).
+ * All ranks must issue the same sequence of hn_forward_split calls. A peer that never shows up makes the waiting
+ * kernels give up after ~2 s (hn_exchange_error reports it) instead of hanging the GPU. */
+HN_API size_t hn_exchange_bytes(const hn_handle* h, int batch);
+HN_API int hn_exchange_alloc(size_t bytes, void** dev_ptr, unsigned char* ipc_handle_out /* 64 bytes */);
+HN_API int hn_exchange_open(const unsigned char* ipc_handle /* 64 bytes */, void** peer_ptr);
+HN_API int hn_exchange_close(void* peer_ptr);
+HN_API int hn_exchange_free(void* dev_ptr);
+HN_API int hn_set_exchange(hn_handle* h, int rank, int world, void* const* bufs /* [world], own buffer at [rank] */,
+                           size_t bytes);
+HN_API int hn_exchange_error(const hn_handle* h, int* error_out);  /* synchronous read of the time-out flag */
+HN_API size_t hn_workspace_bytes_split(const hn_handle* h, int batch, const int* axis_sizes, const long* tok_count);
+HN_API int hn_forward_split(hn_handle* h, int batch, const void* const* modality_ptrs,
+                            void* const* modality_ready_events, const int* axis_sizes, const long* tok_begin,
+                            const long* tok_count, const int* skip_latent_block, const uint8_t* mask,
+                            long mask_tokens, float* latents_out, float* logits_out, void* workspace,
+                            size_t workspace_bytes, void* cuda_stream);
+
 /* Number of kernels hn_forward enqueued on its last call for this handle (for bench accounting). */
 HN_API int hn_last_launch_count(const hn_handle* h);
 

@@ -64,3 +64,51 @@ def test_sharded_forward_world2(tmp_path, batch):
     port = _free_port()
     mp.spawn(_worker, args=(world, port, batch, str(tmp_path)), nprocs=world, join=True)
     assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
+
+
+# ---------------------------------------------------------------------------------- token-axis sharding (row f4)
+from healnet_b200.distributed import merge_softmax_partials, token_shard_bounds  # noqa: E402
+
+
+def test_token_shard_bounds_cover_the_axis_in_tile_units():
+    for n in (2049, 4970, 50176, 602112, 65536):
+        for world in (1, 2, 3, 4, 8):
+            spans = [token_shard_bounds(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for (a, b), (c, d) in zip(spans, spans[1:]):
+                assert b == c and b > a and b % 64 == 0      # cuts on tile boundaries, nobody empty
+            tiles = [-(-(b - a) // 64) for a, b in spans]
+            assert max(tiles) - min(tiles) <= 1
+
+
+def _split_worker(rank, world, port, result_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(7)
+    b, h, L, N, dh = 2, 3, 16, 4970, 8
+    q = torch.randn(b, h, L, dh, generator=g, dtype=torch.float64)
+    k = torch.randn(b, h, N, dh, generator=g, dtype=torch.float64)
+    v = torch.randn(b, h, N, dh, generator=g, dtype=torch.float64)
+    keep = torch.rand(b, N, generator=g) > 0.2
+    sim = torch.einsum("bhld,bhnd->bhln", q, k).masked_fill(~keep[:, None, None, :], float("-inf"))
+    full = torch.softmax(sim, dim=-1) @ v
+    lo, hi = token_shard_bounds(N, world, rank)
+    s = sim[..., lo:hi]
+    m = s.amax(dim=-1)                                   # what a rank's streaming kernel leaves behind:
+    p = torch.exp(s - m[..., None])                      # running max, row sum and un-normalised accumulator
+    part = (m, p.sum(-1), p @ v[:, :, lo:hi])
+    gathered = [[torch.empty_like(t) for _ in range(world)] for t in part]
+    for t, outs in zip(part, gathered):
+        dist.all_gather(outs, t.contiguous())
+    merged = merge_softmax_partials(*gathered)
+    torch.testing.assert_close(merged, full, rtol=1e-10, atol=1e-12)
+    dist.barrier()
+    dist.destroy_process_group()
+    open(os.path.join(result_dir, f"ok{rank}"), "w").close()
+
+
+def test_token_sharded_partials_merge_world2(tmp_path):
+    world = 2
+    mp.spawn(_split_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
