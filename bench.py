@@ -174,10 +174,55 @@ def _cut(shapes, big, keep):
     return out
 
 
+def run_reference_gpu_eager(args):
+    """Opt-in (`--impl reference --ref-device cuda`): the reference algorithm as PyTorch eager ops on ONE GPU (the
+    oracle port on CUDA tensors: materialised K/V and attention matrices, TF32 flags at torch defaults), the
+    denominator of the north star's '>= 10x the reference single-GPU eager forward'. Not part of the driver's arms."""
+    import torch
+    from oracle import healnet_oracle as O
+    from healnet_b200 import HealNet
+    kwargs, shapes, per_gpu = WORKLOADS[args.workload]
+    batch = args.batch or per_gpu
+    dev = torch.device("cuda", 0)
+    cfg = O.OracleConfig(**{k: v for k, v in kwargs.items() if k in O.OracleConfig.__dataclass_fields__})
+    torch.manual_seed(0)
+    sd = {k: v.detach().to(dev) for k, v in HealNet(**kwargs).state_dict().items()}
+    g = torch.Generator().manual_seed(0)
+    xs = [torch.rand((batch,) + tuple(s), generator=g).to(dev) for s in shapes]
+    # the (b*h, L, N) attention matrix of the volume is 9.87 GB per sample in fp32: evaluate two heads at a time
+    chunk = 2
+
+    def step():
+        with torch.no_grad():
+            return O.forward(sd, cfg, xs, head_chunk=chunk)
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = max(1, min(args.steps, 5))
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    line = dict(metric=METRIC, value=batch / (ms * 1e-3), unit="samples/s", n_gpus=1, steps=steps, warmup=args.warmup,
+                ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                impl="reference", device="cuda-eager",
+                config=dict(workload=args.workload, batch_per_gpu=batch, shapes=[list(s) for s in shapes],
+                            head_chunk=chunk, **{k: kwargs[k] for k in ("l_c", "l_d")}),
+                peak_mem_gb=torch.cuda.max_memory_allocated(dev) / 2 ** 30)
+    print(json.dumps(line), flush=True)
+    return 0
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    if args.ref_device == "cuda":
+        return run_reference_gpu_eager(args)
     kwargs, shapes, per_gpu = WORKLOADS[args.workload]
     threads = len(os.sched_getaffinity(0))
     total = max(1, args.steps + args.warmup)
@@ -339,6 +384,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
     ap.add_argument("--shard", default="batch", choices=["batch", "tokens"],
                     help="multi-GPU partitioning: batch (weak scaling, default) or tokens (strong scaling of one batch)")
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference only: cpu (default, the driver's arm) or cuda (PyTorch eager on one GPU)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline sample")
     args = ap.parse_args()

@@ -30,6 +30,31 @@ const char* get_error();
     }                                                                                                \
   } while (0)
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// Every kernel of the forward is launched with the programmatic-stream-serialization attribute and calls
+// HN_PDL_LAUNCH() first thing and HN_PDL_WAIT() before it touches global memory: the next kernel's launch latency and
+// prologue (barrier init, TMEM allocation, descriptor prefetch) then overlap the tail of the current one. A forward is
+// ~150 short dependent kernels, so the ~2-3 us saved per launch add up. HN_PDL=0 turns the attribute off (the device
+// side instructions are no-ops then).
+#define HN_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#define HN_PDL_LAUNCH() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                            Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 static inline long round_up_l(long x, long m) { return (x + m - 1) / m * m; }
 

@@ -37,7 +37,6 @@ namespace {
 using namespace tc05;
 
 constexpr int BM = 128;
-constexpr int BK = 64;
 
 struct GemmDev {
   int M, N, K;
@@ -115,6 +114,8 @@ __global__ void __launch_bounds__((2 + EPI_WARPS) * 32, 1) gemm_kernel(const __g
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = tmem_base_s;
+  HN_PDL_LAUNCH();
+  HN_PDL_WAIT();  // everything above overlapped the previous kernel's tail; operands / x are valid from here on
 
   if (warp == 0) {
     if (elect_one()) {
@@ -321,8 +322,7 @@ int launch_t(const GemmArgs& a, cudaStream_t stream) {
                                      SMEM_BUDGET + 1024));
   const long n_tiles = static_cast<long>((a.N + BN - 1) / BN) * ((a.M + BM - 1) / BM);
   const unsigned grid = static_cast<unsigned>(n_tiles < sms ? n_tiles : sms);
-  gemm_kernel<BN, BK><<<grid, (2 + EPI_WARPS) * 32, smem, stream>>>(tmA, tmB, p);
-  HN_CHECK_CUDA(cudaGetLastError());
+  HN_CHECK_CUDA(launch_k(gemm_kernel<BN, BK>, dim3(grid), dim3((2 + EPI_WARPS) * 32), smem, stream, tmA, tmB, p));
   return 0;
 }
 }  // namespace

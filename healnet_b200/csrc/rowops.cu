@@ -6,9 +6,21 @@
 // LayerNorm of the context is split as LN(c) = gamma * z + beta with z = (c - mean) * rstd: z depends only
 // on the input, so it is built ONCE per forward and shared by all `depth` layers; gamma/beta are folded
 // into the projection weights at pack time (pack.cu).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace hn {
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("HN_PDL");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
 namespace {
 
 constexpr float LN_EPS = 1e-5f;
@@ -38,6 +50,8 @@ __global__ void __launch_bounds__(256) layernorm_f16_kernel(const float* __restr
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, __half* __restrict__ y,
                                                             int ldy, int seg, int lo_seg, long rows, int D) {
+  HN_PDL_LAUNCH();
+  HN_PDL_WAIT();
   const int lane = threadIdx.x & 31;
   const long row = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -72,6 +86,8 @@ __global__ void __launch_bounds__(256) layernorm_f16_big_kernel(const float* __r
                                                                 const float* __restrict__ beta,
                                                                 __half* __restrict__ y, int ldy, int seg, int lo_seg,
                                                                 long rows, int D) {
+  HN_PDL_LAUNCH();
+  HN_PDL_WAIT();
   const int lane = threadIdx.x & 31;
   const long row = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -99,6 +115,8 @@ struct AxisInfo {
   int off[4];
 };
 __global__ void axis_tables_kernel(float* __restrict__ tab, AxisInfo ax, int B, float max_freq) {
+  HN_PDL_LAUNCH();
+  HN_PDL_WAIT();
   const int F = 2 * B + 1;
   int total = 0;
   for (int a = 0; a < ax.n_axes; ++a) total += ax.size[a];
@@ -140,6 +158,8 @@ template <int ZW>
 __global__ void __launch_bounds__(256) build_z_small_kernel(const float* __restrict__ raw, __half* __restrict__ z,
                                                             long tokens_total, long N, int c_raw, AxisInfo ax,
                                                             int F, const float* __restrict__ tab, long tok0) {
+  HN_PDL_LAUNCH();
+  HN_PDL_WAIT();
   const long t = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= tokens_total) return;
   const long n = t % N + tok0;
@@ -209,6 +229,8 @@ __global__ void __launch_bounds__(256) build_z_large_kernel(const float* __restr
                                                             int ldz, int seg, int lo_seg, long tokens_total, long N,
                                                             int c_raw, AxisInfo ax, int F,
                                                             const float* __restrict__ tab, long tok0) {
+  HN_PDL_LAUNCH();
+  HN_PDL_WAIT();
   const int lane = threadIdx.x & 31;
   const long t = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= tokens_total) return;
@@ -245,6 +267,8 @@ __global__ void __launch_bounds__(256) build_z_large_kernel(const float* __restr
 // stage 1: pooled[b][d] = mean_l x[b][l][d]; block = (sample, 32 columns), 8 warps stride the rows
 __global__ void __launch_bounds__(256) pool_kernel(const float* __restrict__ x, int L, int D,
                                                    float* __restrict__ pooled) {
+  HN_PDL_LAUNCH();
+  HN_PDL_WAIT();
   __shared__ float part[8][33];
   const int b = blockIdx.y, d = blockIdx.x * 32 + (threadIdx.x & 31), w = threadIdx.x >> 5;
   const float* xb = x + static_cast<size_t>(b) * L * D;
@@ -265,6 +289,8 @@ __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ poo
                                                    const float* __restrict__ ln_w, const float* __restrict__ ln_b,
                                                    const float* __restrict__ W, const float* __restrict__ bias,
                                                    int out_dims, float* __restrict__ logits) {
+  HN_PDL_LAUNCH();
+  HN_PDL_WAIT();
   extern __shared__ float pooled[];  // D floats
   __shared__ float red[32];
   const int b = blockIdx.x;
@@ -305,6 +331,8 @@ __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ poo
 // ------------------------------------------------------------------ mask bytes -> tile bit words
 __global__ void pack_mask_kernel(const uint8_t* __restrict__ mask, uint64_t* __restrict__ bits, long N,
                                  long tiles_per_sample, long total_tiles) {
+  HN_PDL_LAUNCH();
+  HN_PDL_WAIT();
   const long w = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (w >= total_tiles) return;
   const long b = w / tiles_per_sample, tile = w % tiles_per_sample;
@@ -354,6 +382,8 @@ __global__ void __launch_bounds__(256) merge_signal_kernel(const float* __restri
                                                            const float* __restrict__ part_ml, int batch, int nsplit,
                                                            int H, int L, int w, float* __restrict__ slot_acc,
                                                            float* __restrict__ slot_ml, PeerParts pp) {
+  HN_PDL_LAUNCH();
+  HN_PDL_WAIT();
   const int lane = threadIdx.x & 31;
   const long wid = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long total = static_cast<long>(batch) * H * L;
@@ -405,6 +435,8 @@ __global__ void __launch_bounds__(256) combine_generic_kernel(const float* __res
                                                               const float* __restrict__ part_ml, int batch,
                                                               int nsplit, int H, int L, __half* __restrict__ O,
                                                               int o_ld, int lo_seg, int hp, PeerParts pp) {
+  HN_PDL_LAUNCH();
+  HN_PDL_WAIT();
   peers_wait(pp);
   const int lane = threadIdx.x & 31;
   const long wid = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -448,6 +480,8 @@ __global__ void __launch_bounds__(256) combine_vproj_kernel(const float* __restr
                                                             const float* __restrict__ Wv,
                                                             const float* __restrict__ bv, __half* __restrict__ O,
                                                             int o_ld, int lo_seg, int hp, PeerParts pp) {
+  HN_PDL_LAUNCH();
+  HN_PDL_WAIT();
   __shared__ float wT[64][129];  // wT[c][d] = Wv'[h*dh + d][c]
   __shared__ float u_s[32][65];  // merged, normalised rows
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -494,6 +528,8 @@ __global__ void __launch_bounds__(256) combine_vproj_kernel(const float* __restr
 }
 
 __global__ void broadcast_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, long n, int batch) {
+  HN_PDL_LAUNCH();
+  HN_PDL_WAIT();
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<long>(gridDim.x) * blockDim.x) {
     const float v = src[i];
@@ -513,6 +549,8 @@ __global__ void __launch_bounds__(256) attn_export_kernel(
     int k_col0, int k_lo_off, int q_pitch, int k_pitch, int batch, int H, int L, long N, int nsplit,
     const float* __restrict__ part_acc, const float* __restrict__ part_ml, int acc_w, int den_col,
     const uint64_t* __restrict__ mask_bits, float* __restrict__ out) {
+  HN_PDL_LAUNCH();
+  HN_PDL_WAIT();
   __shared__ float q_s[16][KW];
   __shared__ float m_s[16], inv_s[16];
   const int bh = blockIdx.z, b = bh / H, h = bh % H;
@@ -600,13 +638,17 @@ int launch_layernorm_f16(const float* x, int ldx, const float* gamma, const floa
   const int wpb = 8;
   const unsigned grid = static_cast<unsigned>((rows + wpb - 1) / wpb);
   if (seg <= 128)
-    layernorm_f16_kernel<4><<<grid, wpb * 32, 0, stream>>>(x, ldx, gamma, beta, y, ldy, seg, lo_seg, rows, D);
+    HN_CHECK_CUDA(launch_k(layernorm_f16_kernel<4>, dim3(grid), dim3(wpb * 32), 0, stream, x, ldx, gamma, beta, y, ldy,
+                           seg, lo_seg, rows, D));
   else if (seg <= 512)
-    layernorm_f16_kernel<16><<<grid, wpb * 32, 0, stream>>>(x, ldx, gamma, beta, y, ldy, seg, lo_seg, rows, D);
+    HN_CHECK_CUDA(launch_k(layernorm_f16_kernel<16>, dim3(grid), dim3(wpb * 32), 0, stream, x, ldx, gamma, beta, y, ldy,
+                           seg, lo_seg, rows, D));
   else if (seg <= 1024)
-    layernorm_f16_kernel<32><<<grid, wpb * 32, 0, stream>>>(x, ldx, gamma, beta, y, ldy, seg, lo_seg, rows, D);
+    HN_CHECK_CUDA(launch_k(layernorm_f16_kernel<32>, dim3(grid), dim3(wpb * 32), 0, stream, x, ldx, gamma, beta, y, ldy,
+                           seg, lo_seg, rows, D));
   else
-    layernorm_f16_big_kernel<<<grid, wpb * 32, 0, stream>>>(x, ldx, gamma, beta, y, ldy, seg, lo_seg, rows, D);
+    HN_CHECK_CUDA(launch_k(layernorm_f16_big_kernel, dim3(grid), dim3(wpb * 32), 0, stream, x, ldx, gamma, beta, y, ldy,
+                           seg, lo_seg, rows, D));
   HN_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -615,7 +657,7 @@ int launch_axis_tables(float* tab, const int* axis_sizes, int n_axes, int n_band
                        cudaStream_t stream) {
   HN_REQUIRE(n_axes >= 1 && n_axes <= 4, "at most 4 spatial axes are supported");
   AxisInfo ax = make_axis(axis_sizes, n_axes);
-  axis_tables_kernel<<<8, 256, 0, stream>>>(tab, ax, n_bands, max_freq);
+  HN_CHECK_CUDA(launch_k(axis_tables_kernel, dim3(8), dim3(256), 0, stream, tab, ax, n_bands, max_freq));
   HN_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -631,9 +673,11 @@ int launch_build_z_small(const float* raw, __half* z, int zw, int batch, long N,
   const long total = static_cast<long>(batch) * N;
   const unsigned grid = static_cast<unsigned>((total + 255) / 256);
   if (zw == 32)
-    build_z_small_kernel<32><<<grid, 256, 0, stream>>>(raw, z, total, N, c_raw, ax, F, tab, tok0);
+    HN_CHECK_CUDA(launch_k(build_z_small_kernel<32>, dim3(grid), dim3(256), 0, stream, raw, z, total, N, c_raw, ax, F, tab,
+                           tok0));
   else
-    build_z_small_kernel<64><<<grid, 256, 0, stream>>>(raw, z, total, N, c_raw, ax, F, tab, tok0);
+    HN_CHECK_CUDA(launch_k(build_z_small_kernel<64>, dim3(grid), dim3(256), 0, stream, raw, z, total, N, c_raw, ax, F, tab,
+                           tok0));
   HN_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -647,16 +691,18 @@ int launch_build_z_large(const float* raw, __half* z, int ldz, int lo_seg, int b
   AxisInfo ax = make_axis(axis_sizes, n_axes);
   const long total = static_cast<long>(batch) * N;
   const unsigned grid = static_cast<unsigned>((total + 7) / 8);
-  build_z_large_kernel<<<grid, 256, 0, stream>>>(raw, z, ldz, seg, lo_seg, total, N, c_raw, ax, F, tab, tok0);
+  HN_CHECK_CUDA(launch_k(build_z_large_kernel, dim3(grid), dim3(256), 0, stream, raw, z, ldz, seg, lo_seg, total, N, c_raw,
+                         ax, F, tab, tok0));
   HN_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_head(const float* x, int batch, int L, int D, const float* ln_w, const float* ln_b, const float* W,
                 const float* bias, int out_dims, float* pooled, float* logits, cudaStream_t stream) {
-  pool_kernel<<<dim3((D + 31) / 32, batch), 256, 0, stream>>>(x, L, D, pooled);
+  HN_CHECK_CUDA(launch_k(pool_kernel, dim3((D + 31) / 32, batch), dim3(256), 0, stream, x, L, D, pooled));
   HN_CHECK_CUDA(cudaGetLastError());
-  head_kernel<<<batch, 256, (D + 2) * sizeof(float), stream>>>(pooled, D, ln_w, ln_b, W, bias, out_dims, logits);
+  HN_CHECK_CUDA(launch_k(head_kernel, dim3(batch), dim3(256), (D + 2) * sizeof(float), stream, pooled, D, ln_w, ln_b, W,
+                         bias, out_dims, logits));
   HN_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -664,7 +710,8 @@ int launch_head(const float* x, int batch, int L, int D, const float* ln_w, cons
 int launch_pack_mask(const uint8_t* mask, uint64_t* bits, int batch, long N, cudaStream_t stream) {
   const long tiles = (N + 63) / 64;
   const long total = tiles * batch;
-  pack_mask_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, stream>>>(mask, bits, N, tiles, total);
+  HN_CHECK_CUDA(launch_k(pack_mask_kernel, dim3(static_cast<unsigned>((total + 127) / 128)), dim3(128), 0, stream, mask,
+                         bits, N, tiles, total));
   HN_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -675,8 +722,8 @@ int launch_combine_generic(const float* part_acc, const float* part_ml, int batc
   const long total = static_cast<long>(batch) * L * H;
   PeerParts pp;
   if (peers != nullptr) pp = *peers;
-  combine_generic_kernel<<<static_cast<unsigned>((total + 7) / 8), 256, 0, stream>>>(
-      part_acc, part_ml, batch, pp.world ? pp.world : nsplit, H, L, O, o_ld, lo_seg, hp, pp);
+  HN_CHECK_CUDA(launch_k(combine_generic_kernel, dim3(static_cast<unsigned>((total + 7) / 8)), dim3(256), 0, stream,
+                         part_acc, part_ml, batch, pp.world ? pp.world : nsplit, H, L, O, o_ld, lo_seg, hp, pp));
   HN_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -688,8 +735,8 @@ int launch_combine_vproj(const float* part_acc, const float* part_ml, int batch,
              "combine_vproj: C < zw and dim_head <= head pitch (64 | 128) required");
   PeerParts pp;
   if (peers != nullptr) pp = *peers;
-  combine_vproj_kernel<<<dim3((L + 31) / 32, H, batch), 256, 0, stream>>>(
-      part_acc, part_ml, batch, pp.world ? pp.world : nsplit, H, L, C, zw, dh, Wv, bv, O, o_ld, lo_seg, hp, pp);
+  HN_CHECK_CUDA(launch_k(combine_vproj_kernel, dim3((L + 31) / 32, H, batch), dim3(256), 0, stream, part_acc, part_ml,
+                         batch, pp.world ? pp.world : nsplit, H, L, C, zw, dh, Wv, bv, O, o_ld, lo_seg, hp, pp));
   HN_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -699,8 +746,8 @@ int launch_merge_signal(const float* part_acc, const float* part_ml, int batch, 
   HN_REQUIRE(peers.world >= 1 && peers.world <= HN_MAX_PEERS, "merge: bad peer table");
   HN_REQUIRE(w == 32 || w == 64 || w == 128, "merge: accumulator rows are 32, 64 or 128 wide");
   const long total = static_cast<long>(batch) * H * L;
-  merge_signal_kernel<<<static_cast<unsigned>((total + 7) / 8), 256, 0, stream>>>(part_acc, part_ml, batch, nsplit, H,
-                                                                                  L, w, slot_acc, slot_ml, peers);
+  HN_CHECK_CUDA(launch_k(merge_signal_kernel, dim3(static_cast<unsigned>((total + 7) / 8)), dim3(256), 0, stream, part_acc,
+                         part_ml, batch, nsplit, H, L, w, slot_acc, slot_ml, peers));
   HN_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -732,7 +779,7 @@ int launch_attn_export(const AttnArgs& a, float* out, cudaStream_t stream) {
 
 int launch_broadcast_rows(const float* src, float* dst, long n, int batch, cudaStream_t stream) {
   const unsigned grid = static_cast<unsigned>(n / 256 + 1 < 1184 ? n / 256 + 1 : 1184);
-  broadcast_rows_kernel<<<grid, 256, 0, stream>>>(src, dst, n, batch);
+  HN_CHECK_CUDA(launch_k(broadcast_rows_kernel, dim3(grid), dim3(256), 0, stream, src, dst, n, batch));
   HN_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

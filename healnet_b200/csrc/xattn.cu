@@ -93,6 +93,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
 
   const long part_row0 = ((static_cast<long>(b) * p.nsplit + split) * p.H + h) * p.L + lt * BM;
   if (n <= 0) {  // more splits than tiles: publish an empty partial
+    HN_PDL_WAIT();
     for (int r = threadIdx.x; r < BM; r += blockDim.x) {
       if (lt * BM + r < p.L) {
         float* acc = p.part_acc + (part_row0 + r) * VD;
@@ -124,6 +125,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   fence_after_sync();
   const uint32_t tmem = tmem_base_s;
   const uint32_t tS0 = tmem, tP0 = tmem + 128, tU = tmem + 192;
+  HN_PDL_LAUNCH();
+  HN_PDL_WAIT();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -348,8 +351,8 @@ int launch_t(const AttnArgs& a, cudaStream_t stream) {
       cudaFuncSetAttribute(attn_kernel<KD, SHARED, PREC, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
   const long grid = static_cast<long>(p.n_ltiles) * a.H * a.batch * a.nsplit;
   HN_REQUIRE(grid > 0 && grid < 2147483647L, "attention: grid too large");
-  attn_kernel<KD, SHARED, PREC, NA><<<static_cast<unsigned>(grid), 192, SMEM, stream>>>(tmQ, tmKV, p);
-  HN_CHECK_CUDA(cudaGetLastError());
+  HN_CHECK_CUDA(launch_k(attn_kernel<KD, SHARED, PREC, NA>, dim3(static_cast<unsigned>(grid)), dim3(192), SMEM, stream,
+                         tmQ, tmKV, p));
   return 0;
 }
 }  // namespace

@@ -187,6 +187,7 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   const int n = t_end - t_begin;
 
   if (n <= 0) {  // more splits than tiles: publish empty partials
+    HN_PDL_WAIT();
     for (int g = 0; g < n_active; ++g) {
       const int rb = rb0 + g, h = rb / p.n_ltiles, lt = rb % p.n_ltiles;
       const long row0 = ((static_cast<long>(b) * p.nsplit + split) * p.H + h) * p.L + lt * BM;
@@ -224,6 +225,8 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = tmem_base_s;
+  HN_PDL_LAUNCH();
+  HN_PDL_WAIT();
 
   if (warp == PRODUCER_WARP) {
     // ------------------------------------------------------------ TMA producer
@@ -515,9 +518,11 @@ int launch_small_t(const AttnArgs& a, cudaStream_t stream) {
   if (g_trace_buf != nullptr && (PMODE == 6 || PMODE == 9)) {
     HN_CHECK_CUDA(cudaFuncSetAttribute(attn_small_kernel<KD, G, PMODE, true>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attn_small_kernel<KD, G, PMODE, true><<<static_cast<unsigned>(grid), (5 * G + 1) * 32, SMEM, stream>>>(tmQ, tmZ, p);
+    HN_CHECK_CUDA(launch_k(attn_small_kernel<KD, G, PMODE, true>, dim3(static_cast<unsigned>(grid)),
+                           dim3((5 * G + 1) * 32), SMEM, stream, tmQ, tmZ, p));
   } else
-  attn_small_kernel<KD, G, PMODE><<<static_cast<unsigned>(grid), (5 * G + 1) * 32, SMEM, stream>>>(tmQ, tmZ, p);
+    HN_CHECK_CUDA(launch_k(attn_small_kernel<KD, G, PMODE, false>, dim3(static_cast<unsigned>(grid)),
+                           dim3((5 * G + 1) * 32), SMEM, stream, tmQ, tmZ, p));
   HN_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

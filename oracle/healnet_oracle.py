@@ -47,14 +47,14 @@ class OracleConfig:
     extra: dict = field(default_factory=dict)
 
 
-def fourier_table(size: int, max_freq: float, num_bands: int, dtype=torch.float32) -> torch.Tensor:
+def fourier_table(size: int, max_freq: float, num_bands: int, dtype=torch.float32, device=None) -> torch.Tensor:
     """Per-axis feature table, rows = positions, cols = [sin(pi p f_k)]_k ++ [cos(pi p f_k)]_k ++ [p].
 
     healnet.py:212 (linspace(-1,1,size)), :292-302 (fourier_encode: scales = linspace(1, max_freq/2, B),
     x*scales*pi, cat(sin, cos), cat(.., orig_x)).
     """
-    p = torch.linspace(-1.0, 1.0, steps=size, dtype=dtype)
-    scales = torch.linspace(1.0, max_freq / 2, num_bands, dtype=dtype)
+    p = torch.linspace(-1.0, 1.0, steps=size, dtype=dtype, device=device)  # (the reference builds it on data.device, :212)
+    scales = torch.linspace(1.0, max_freq / 2, num_bands, dtype=dtype, device=device)
     x = p[:, None] * scales[None, :] * math.pi
     return torch.cat([x.sin(), x.cos(), p[:, None]], dim=-1)
 
@@ -66,7 +66,7 @@ def encode_modality(data: torch.Tensor, n_axes: int, max_freq: float, num_bands:
     if fourier:
         feats = []
         for a, size in enumerate(axes):  # meshgrid(indexing='ij') + '... n d -> ... (n d)'  healnet.py:213-215
-            t = fourier_table(size, max_freq, num_bands, data.dtype)  # (size, 2B+1)
+            t = fourier_table(size, max_freq, num_bands, data.dtype, data.device)  # (size, 2B+1)
             shape = [1] * len(axes) + [t.shape[1]]
             shape[a] = size
             feats.append(t.reshape(shape).expand(*axes, t.shape[1]))
@@ -100,7 +100,7 @@ def attention(x: torch.Tensor, ctx: torch.Tensor, wq, wkv, wo, bo, heads: int,
     q = q.reshape(b, L, heads, dh).permute(0, 2, 1, 3)  # '(b h) n d' healnet.py:407
     k = k.reshape(b, N, heads, dh).permute(0, 2, 1, 3)
     v = v.reshape(b, N, heads, dh).permute(0, 2, 1, 3)
-    out = torch.empty(b, heads, L, dh, dtype=x.dtype)
+    out = torch.empty(b, heads, L, dh, dtype=x.dtype, device=x.device)
     weights = [] if want_weights else None
     step = head_chunk if head_chunk > 0 else heads
     for h0 in range(0, heads, step):
