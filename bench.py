@@ -48,7 +48,7 @@ METRIC = "HealNet forward samples/sec (3-modality, latent 512x512)"
 
 def load_traffic():
     """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/), or None."""
-    p = os.path.join(ROOT, "profiles", "r1_attn_small_kernel_summary.json")
+    p = os.path.join(ROOT, "profiles", "r1_final_attn_small_kernel_summary.json")
     try:
         return float(json.load(open(p))["dram_bytes_per_launch"])
     except (OSError, KeyError, ValueError):
