@@ -25,6 +25,10 @@
 //   * two accumulators in TMEM (2 x BN columns): the epilogue of tile j overlaps the main loop of tile j+1, and the
 //     per-CTA set-up (barriers, TMEM allocation, descriptor fetch) is paid once per SM instead of once per tile;
 //   * BN = 256 whenever that still gives every SM a tile (halves the A bytes per FLOP).
+//   * thread-block clusters with TMA multicast (CN = 2 | 4 CTAs): the CTAs of a cluster work on output tiles that share
+//     one operand tile (the activations when the cluster runs along N, the weights when it runs along M); each CTA
+//     fetches 1/CN of that tile and multicasts it to all of them, so the dominant L2 -> SM traffic drops by CN. The
+//     stage's empty barrier then collects one tcgen05.commit from every CTA of the cluster (multicast arrive).
 // M/N/K tails are handled by TMA out-of-bounds zero fill plus guards in the epilogue, so any shape whose row pitches
 // are multiples of 8 elements is legal.
 #include <cstdlib>
@@ -50,6 +54,7 @@ struct GemmDev {
   int out_seg;       // fp16 outputs: > 0 -> also store lo = fp16(v - hi) at column + out_seg
   int stages;        // depth of the operand ring (host: as many as fit the SM's shared memory, <= 8)
   int bias_vec;      // bias is 16-byte aligned -> float4 loads
+  int tiles_m, tiles_n;  // output tiles; with clusters: super-tiles of CN tiles along N (SHARE_A) or M (!SHARE_A)
 };
 
 __device__ __forceinline__ void split_half(float v, __half& hi, __half& lo) {
@@ -78,7 +83,10 @@ constexpr int SMEM_BUDGET = 220 * 1024;
 
 constexpr int EPI_WARPS = 8;  // two per TMEM lane quadrant: each takes every other 32-column chunk of the tile
 
-template <int BN, int BK>
+// CN: CTAs per cluster (1 = no cluster). SHARE_A: the cluster's CTAs take CN consecutive n-tiles of the same m-tile and
+// share (multicast) the A tile; otherwise CN consecutive m-tiles of the same n-tile sharing the B tile. The tensor
+// map of the shared operand has a box of 1/CN of the tile rows.
+template <int BN, int BK, int CN, bool SHARE_A>
 __global__ void __launch_bounds__((2 + EPI_WARPS) * 32, 1) gemm_kernel(const __grid_constant__ CUtensorMap tmA,
                                                       const __grid_constant__ CUtensorMap tmB, GemmDev p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -94,14 +102,20 @@ __global__ void __launch_bounds__((2 + EPI_WARPS) * 32, 1) gemm_kernel(const __g
   const int n_a = p.terms == 3 ? 2 : 1, n_b = p.terms >= 2 ? 2 : 1;  // distinct A / B tiles per k-tile
   const int stage_bytes = n_a * A_BYTES + n_b * B_BYTES;
   const int stages = p.stages;
-  const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
-  const int n_tiles = tiles_m * tiles_n;
+  // persistent loop over super-tiles (= tiles when CN == 1); every CTA of a cluster walks the same sequence
+  const int crank = CN > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int sup_m = SHARE_A ? p.tiles_m : p.tiles_m / CN, sup_n = SHARE_A ? p.tiles_n / CN : p.tiles_n;
+  const int n_tiles = sup_m * sup_n;
+  const int first = static_cast<int>(blockIdx.x) / CN, stride = static_cast<int>(gridDim.x) / CN;
   const int k_tiles = (p.K + BK - 1) / BK;
+  constexpr uint16_t CMASK = static_cast<uint16_t>((1u << CN) - 1u);
+  auto tile_m0 = [&](int t) { return ((t % sup_m) * (SHARE_A ? 1 : CN) + (SHARE_A ? 0 : crank)) * BM; };
+  auto tile_n0 = [&](int t) { return ((t / sup_m) * (SHARE_A ? CN : 1) + (SHARE_A ? crank : 0)) * BN; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CN);  // one tcgen05.commit from every CTA of the cluster
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
@@ -114,6 +128,7 @@ __global__ void __launch_bounds__((2 + EPI_WARPS) * 32, 1) gemm_kernel(const __g
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = tmem_base_s;
+  if (CN > 1) cluster_sync_all();  // every CTA's barriers exist before any peer multicasts into it
   HN_PDL_LAUNCH();
   HN_PDL_WAIT();  // everything above overlapped the previous kernel's tail; operands / x are valid from here on
 
@@ -122,18 +137,31 @@ __global__ void __launch_bounds__((2 + EPI_WARPS) * 32, 1) gemm_kernel(const __g
       tma_prefetch_desc(&tmA);
       tma_prefetch_desc(&tmB);
       int it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+      for (int tile = first; tile < n_tiles; tile += stride) {
+        const int m0 = tile_m0(tile), n0 = tile_n0(tile);
         for (int kt = 0; kt < k_tiles; ++kt, ++it) {
           const int s = it % stages;
-          mbar_wait(&empty_bar[s], ((it / stages) & 1) ^ 1);
+          mbar_wait(&empty_bar[s], ((it / stages) & 1) ^ 1);  // (clusters: released by every CTA that reads it)
           mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
           uint8_t* st = smem + s * stage_bytes;
           const int k0 = kt * BK;
-          tma_load_2d(st, &tmA, &full_bar[s], k0, m0);
-          if (n_a == 2) tma_load_2d(st + A_BYTES, &tmA, &full_bar[s], k0 + p.a_seg, m0);
-          tma_load_2d(st + n_a * A_BYTES, &tmB, &full_bar[s], k0, n0);
-          if (n_b == 2) tma_load_2d(st + n_a * A_BYTES + B_BYTES, &tmB, &full_bar[s], k0 + p.b_seg, n0);
+          if (CN > 1 && SHARE_A) {  // my quarter (half) of the shared A tile, delivered to every CTA of the cluster
+            constexpr int SL = A_BYTES / CN, ROWS = BM / CN;
+            tma_load_2d_mc(st + crank * SL, &tmA, &full_bar[s], k0, m0 + crank * ROWS, CMASK);
+            if (n_a == 2) tma_load_2d_mc(st + A_BYTES + crank * SL, &tmA, &full_bar[s], k0 + p.a_seg, m0 + crank * ROWS, CMASK);
+          } else {
+            tma_load_2d(st, &tmA, &full_bar[s], k0, m0);
+            if (n_a == 2) tma_load_2d(st + A_BYTES, &tmA, &full_bar[s], k0 + p.a_seg, m0);
+          }
+          if (CN > 1 && !SHARE_A) {
+            constexpr int SL = B_BYTES / CN, ROWS = BN / CN;
+            tma_load_2d_mc(st + n_a * A_BYTES + crank * SL, &tmB, &full_bar[s], k0, n0 + crank * ROWS, CMASK);
+            if (n_b == 2)
+              tma_load_2d_mc(st + n_a * A_BYTES + B_BYTES + crank * SL, &tmB, &full_bar[s], k0 + p.b_seg, n0 + crank * ROWS, CMASK);
+          } else {
+            tma_load_2d(st + n_a * A_BYTES, &tmB, &full_bar[s], k0, n0);
+            if (n_b == 2) tma_load_2d(st + n_a * A_BYTES + B_BYTES, &tmB, &full_bar[s], k0 + p.b_seg, n0);
+          }
         }
       }
     }
@@ -141,7 +169,7 @@ __global__ void __launch_bounds__((2 + EPI_WARPS) * 32, 1) gemm_kernel(const __g
     if (elect_one()) {
       constexpr uint32_t idesc = idesc_f16(BM, BN, false, false);
       int it = 0, j = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+      for (int tile = first; tile < n_tiles; tile += stride, ++j) {
         const int acc = j & 1;
         mbar_wait(&acc_empty[acc], ((j >> 1) & 1) ^ 1);  // epilogue of tile j-2 has drained this accumulator
         fence_after_sync();
@@ -161,7 +189,7 @@ __global__ void __launch_bounds__((2 + EPI_WARPS) * 32, 1) gemm_kernel(const __g
             if (p.terms == 3) umma_ss(tD, smem_desc(a_lo + k * 32, 16, SBO, LAYOUT), dbh, idesc, true);
             if (p.terms >= 2) umma_ss(tD, dah, smem_desc(b_lo + k * 32, 16, SBO, LAYOUT), idesc, true);
           }
-          umma_commit(&empty_bar[s]);
+          if (CN > 1) umma_commit_mc(&empty_bar[s], CMASK); else umma_commit(&empty_bar[s]);
         }
         umma_commit(&acc_full[acc]);
       }
@@ -173,8 +201,8 @@ __global__ void __launch_bounds__((2 + EPI_WARPS) * 32, 1) gemm_kernel(const __g
     const uint32_t lane_base = (warp & 3) * 32;
     const int chunk0 = (warp - 2) >> 2;
     int j = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
-    const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+    for (int tile = first; tile < n_tiles; tile += stride, ++j) {
+    const int m0 = tile_m0(tile), n0 = tile_n0(tile);
     const int acc = j & 1;
     const uint32_t tD = tmem + acc * BN;
     const int row = m0 + lane_base + lane;
@@ -288,10 +316,11 @@ __global__ void __launch_bounds__((2 + EPI_WARPS) * 32, 1) gemm_kernel(const __g
   }
   fence_before_sync();
   __syncthreads();
+  if (CN > 1) cluster_sync_all();  // nobody leaves while a peer may still multicast into, or arrive on, its memory
   if (warp == 1) tmem_dealloc<2 * BN>(tmem);
 }
 
-template <int BN, int BK>
+template <int BN, int BK, int CN, bool SHARE_A>
 int launch_t(const GemmArgs& a, cudaStream_t stream) {
   CUtensorMap tmA, tmB;
   // single-segment operands rely on TMA zero fill beyond column K; split operands declare hi|lo and keep
@@ -299,8 +328,8 @@ int launch_t(const GemmArgs& a, cudaStream_t stream) {
   const uint64_t a_cols = a.terms == 3 ? static_cast<uint64_t>(a.a_seg) + a.K : a.K;
   const uint64_t b_cols = a.terms >= 2 ? static_cast<uint64_t>(a.b_seg) + a.K : a.K;
   const CUtensorMapSwizzle swz = BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-  if (!make_tmap_2d_f16(&tmA, a.A, a.M, a_cols, static_cast<uint64_t>(a.lda) * 2, BM, BK, swz) ||
-      !make_tmap_2d_f16(&tmB, a.B, a.N, b_cols, static_cast<uint64_t>(a.ldb) * 2, BN, BK, swz)) {
+  if (!make_tmap_2d_f16(&tmA, a.A, a.M, a_cols, static_cast<uint64_t>(a.lda) * 2, SHARE_A ? BM / CN : BM, BK, swz) ||
+      !make_tmap_2d_f16(&tmB, a.B, a.N, b_cols, static_cast<uint64_t>(a.ldb) * 2, SHARE_A ? BN : BN / CN, BK, swz)) {
     set_error("gemm: cuTensorMapEncodeTiled failed");
     return -2;
   }
@@ -310,19 +339,22 @@ int launch_t(const GemmArgs& a, cudaStream_t stream) {
   const int stage_bytes = ((a.terms == 3 ? 2 : 1) * BM + (a.terms >= 2 ? 2 : 1) * BN) * BK * 2;
   int stages = SMEM_BUDGET / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
+  const int tiles_m = (a.M + BM - 1) / BM, tiles_n = (a.N + BN - 1) / BN;
   GemmDev p{a.M, a.N, a.K, a.epi, a.act, a.bias, a.out, a.ldo, vec_ok, a.terms, a.a_seg, a.b_seg,
             half_out ? a.out_seg : 0, stages,
-            (a.bias != nullptr && (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0) ? 1 : 0};
+            (a.bias != nullptr && (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0) ? 1 : 0, tiles_m, tiles_n};
   const int smem = stages * stage_bytes + 1024;
   int dev = 0, sms = 0;
   HN_CHECK_CUDA(cudaGetDevice(&dev));
   HN_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   // per device and cheap: set on every launch so a process driving several GPUs never misses it
-  HN_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  HN_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, BK, CN, SHARE_A>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      SMEM_BUDGET + 1024));
-  const long n_tiles = static_cast<long>((a.N + BN - 1) / BN) * ((a.M + BM - 1) / BM);
-  const unsigned grid = static_cast<unsigned>(n_tiles < sms ? n_tiles : sms);
-  HN_CHECK_CUDA(launch_k(gemm_kernel<BN, BK>, dim3(grid), dim3((2 + EPI_WARPS) * 32), smem, stream, tmA, tmB, p));
+  const long n_super = static_cast<long>(tiles_m) * tiles_n / CN;  // the caller guarantees divisibility
+  const long max_clusters = sms / CN;
+  const unsigned grid = static_cast<unsigned>((n_super < max_clusters ? n_super : max_clusters) * CN);
+  HN_CHECK_CUDA(launch_kc(gemm_kernel<BN, BK, CN, SHARE_A>, dim3(grid), dim3((2 + EPI_WARPS) * 32), smem, stream,
+                          static_cast<unsigned>(CN), tmA, tmB, p));
   return 0;
 }
 }  // namespace
@@ -349,9 +381,27 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   }
   const int bn = force ? force : (tiles256 >= 120 ? 256 : tiles128 >= 120 ? 128 : 64);
   const int bk = force_bk ? force_bk : 64;  // 128-byte operand rows: half the L2 requests of BK = 32 (measured faster for every shape)
-  if (bn == 256) return bk == 64 ? launch_t<256, 64>(a, stream) : launch_t<256, 32>(a, stream);
-  if (bn == 128) return bk == 64 ? launch_t<128, 64>(a, stream) : launch_t<128, 32>(a, stream);
-  return bk == 64 ? launch_t<64, 64>(a, stream) : launch_t<64, 32>(a, stream);
+  // clusters (HN_GEMM_CLUSTER=0 turns them off, =1 forces them for every size): along N sharing the activations for
+  // the narrow-output GEMMs, along M sharing the weights for the wide FF1 tile; only when the tile grid divides
+  // evenly. Measured (tools/bench_gemm.py): at 2048 latent rows (batch 4) these GEMMs are latency-bound and the
+  // cluster hand-shakes cost 2-3 %; from ~16 k rows on they are operand-feed-bound and multicast gains 2-3 %.
+  static int cl = -1;
+  if (cl < 0) {
+    const char* e = getenv("HN_GEMM_CLUSTER");
+    cl = e ? atoi(e) : 4;
+    if (cl == 1) cl = -4;  // forced
+  }
+  const int tn = (a.N + bn - 1) / bn;
+  const bool want_cluster = cl < 0 || (cl > 1 && a.M >= 16384);
+  if (bk == 64 && want_cluster) {
+    if (bn == 64 && tn % 4 == 0) return launch_t<64, 64, 4, true>(a, stream);
+    if (bn == 64 && tn % 2 == 0) return launch_t<64, 64, 2, true>(a, stream);
+    if (bn == 128 && tn % 2 == 0) return launch_t<128, 64, 2, true>(a, stream);
+    if (bn == 256 && mt % 2 == 0) return launch_t<256, 64, 2, false>(a, stream);
+  }
+  if (bn == 256) return bk == 64 ? launch_t<256, 64, 1, true>(a, stream) : launch_t<256, 32, 1, true>(a, stream);
+  if (bn == 128) return bk == 64 ? launch_t<128, 64, 1, true>(a, stream) : launch_t<128, 32, 1, true>(a, stream);
+  return bk == 64 ? launch_t<64, 64, 1, true>(a, stream) : launch_t<64, 32, 1, true>(a, stream);
 }
 
 }  // namespace hn

@@ -27,7 +27,9 @@ def _split(x, seg):
     return out
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 72, 200), (2048, 512, 512), (5, 1024, 2005)])
+# (the 16384-row cases take the cluster / TMA-multicast path: shared A for the narrow outputs, shared B for N = 4096)
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 72, 200), (2048, 512, 512), (5, 1024, 2005),
+                                   (16384, 512, 192), (16384, 4096, 128), (16400, 1536, 64)])
 @pytest.mark.parametrize("terms", [1, 2, 3])
 def test_gemm_split_precision(M, N, K, terms):
     lib, st = _lib_stream()

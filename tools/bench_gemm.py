@@ -5,11 +5,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import healnet_b200
 lib = healnet_b200.load_library()
 st = torch.cuda.current_stream().cuda_stream
+RM = int(os.environ.get("HN_BENCH_ROWS", "2048"))   # latent rows = batch * l_c
 shapes = [("Q' small", 2048, 256, 512, 0, 0), ("Q tab", 2048, 512, 512, 0, 1), ("out-proj", 2048, 512, 512, 3, 0),
           ("FF1 gate", 2048, 4096, 512, 1, 1), ("FF2 res", 2048, 512, 2048, 2, 0), ("QKV self", 2048, 1536, 512, 0, 1),
           ("KV tab", 4, 1024, 2005, 0, 1)]
 tot = 0.0
 counts = {"Q' small": 6, "Q tab": 3, "out-proj": 18, "FF1 gate": 18, "FF2 res": 18, "QKV self": 9, "KV tab": 3}
+shapes = [(n, RM if M == 2048 else M, N, K, e, so) for (n, M, N, K, e, so) in shapes]
 for name, M, N, K, epi, split_out in shapes:
     seg = (K + 63) // 64 * 64
     A = (torch.randn(M, 2 * seg, device="cuda") * 0.1).half()
