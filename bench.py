@@ -35,6 +35,10 @@ WORKLOADS = {
              [(1, 2000), (224, 224, 3), (12, 224, 224, 3)], 4),
     "cfg2": (dict(n_modalities=2, channel_dims=[2000, 1024], num_spatial_axes=[1, 1], out_dims=4, l_c=256, l_d=512),
              [(1, 2000), (4096, 1024)], 8),
+    # cfg 3 of BASELINE.json: parameters and inputs in bf16 (the module computes in split fp16 / fp32 either way)
+    "cfg3": (dict(n_modalities=3, channel_dims=[2000, 3, 3], num_spatial_axes=[1, 2, 3], out_dims=4, l_c=512,
+                  l_d=1024, depth=8),
+             [(1, 2000), (224, 224, 3), (12, 224, 224, 3)], 16),
     "cfg4": (dict(n_modalities=2, channel_dims=[2000, 768], num_spatial_axes=[1, 1], out_dims=4, l_c=512, l_d=512),
              [(1, 2000), (8192, 768)], 4),
     "cfg5": (dict(n_modalities=1, channel_dims=[512], num_spatial_axes=[1], out_dims=4, l_c=512, l_d=512),
@@ -268,11 +272,14 @@ def run_gpu_arm(args):
 
     torch.manual_seed(0)
     model = HealNet(**kwargs).eval().to(dev)
+    io_dtype = torch.bfloat16 if args.workload == "cfg3" else torch.float32
+    if io_dtype != torch.float32:
+        model = model.to(io_dtype)
     token_shard = args.shard == "tokens" and world > 1
     # batch sharding (default): every rank owns its own samples; token sharding: every rank sees the SAME samples and
     # streams 1/world of each long token axis (strong scaling of a batch too small to spread over the GPUs)
     g = torch.Generator().manual_seed(0 if token_shard else rank)
-    host = [torch.rand((batch,) + tuple(s), generator=g).pin_memory() for s in shapes]
+    host = [torch.rand((batch,) + tuple(s), generator=g).to(io_dtype).pin_memory() for s in shapes]
     resident = [t.to(dev) for t in host]
     global_batch = batch if token_shard else batch * world
     if token_shard:
@@ -341,7 +348,7 @@ def run_gpu_arm(args):
         line = dict(
             metric=METRIC, value=value, unit="samples/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
             ms_per_step=ms_per_step, higher_is_better=True, scaling="strong" if token_shard else "weak",
-            vs_baseline=None, dtype="f32",
+            vs_baseline=None, dtype="f32" if io_dtype == torch.float32 else "bf16 I/O, fp16-split / fp32 arithmetic",
             data="synthetic",
             config=dict(workload=args.workload, batch_per_gpu=batch, global_batch=global_batch,
                         shapes=[list(s) for s in shapes], depth=cfg.depth, l_c=cfg.l_c, l_d=cfg.l_d,
@@ -350,7 +357,8 @@ def run_gpu_arm(args):
                         l2="per-step working set (standardised context rows + inputs) exceeds the 126 MB L2"),
             clocks=dict(sm_mhz=csum["sm_mhz"], sm_max_mhz=csum["sm_max_mhz"], reasons=csum["reasons"]),
             e2e=dict(value=global_batch * args.steps / e2e_s, unit="samples/s",
-                     h2d_bytes_per_step=sum(t.numel() * 4 for t in host), d2h_bytes_per_step=out_h.numel() * 4),
+                     h2d_bytes_per_step=sum(t.numel() * t.element_size() for t in host),
+                     d2h_bytes_per_step=out_h.numel() * out_h.element_size()),
             gpu_launches=launches,
             roofline=dict(bound="tensor", achieved=achieved, peak=peaks["tflops"], unit="TFLOP/s",
                           frac=achieved / peaks["tflops"],

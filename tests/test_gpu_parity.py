@@ -123,6 +123,9 @@ ORACLE_CASES = {
     # cfg 2 family: omic + WSI patch features (generic K/V projection path), latent 256 x 512 at reduced N
     "omic_wsi": (dict(n_modalities=2, channel_dims=[2000, 1024], num_spatial_axes=[1, 1], out_dims=4, l_c=256,
                       l_d=512, depth=2), [(2, 1, 2000), (2, 700, 1024)]),
+    # cfg 3 family: wide latents (l_d = 1024), depth 8, all three modalities at reduced spatial extent
+    "wide_latents_deep": (dict(n_modalities=3, channel_dims=[500, 3, 3], num_spatial_axes=[1, 2, 3], out_dims=4,
+                               l_c=128, l_d=1024, depth=8), [(2, 1, 500), (2, 48, 48, 3), (2, 3, 32, 32, 3)]),
     # tuned production hyper-parameters (config/best_hyperparams.yml:8-18,30): tiny odd latents, 1 head of 63
     # long token axis with a wide head: generic streaming path, two atoms per head, non-precise
     "wide_head_long_axis": (dict(n_modalities=1, channel_dims=[96], num_spatial_axes=[1], out_dims=4, l_c=64, l_d=96,
