@@ -547,7 +547,7 @@ template <int KW>  // operand width per head in fp16 elements (32, 64 or 128)
 __global__ void __launch_bounds__(256) attn_export_kernel(
     const __half* __restrict__ Q, int q_ld, int q_col0, int q_lo_off, const __half* __restrict__ K, long k_ld,
     int k_col0, int k_lo_off, int q_pitch, int k_pitch, int batch, int H, int L, long N, int nsplit,
-    const float* __restrict__ part_acc, const float* __restrict__ part_ml, int acc_w, int den_col,
+    const float* __restrict__ part_acc, const float* __restrict__ part_ml, int acc_w, int den_col, float den_scale,
     const uint64_t* __restrict__ mask_bits, float* __restrict__ out) {
   HN_PDL_LAUNCH();
   HN_PDL_WAIT();
@@ -580,7 +580,7 @@ __global__ void __launch_bounds__(256) attn_export_kernel(
       }
     }
     m_s[threadIdx.x] = M;
-    inv_s[threadIdx.x] = 1.f / den;
+    inv_s[threadIdx.x] = 1.f / (den * den_scale);
   }
   __syncthreads();
   if (n >= N) return;
@@ -762,10 +762,12 @@ int launch_attn_export(const AttnArgs& a, float* out, cudaStream_t stream) {
   const int q_pitch = kw, k_pitch = a.shared_kv ? 0 : a.hp;
   const int k_col0 = a.shared_kv ? 0 : a.k_col0;
   const int den_col = a.shared_kv ? a.c_ones : -1;
+  // xattn_small.cu accumulates P' = 2^P_SHIFT * P (P_SHIFT = 10): its denominator column carries that factor
+  const float den_scale = (a.shared_kv && !a.legacy_small) ? 0.0009765625f : 1.f;
 #define HN_EXPORT(KW)                                                                                              \
   attn_export_kernel<KW><<<grid, 256, 0, stream>>>(a.Q, a.q_ld, 0, q_lo, a.KV, a.kv_ld, k_col0, k_lo, q_pitch,      \
                                                    k_pitch, a.batch, a.H, a.L, a.N, a.nsplit, a.part_acc,          \
-                                                   a.part_ml, kw, den_col, a.mask_bits, out)
+                                                   a.part_ml, kw, den_col, den_scale, a.mask_bits, out)
   if (kw == 32)
     HN_EXPORT(32);
   else if (kw == 64)

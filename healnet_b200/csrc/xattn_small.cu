@@ -46,12 +46,15 @@ constexpr int BM = 128;  // latent rows per row block
 constexpr int BT = 64;   // tokens per tile
 constexpr int NST = 8;   // z ring depth
 constexpr int MAXG = 4;
-// P = 2^(s - m_ref) is stored in fp16 (subnormals included: representable down to 2^-24). A raise puts the
-// reference AT the row max seen so far; it then stays put until some P exceeds 2^5 (or is inf / garbage), i.e.
-// until the running max has grown by another 5 log2 units; that triggers the exact path, which raises it again.
-// (2^5 rather than fp16's 2^15 because the half2 polynomial below builds 2^(x+10) before scaling back.)
-constexpr float REF_SHIFT = 0.f;
-constexpr uint32_t P_RAISE_BITS = 0x5000u;  // fp16(32)
+// P is stored in fp16. A raise puts the reference AT the row max seen so far; it then stays put until some P exceeds
+// 2^5 times the reference weight (or is inf / garbage), i.e. until the running max has grown by another 5 log2 units;
+// that triggers the exact path, which raises it again.
+// P' = 2^(s - m_ref + P_SHIFT): the tile the UMMA delivers already carries -m_ref + P_SHIFT (folded into Q'), so the
+// half2 polynomial can build its result directly as a NORMAL fp16 (exponent field = rint(x') + 15 >= 1 for x' >= -14,
+// i.e. down to 2^-24 of the reference) without the final 2^-10 rescale, and MUFU results use the top of the fp16
+// range. Numerator and denominator (the ones column) carry the same 2^P_SHIFT, so it cancels in the combine kernels.
+constexpr float P_SHIFT = 10.f;
+constexpr uint32_t P_RAISE_BITS = 0x7800u;  // fp16(2^15) = 2^(RESCALE_THRESHOLD + P_SHIFT)
 constexpr float RESCALE_THRESHOLD = 5.f;    // log2 units
 
 struct SmallDev {
@@ -115,19 +118,19 @@ __device__ __forceinline__ constexpr bool poly_slot(int j) {
          : PMODE == 3 ? ((j % 8) == 1 || (j % 8) == 4 || (j % 8) == 6)
                       : (j % 2) == 1;
 }
-// packed-pair variant: both exponentials of a column pair on the FMA / ALU pipes in half2 arithmetic (12
-// instructions per PAIR incl. the fp16 pack, vs 17 for two fp32 polynomials + pack). n = rint(x) via the magic
-// constant trick (fp16 ulp is 1 in [1024, 2048)); the constant is 1536 + 10, so the integer that lands in the low
-// mantissa bits is n + 10 and the exponent insert (a lane-wise integer add) builds 2^(x+10) — normal fp16 for
-// every x >= -24 — which one exact HMUL2 by 2^-10 brings back, denormalising correctly. x above 5.5 overflows the
-// exponent field into inf / NaN / the sign bit: all of them read as "> 2^5" by the unsigned max check that
-// triggers the exact path. Relative error ~6e-4 rms (3x the fp16 rounding of P itself, zero-mean).
+// packed-pair variant: both exponentials of a column pair on the FMA / ALU pipes in half2 arithmetic (11
+// instructions per PAIR incl. the fp16 pack, vs 17 for two fp32 polynomials + pack). The argument already carries
+// +P_SHIFT (see above). n = rint(x) via the magic constant trick (fp16 ulp is 1 in [1024, 2048)): the integer lands in
+// the low mantissa bits and the exponent insert (a lane-wise integer add) builds 2^x — a normal fp16 for every
+// x >= -14, below which the argument is clamped (2^-24 of the reference weight). x above 15.5 overflows the exponent
+// field into inf / NaN / the sign bit: all of them read as "> 2^15" by the unsigned max check that triggers the exact
+// path. Relative error ~6e-4 rms (3x the fp16 rounding of P itself, zero-mean).
 __device__ __forceinline__ uint32_t ex2_pair_h2(float x0, float x1) {
   __half2 xh = __floats2half2_rn(x0, x1);
-  xh = __hmax2(xh, __float2half2_rn(-24.f));
-  const __half2 magic = __float2half2_rn(1546.f);
+  xh = __hmax2(xh, __float2half2_rn(-14.f));
+  const __half2 magic = __float2half2_rn(1536.f);
   const __half2 t = __hadd2(xh, magic);
-  const __half2 f = __hsub2(xh, __hsub2(t, magic));  // t = 1546 + rint(x) exactly
+  const __half2 f = __hsub2(xh, __hsub2(t, magic));  // t = 1536 + rint(x) exactly
   __half2 p = __float2half2_rn(0.05517167f);
   p = __hfma2(p, f, __float2half2_rn(0.24261112f));
   p = __hfma2(p, f, __float2half2_rn(0.69326099f));
@@ -135,8 +138,7 @@ __device__ __forceinline__ uint32_t ex2_pair_h2(float x0, float x1) {
   const uint32_t e = (*reinterpret_cast<const uint32_t*>(&t) << 10) & 0xFC00FC00u;
   uint32_t r;
   asm("add.u16x2 %0, %1, %2;" : "=r"(r) : "r"(*reinterpret_cast<const uint32_t*>(&p)), "r"(e));
-  const __half2 scaled = __hmul2(*reinterpret_cast<const __half2*>(&r), __float2half2_rn(0.0009765625f));
-  return *reinterpret_cast<const uint32_t*>(&scaled);
+  return r;
 }
 // PMODE >= 5: which column PAIRS take the half2 polynomial: 5 = 1/3, 6 = 1/2, 7 = 2/3, 8 = 3/4
 template <int PMODE>
@@ -301,7 +303,7 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const uint32_t tU = tL + 128;
       uint8_t* qrow_fold = sQ + g * Q_TILE;  // Q'[trow][C_ones] holds -m_ref (fp16): the UMMA subtracts the max for us
       float m_ref = -INFINITY;  // reference max (log2 units), always exactly representable in fp16
-      float m_in0 = 0.f, m_in1 = 0.f;  // offset baked into S buffer 0 / 1 by the fold (0: none)
+      float m_in0 = 0.f, m_in1 = 0.f;  // offset baked into S buffer 0 / 1 by the fold (0: none; else m_ref - P_SHIFT)
 
       // tiles [0, n_steady) can take the steady-state path (complete, unmasked 64-token tiles; only the globally last
       // tile of the token axis can be ragged)
@@ -365,7 +367,7 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           if (has_mask) bits = p.mask_bits[static_cast<long>(b) * p.tiles_total + tile_idx];
           const long rem = p.N - static_cast<long>(tile_idx) * BT;
           if (rem < BT) bits &= (1ull << rem) - 1ull;
-          const float m_in = buf ? m_in1 : m_in0;
+          const float m_in = buf ? m_in1 : m_in0;  // what the fold subtracted from the raw scores of this buffer
           float mx = -INFINITY;
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
@@ -384,8 +386,10 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           // raise lazily: keep the reference while the tile stays within 2^5 of it
           const bool raise = __any_sync(0xffffffffu, mx > m_ref + RESCALE_THRESHOLD);
           if (raise) {
-            // round the new reference to fp16 so that the folded offset IS the reference
-            const float m_new = fmaxf(m_ref, __half2float(__float2half_rn(mx - REF_SHIFT)));
+            // the fold (-m_ref + P_SHIFT) lives in Q' as fp16: round IT, and define the reference from the rounded
+            // value, so that the folded offset is exactly the reference the steady state assumes
+            const __half fold_h = __float2half_rn(P_SHIFT - fmaxf(m_ref, mx));
+            const float m_new = (mx == -INFINITY && m_ref == -INFINITY) ? -INFINITY : P_SHIFT - __half2float(fold_h);
             if (i > 0) {
               mbar_wait(&u_done[g], (i - 1) & 1);  // PV(i-1) landed; PV(i) cannot start before our p_ready arrive
               fence_after_sync();
@@ -408,12 +412,12 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
               ready = true;
             }
             m_ref = m_new;
-            const float fold = (m_ref == -INFINITY) ? 0.f : -m_ref;
-            *reinterpret_cast<__half*>(qrow_fold + swizzled_off<KD>(trow, p.c_ones)) = __float2half_rn(fold);
+            *reinterpret_cast<__half*>(qrow_fold + swizzled_off<KD>(trow, p.c_ones)) =
+                (m_ref == -INFINITY) ? __float2half_rn(0.f) : fold_h;
             fence_proxy_async_smem();
             stale = true;  // S(i+1) was computed with the previous offset
           }
-          const float m_cur = (m_ref == -INFINITY) ? 0.f : m_ref;
+          const float m_cur = (m_ref == -INFINITY) ? 0.f : m_ref - P_SHIFT;  // offset the current fold subtracts
           const float delta = m_in - m_cur;
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
