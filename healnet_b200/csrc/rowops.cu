@@ -223,6 +223,66 @@ __global__ void __launch_bounds__(256) build_z_small_kernel(const float* __restr
   }
 }
 
+// Specialisation for the shapes the path is run on (image / volume: 1-4 raw channels, 1-3 axes, the default 2
+// frequency bands -> F = 5): every feature lands in a compile-time register slot, so the row costs ~150 instructions
+// instead of the ~1000 of the generic kernel above (whose runtime column positions need a compare per slot).
+template <int CRAW, int NAX>
+__global__ void __launch_bounds__(256) build_z_small32_fast_kernel(const float* __restrict__ raw, __half* __restrict__ z,
+                                                                   long tokens_total, long N, AxisInfo ax,
+                                                                   const float* __restrict__ tab, long tok0) {
+  HN_PDL_LAUNCH();
+  HN_PDL_WAIT();
+  constexpr int F = 5, ZW = 32, C = CRAW + NAX * F;
+  static_assert(C < ZW, "context row must leave room for the ones column");
+  const long t = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= tokens_total) return;
+  unsigned rem = (tokens_total < (1L << 31))
+                     ? static_cast<unsigned>(t) % static_cast<unsigned>(N) + static_cast<unsigned>(tok0)
+                     : static_cast<unsigned>(t % N + tok0);
+  float v[C];
+  const float* r = raw + t * CRAW;
+#pragma unroll
+  for (int i = 0; i < CRAW; ++i) v[i] = __ldg(r + i);
+#pragma unroll
+  for (int a = NAX - 1; a >= 0; --a) {
+    const unsigned sz = static_cast<unsigned>(ax.size[a]);
+    const unsigned qd = rem / sz;
+    const float* tr = tab + static_cast<long>(ax.off[a] + static_cast<int>(rem - qd * sz)) * F;
+    rem = qd;
+#pragma unroll
+    for (int k = 0; k < F; ++k) v[CRAW + a * F + k] = __ldg(tr + k);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < C; ++i) s += v[i];
+  const float mean = s / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < C; ++i) {
+    const float d = v[i] - mean;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(q / C + LN_EPS);
+  uint4* dst = reinterpret_cast<uint4*>(z + t * ZW);
+#pragma unroll
+  for (int g = 0; g < ZW / 8; ++g) {
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int i = g * 8 + j;
+      o[j] = i < C ? (v[i < C ? i : 0] - mean) * rstd : (i == C ? 1.f : 0.f);
+    }
+    uint4 w;
+    __half2 h0 = __floats2half2_rn(o[0], o[1]), h1 = __floats2half2_rn(o[2], o[3]);
+    __half2 h2 = __floats2half2_rn(o[4], o[5]), h3 = __floats2half2_rn(o[6], o[7]);
+    w.x = *reinterpret_cast<uint32_t*>(&h0);
+    w.y = *reinterpret_cast<uint32_t*>(&h1);
+    w.z = *reinterpret_cast<uint32_t*>(&h2);
+    w.w = *reinterpret_cast<uint32_t*>(&h3);
+    dst[g] = w;
+  }
+}
+
 // ------------------------------------------------------------------ z rows, generic layout (any C)
 // one warp per token row
 __global__ void __launch_bounds__(256) build_z_large_kernel(const float* __restrict__ raw, __half* __restrict__ z,
@@ -672,6 +732,17 @@ int launch_build_z_small(const float* raw, __half* z, int zw, int batch, long N,
   AxisInfo ax = make_axis(axis_sizes, n_axes);
   const long total = static_cast<long>(batch) * N;
   const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  if (zw == 32 && F == 5 && c_raw >= 1 && c_raw <= 4 && n_axes >= 1 && n_axes <= 3) {
+#define HN_FAST(CR, NA)                                                                                      \
+  if (c_raw == CR && n_axes == NA) {                                                                         \
+    HN_CHECK_CUDA(launch_k(build_z_small32_fast_kernel<CR, NA>, dim3(grid), dim3(256), 0, stream, raw, z, total, N, ax, \
+                           tab, tok0));                                                                      \
+    return 0;                                                                                                \
+  }
+    HN_FAST(1, 1) HN_FAST(1, 2) HN_FAST(1, 3) HN_FAST(2, 1) HN_FAST(2, 2) HN_FAST(2, 3)
+    HN_FAST(3, 1) HN_FAST(3, 2) HN_FAST(3, 3) HN_FAST(4, 1) HN_FAST(4, 2) HN_FAST(4, 3)
+#undef HN_FAST
+  }
   if (zw == 32)
     HN_CHECK_CUDA(launch_k(build_z_small_kernel<32>, dim3(grid), dim3(256), 0, stream, raw, z, total, N, c_raw, ax, F, tab,
                            tok0));
