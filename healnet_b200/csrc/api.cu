@@ -52,6 +52,8 @@ struct AttnPacked {     // one PreNorm(Attention) module
   __half* WqS = nullptr;    // [H*zw][2 segD]  Wk^T Wq reassociated, gamma and scale folded
   float* Wv = nullptr;      // [I][zw]  gamma folded
   float* bv = nullptr;      // [I]      beta folded
+  __half* WoS = nullptr;    // [D][2 seg(H*zw)]  Wo . Wv' folded (split hi | lo): the small path's out-projection weight
+  float* boS = nullptr;     // [D]      bo + Wo . bv
   __half* Wo = nullptr;     // [D][2 * H*64] head-padded columns
 };
 struct FFPacked {
@@ -144,6 +146,8 @@ int plan_packed(hn_handle* h, Arena& ar) {
             p.WqS = ar.take<__half>(static_cast<size_t>(d.x_heads) * p.zw * 2 * h->segD);
             p.Wv = ar.take<float>(static_cast<size_t>(h->I) * p.zw);
             p.bv = ar.take<float>(h->I);
+            p.WoS = ar.take<__half>(static_cast<size_t>(D) * 2 * seg_of(d.x_heads * p.zw));
+            p.boS = ar.take<float>(D);
           }
           p.Wq = ar.take<__half>(static_cast<size_t>(d.x_heads) * h->hpx * 2 * h->segD);
           p.Wkv = ar.take<__half>(static_cast<size_t>(2) * d.x_heads * h->hpx * 2 * seg_of(p.C));
@@ -464,6 +468,10 @@ int hn_pack_weights(hn_handle* h, void* cuda_stream) {
           if (ap.small) {
             rc = pack_smallc_q(ap.WqS, 2 * sD, wa[4], wa[5], wa[2], H, D, C, dh, scale, ap.zw, sD, sD, st);
             if (rc == 0) rc = pack_smallc_v(ap.Wv, ap.bv, wa[5], wa[2], wa[3], h->I, C, ap.zw, st);
+            if (rc == 0) {
+              const int sHZ = seg_of(H * ap.zw);
+              rc = pack_smallc_out(ap.WoS, 2 * sHZ, ap.boS, wa[6], wa[7], ap.Wv, ap.bv, D, h->I, H, dh, ap.zw, sHZ, sHZ, st);
+            }
           }
           if (rc == 0) {
             const int sC = seg_of(C);
@@ -796,9 +804,12 @@ static int forward_impl(hn_handle* h, int batch, const void* const* modality_ptr
           profile_end(h, st);
           if (h->export_ptrs[l * (M + 1) + m] != nullptr) HN_TRY(launch_attn_export(aa, h->export_ptrs[l * (M + 1) + m], st));
           if (mp.sharded) HN_TRY(exchange_partials(h, ws, batch, mp.nsplit, H, L, mp.zw, pp, st));
-          HN_TRY(launch_combine_vproj(ws.part_acc, ws.part_ml, batch, mp.nsplit, H, L, mp.C, mp.zw,
-                                      d.cross_dim_head, ap.Wv, ap.bv, ws.o, 2 * ow, ow, HPx, st,
-                                      mp.sharded ? &pp : nullptr));
+          // merge + normalise only: u[b*L][h*zw + c] (split hi | lo); the V projection is folded into WoS
+          const int sHZ = seg_of(H * mp.zw);
+          if (sHZ != H * mp.zw)
+            HN_CHECK_CUDA(cudaMemsetAsync(ws.o, 0, sizeof(__half) * rows * 2 * sHZ, st));
+          HN_TRY(launch_combine_generic(ws.part_acc, ws.part_ml, batch, mp.nsplit, H, L, ws.o, 2 * sHZ, sHZ, mp.zw, st,
+                                        mp.sharded ? &pp : nullptr, mp.C));
         } else {
           // K/V projection of the standardised context (context LayerNorm affine folded into the weights).
           // Weights are always split (their rounding would not average out over tokens); z, K and V are split
@@ -830,9 +841,16 @@ static int forward_impl(hn_handle* h, int batch, const void* const* modality_ptr
                                         mp.sharded ? &pp : nullptr));
         }
         // x = LeakyReLU(O Wo^T + bo) + x   (healnet.py:383-386, 426, 236)
-        GemmArgs go{ws.o, ap.Wo, static_cast<int>(rows), D, ow, 2 * ow, 2 * ow, EPI_RES_LEAKY, 0, wa[7], ws.x, D,
-                    3, ow, ow, 0};
-        HN_TRY(launch_gemm(go, st));
+        if (mp.small) {
+          const int kz = H * mp.zw, sHZ = seg_of(kz);
+          GemmArgs go{ws.o, ap.WoS, static_cast<int>(rows), D, kz, 2 * sHZ, 2 * sHZ, EPI_RES_LEAKY, 0, ap.boS, ws.x,
+                      D, 3, sHZ, sHZ, 0};
+          HN_TRY(launch_gemm(go, st));
+        } else {
+          GemmArgs go{ws.o, ap.Wo, static_cast<int>(rows), D, ow, 2 * ow, 2 * ow, EPI_RES_LEAKY, 0, wa[7], ws.x, D,
+                      3, ow, ow, 0};
+          HN_TRY(launch_gemm(go, st));
+        }
         rc = run_ff(h, wf, fp, ws, rows, st);
         if (rc != 0) return rc;
       }

@@ -187,7 +187,9 @@ int launch_merge_signal(const float* part_acc, const float* part_ml, int batch, 
 // (lo_seg > 0: O rows are split [hi | lo], lo at column + lo_seg)
 int launch_combine_generic(const float* part_acc, const float* part_ml, int batch, int nsplit, int H, int L,
                            __half* O, int o_ld, int lo_seg, int hp, cudaStream_t stream,
-                           const PeerParts* peers = nullptr);
+                           const PeerParts* peers = nullptr, int den_col = -1);
+// (den_col >= 0: small-context partials, hp = zw = 32 | 64: O = acc[0..den_col) / acc[den_col], zeros beyond; the V and
+// output projections are folded into one weight, pack_smallc_out)
 // small-C: u = sum_s w_s acc_s[0..C) / sum_s w_s acc_s[C];  O[b*L][h*64+d] = u . Wv[h*dh+d][:] + bv[h*dh+d]
 int launch_combine_vproj(const float* part_acc, const float* part_ml, int batch, int nsplit, int H, int L, int C,
                          int zw, int dh, const float* Wv /*[H*dh][zw]*/, const float* bv /*[H*dh]*/, __half* O,

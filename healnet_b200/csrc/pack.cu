@@ -117,6 +117,41 @@ __global__ void pack_smallc_v_kernel(float* __restrict__ Wv_dst, float* __restri
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if (lane == 0) bv_dst[i] = acc;
 }
+
+// small-C output side: the V projection and the output projection are both linear in the merged accumulator u, so
+// they fold into ONE weight:  WoS[n][h*zw + c] = sum_d Wo[n][h*dh + d] * Wv'[h*dh + d][c]  (split hi | lo rows),
+// boS[n] = bo[n] + sum_i Wo[n][i] * bv'[i]. The out-projection GEMM then contracts over H*zw (256) instead of
+// H*64 (512) columns and the combine kernel only has to merge and normalise.
+__global__ void pack_smallc_out_kernel(__half* __restrict__ WoS, int ld_dst, float* __restrict__ boS,
+                                       const float* __restrict__ Wo, const float* __restrict__ bo,
+                                       const float* __restrict__ Wv, const float* __restrict__ bv, int inner, int H,
+                                       int dh, int zw, int seg, int lo_off) {
+  const int n = blockIdx.x;
+  const float* wo = Wo + static_cast<size_t>(n) * inner;
+  __half* dst = WoS + static_cast<size_t>(n) * ld_dst;
+  for (int j = threadIdx.x; j < seg; j += blockDim.x) {
+    float acc = 0.f;
+    if (j < H * zw) {
+      const int h = j / zw, c = j % zw;
+      for (int d = 0; d < dh; ++d) acc += wo[h * dh + d] * Wv[static_cast<size_t>(h * dh + d) * zw + c];
+    }
+    const __half hi = __float2half_rn(acc);
+    dst[j] = hi;
+    dst[lo_off + j] = __float2half_rn(acc - __half2float(hi));
+  }
+  __shared__ float red[32];
+  float b = 0.f;
+  for (int i = threadIdx.x; i < inner; i += blockDim.x) b += wo[i] * bv[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = b;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = bo[n];
+    for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) t += red[w];
+    boS[n] = t;
+  }
+}
 }  // namespace
 
 #define PACK_LAUNCH_CHECK()                    \
@@ -167,6 +202,13 @@ int pack_smallc_q(__half* Aq, int ld_dst, const float* Wq, const float* Wkv, con
 int pack_smallc_v(float* Wv_dst, float* bv_dst, const float* Wkv, const float* gamma, const float* beta, int inner,
                   int C, int zw, cudaStream_t st) {
   pack_smallc_v_kernel<<<inner, 32, 0, st>>>(Wv_dst, bv_dst, Wkv, gamma, beta, inner, C, zw);
+  PACK_LAUNCH_CHECK();
+  return 0;
+}
+
+int pack_smallc_out(__half* WoS, int ld_dst, float* boS, const float* Wo, const float* bo, const float* Wv,
+                    const float* bv, int D, int inner, int H, int dh, int zw, int seg, int lo_off, cudaStream_t st) {
+  pack_smallc_out_kernel<<<D, 256, 0, st>>>(WoS, ld_dst, boS, Wo, bo, Wv, bv, inner, H, dh, zw, seg, lo_off);
   PACK_LAUNCH_CHECK();
   return 0;
 }

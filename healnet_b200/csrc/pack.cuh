@@ -20,4 +20,7 @@ int pack_smallc_q(__half* Aq, int ld_dst, const float* Wq, const float* Wkv, con
                   int dh, float scale, int zw, int seg, int lo_off, cudaStream_t st);
 int pack_smallc_v(float* Wv_dst, float* bv_dst, const float* Wkv, const float* gamma, const float* beta, int inner,
                   int C, int zw, cudaStream_t st);
+// small-C path: V projection folded into the output projection (see pack.cu); Wv / bv are pack_smallc_v's outputs
+int pack_smallc_out(__half* WoS, int ld_dst, float* boS, const float* Wo, const float* bo, const float* Wv,
+                    const float* bv, int D, int inner, int H, int dh, int zw, int seg, int lo_off, cudaStream_t st);
 }  // namespace hn

@@ -494,7 +494,8 @@ __global__ void __launch_bounds__(256) merge_signal_kernel(const float* __restri
 __global__ void __launch_bounds__(256) combine_generic_kernel(const float* __restrict__ part_acc,
                                                               const float* __restrict__ part_ml, int batch,
                                                               int nsplit, int H, int L, __half* __restrict__ O,
-                                                              int o_ld, int lo_seg, int hp, PeerParts pp) {
+                                                              int o_ld, int lo_seg, int hp, int den_col,
+                                                              PeerParts pp) {
   HN_PDL_LAUNCH();
   HN_PDL_WAIT();
   peers_wait(pp);
@@ -523,11 +524,14 @@ __global__ void __launch_bounds__(256) combine_generic_kernel(const float* __res
       if (v < nv) a[v] += w * pac[base * hp + v * 32 + lane];
     den += w * ls;
   }
+  // small-context partials keep their denominator in accumulator column den_col (the column that met z's 1.0);
+  // columns from there on are padding and leave as zeros
+  if (den_col >= 0) den = __shfl_sync(0xffffffffu, den_col < 32 ? a[0] : a[1], den_col & 31);
   const float inv = 1.f / den;
   __half* o = O + (static_cast<long>(b) * L + l) * o_ld + h * hp;
 #pragma unroll
   for (int v = 0; v < 4; ++v)
-    if (v < nv) store_split(o, v * 32 + lane, 0, lo_seg, a[v] * inv);
+    if (v < nv) store_split(o, v * 32 + lane, 0, lo_seg, (den_col >= 0 && v * 32 + lane >= den_col) ? 0.f : a[v] * inv);
 }
 
 // small-C: acc rows are zw wide: [sum_t p z_c (c < C), sum_t p (col C), 0...]; then the V projection
@@ -788,13 +792,15 @@ int launch_pack_mask(const uint8_t* mask, uint64_t* bits, int batch, long N, cud
 }
 
 int launch_combine_generic(const float* part_acc, const float* part_ml, int batch, int nsplit, int H, int L,
-                           __half* O, int o_ld, int lo_seg, int hp, cudaStream_t stream, const PeerParts* peers) {
-  HN_REQUIRE(hp == 64 || hp == 128, "combine: head pitch must be 64 or 128");
+                           __half* O, int o_ld, int lo_seg, int hp, cudaStream_t stream, const PeerParts* peers,
+                           int den_col) {
+  HN_REQUIRE(hp == 32 || hp == 64 || hp == 128, "combine: accumulator rows are 32, 64 or 128 wide");
+  HN_REQUIRE(den_col < hp && den_col < 64, "combine: denominator column outside the accumulator row");
   const long total = static_cast<long>(batch) * L * H;
   PeerParts pp;
   if (peers != nullptr) pp = *peers;
   HN_CHECK_CUDA(launch_k(combine_generic_kernel, dim3(static_cast<unsigned>((total + 7) / 8)), dim3(256), 0, stream,
-                         part_acc, part_ml, batch, pp.world ? pp.world : nsplit, H, L, O, o_ld, lo_seg, hp, pp));
+                         part_acc, part_ml, batch, pp.world ? pp.world : nsplit, H, L, O, o_ld, lo_seg, hp, den_col, pp));
   HN_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
