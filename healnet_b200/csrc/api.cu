@@ -831,14 +831,21 @@ static int forward_impl(hn_handle* h, int batch, const void* const* modality_ptr
           aa.precise = mp.precise ? 1 : 0;
           aa.q_lo_off = qw;
           aa.kv_lo_off = kvw;
+          const bool direct = mp.nsplit == 1 && !mp.sharded;  // one split: the kernel normalises and stores O itself
+          if (direct) {
+            aa.out = ws.o;
+            aa.out_ld = 2 * ow;
+            aa.out_lo_seg = ow;
+          }
           rc = profile_begin(h, m, aa, st);
           if (rc != 0) return rc;
           HN_TRY(launch_attention(aa, st));
           profile_end(h, st);
           if (h->export_ptrs[l * (M + 1) + m] != nullptr) HN_TRY(launch_attn_export(aa, h->export_ptrs[l * (M + 1) + m], st));
           if (mp.sharded) HN_TRY(exchange_partials(h, ws, batch, mp.nsplit, H, L, HPx, pp, st));
-          HN_TRY(launch_combine_generic(ws.part_acc, ws.part_ml, batch, mp.nsplit, H, L, ws.o, 2 * ow, ow, HPx, st,
-                                        mp.sharded ? &pp : nullptr));
+          if (!direct)
+            HN_TRY(launch_combine_generic(ws.part_acc, ws.part_ml, batch, mp.nsplit, H, L, ws.o, 2 * ow, ow, HPx, st,
+                                          mp.sharded ? &pp : nullptr));
         }
         // x = LeakyReLU(O Wo^T + bo) + x   (healnet.py:383-386, 426, 236)
         if (mp.small) {
@@ -887,9 +894,16 @@ static int forward_impl(hn_handle* h, int batch, const void* const* modality_ptr
         aa.mask_bits = nullptr;
         aa.part_acc = ws.part_acc;
         aa.part_ml = ws.part_ml;
+        const bool direct = ws.self_nsplit == 1;
+        if (direct) {
+          aa.out = ws.o;
+          aa.out_ld = 2 * ow;
+          aa.out_lo_seg = ow;
+        }
         HN_TRY(launch_attention(aa, st));
         if (h->export_ptrs[l * (M + 1) + M] != nullptr) HN_TRY(launch_attn_export(aa, h->export_ptrs[l * (M + 1) + M], st));
-        HN_TRY(launch_combine_generic(ws.part_acc, ws.part_ml, batch, ws.self_nsplit, lh, L, ws.o, 2 * ow, ow, HPl, st));
+        if (!direct)
+          HN_TRY(launch_combine_generic(ws.part_acc, ws.part_ml, batch, ws.self_nsplit, lh, L, ws.o, 2 * ow, ow, HPl, st));
         GemmArgs go{ws.o, ap.Wo, static_cast<int>(rows), D, ow, 2 * ow, 2 * ow, EPI_RES_LEAKY, 0, wa[5], ws.x, D,
                     3, ow, ow, 0};
         HN_TRY(launch_gemm(go, st));

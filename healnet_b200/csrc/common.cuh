@@ -152,6 +152,11 @@ struct AttnArgs {
   const uint64_t* mask_bits;  // [batch][ceil(N/64)] or null
   float* part_acc;            // [batch][nsplit][H][L][VD] fp32 un-normalised accumulators
   float* part_ml;             // [batch][nsplit][H][L][2] (running max in log2 units, row sum (generic only))
+  // generic path, nsplit == 1 only: write the normalised rows straight into O[(b*L + l)][h*hp + c] (fp16, lo part at
+  // + out_lo_seg when > 0) instead of the accumulator partials — saves the combine launch (latent self-attention,
+  // tabular row). part_ml is still written (the attention-weight export reads it).
+  __half* out = nullptr;
+  int out_ld = 0, out_lo_seg = 0;
 };
 int launch_attention(const AttnArgs& a, cudaStream_t stream);
 int attention_pick_nsplit(int batch, int L, int H, long N);

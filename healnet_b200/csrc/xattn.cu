@@ -47,6 +47,8 @@ struct AttnDev {
   const uint64_t* mask_bits;
   float* part_acc;
   float* part_ml;
+  __half* out;  // nsplit == 1: normalised output rows (see AttnArgs::out), else null
+  int out_ld, out_lo_seg;
 };
 
 // PREC (generic path only): operands arrive split as hi + lo fp16 pairs; S = Qh.Kh + Ql.Kh + Qh.Kl and
@@ -294,12 +296,33 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     // ---- epilogue: un-normalised accumulator rows + (m, l)
     mbar_wait(&acc_done, 0);
     fence_after_sync();
+    const float inv_l = 1.f / l_sum;  // (a fully masked row gives NaN, like the reference's softmax over -inf)
 #pragma unroll
     for (int c = 0; c < VD; c += 32) {
       uint32_t u[32];
       tmem_ld32(tmem_addr(tU, lane_base, c), u);
       tmem_wait_ld();
-      if (row < p.L) {
+      if (row < p.L && p.out != nullptr) {
+        // single split: normalise and store the fp16 (hi | lo) output row directly
+        __half* o = p.out + (static_cast<long>(b) * p.L + row) * p.out_ld + h * VD + c;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 qh, ql;
+          uint32_t* ph = reinterpret_cast<uint32_t*>(&qh);
+          uint32_t* pl = reinterpret_cast<uint32_t*>(&ql);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float v0 = __uint_as_float(u[j + 2 * k]) * inv_l, v1 = __uint_as_float(u[j + 2 * k + 1]) * inv_l;
+            const __half2 hi = __floats2half2_rn(v0, v1);
+            const float2 hf = __half22float2(hi);
+            const __half2 lo = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+            ph[k] = *reinterpret_cast<const uint32_t*>(&hi);
+            pl[k] = *reinterpret_cast<const uint32_t*>(&lo);
+          }
+          *reinterpret_cast<uint4*>(o + j) = qh;
+          if (p.out_lo_seg > 0) *reinterpret_cast<uint4*>(o + p.out_lo_seg + j) = ql;
+        }
+      } else if (row < p.L) {
         float4* dst = reinterpret_cast<float4*>(p.part_acc + (part_row0 + lane_base + lane) * VD + c);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
@@ -344,6 +367,12 @@ int launch_t(const AttnArgs& a, cudaStream_t stream) {
   p.mask_bits = a.mask_bits;
   p.part_acc = a.part_acc;
   p.part_ml = a.part_ml;
+  p.out = (a.nsplit == 1 && !SHARED) ? a.out : nullptr;
+  p.out_ld = a.out_ld;
+  p.out_lo_seg = a.out_lo_seg;
+  if (p.out != nullptr)
+    HN_REQUIRE((reinterpret_cast<uintptr_t>(a.out) & 15) == 0 && a.out_ld % 8 == 0 && a.out_lo_seg % 8 == 0,
+               "attention: direct output rows must be 16-byte aligned");
   constexpr int NSTAGE = (PREC || NA == 2) ? 2 : 4;
   constexpr int SMEM = (PREC ? 2 : 1) * NA * BM * KD * 2 +
                        NSTAGE * (SHARED ? 1 : (PREC ? 4 : 2) * NA) * BT * KD * 2 + 1024;
