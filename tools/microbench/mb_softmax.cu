@@ -57,6 +57,13 @@ __device__ __forceinline__ uint32_t ex2_pair_h2_v(float x0, float x1) {
   asm("add.u16x2 %0, %1, %2;" : "=r"(r) : "r"(*reinterpret_cast<const uint32_t*>(&p)), "r"(e));
   return r;
 }
+// MUFU pair through the packed half2 form: one pack of the arguments, ex2.approx.f16x2, result already packed
+__device__ __forceinline__ uint32_t ex2_pair_mufu_h2(float x0, float x1) {
+  __half2 xh = __floats2half2_rn(x0, x1);
+  uint32_t r;
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(*reinterpret_cast<const uint32_t*>(&xh)));
+  return r;
+}
 // bf16 pack by truncation: one PRMT per pair, no conversion unit
 __device__ __forceinline__ uint32_t pack_bf16_trunc(float lo, float hi) {
   uint32_t r;
@@ -95,6 +102,7 @@ __device__ __forceinline__ bool poly_pair(int j) {
          : MODE == 6 || MODE == 21 || MODE == 22 || MODE == 25 ? (j % 2) == 1
          : MODE == 23 ? ((j % 8) != 0 && (j % 8) != 3 && (j % 8) != 6)
          : MODE == 24 ? ((j % 8) == 1 || (j % 8) == 4 || (j % 8) == 6)
+         : MODE == 28 ? (j % 2) == 1
          : MODE == 26 ? (j % 4) != 0
          : MODE == 27;
 }
@@ -139,6 +147,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_softmax(float* out, int iters, l
         else if (MODE == 10) pk[c * 16 + j] = pack_bf16_trunc(ex2_mufu(x0), ex2_mufu(x1));
         else if (MODE >= 20 && poly_pair<MODE>(j)) pk[c * 16 + j] = ex2_pair_h2_v<(MODE >= 22), (MODE == 25 ? 2 : 3)>(x0, x1);
         else if (poly_pair<MODE>(j)) pk[c * 16 + j] = ex2_pair_h2(x0, x1);
+        else if (MODE == 28) pk[c * 16 + j] = ex2_pair_mufu_h2(x0, x1);
         else pk[c * 16 + j] = pack_half2(ex2_mufu(x0), ex2_mufu(x1));
         if (MODE != 11) pmax = vmaxu2(pmax, pk[c * 16 + j]);
       }
@@ -197,6 +206,7 @@ int main() {
   run<26, 12>("3/4 polynomial, no final scale, ALU shift");
   run<27, 12>("all polynomial, no final scale, ALU shift");
   run<25, 12>("1/2 degree-2 polynomial, no scale, ALU shift");
+  run<28, 12>("1/2 polynomial (no scale, ALU shift) + MUFU pairs as ex2.f16x2");
   run<22, 16>("1/2 polynomial, no final scale, ALU shift");
   run<23, 16>("5/8 polynomial, no final scale, ALU shift");
   return 0;
