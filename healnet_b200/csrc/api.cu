@@ -206,6 +206,7 @@ struct Workspace {
   float* part_ml = nullptr;
   uint64_t* mask_bits = nullptr;
   float* pooled = nullptr;   // [b][D] mean over latents (head)
+  unsigned* ln_counters = nullptr;  // per 128-row block arrival counters of the fused LayerNorm (gemm.cu)
   int self_nsplit = 1;
   size_t bytes = 0;
 };
@@ -289,6 +290,7 @@ int plan_workspace(const hn_handle* h, int batch, const int* axis_sizes, const b
   ws.part_ml = ar.take<float>(part_ml_elems);
   ws.mask_bits = ar.take<uint64_t>(mask_words);
   ws.pooled = ar.take<float>(static_cast<size_t>(batch) * D);
+  ws.ln_counters = ar.take<unsigned>(static_cast<size_t>((rows + 127) / 128));
   ws.bytes = ar.off + 256;
   return 0;
 }
@@ -323,18 +325,56 @@ void profile_end(hn_handle* h, cudaStream_t st) {
 }
 
 // x += FeedForward(LN(x))   (healnet.py:237/245, 339-351)
+// The PreNorm LayerNorms of a forward in execution order. Every one but the first follows a residual GEMM, which can
+// emit it from its epilogue (GemmArgs::ln_*): `valid` says ws.xn already holds the LayerNorm that is due next.
+struct LnPlan {
+  std::vector<std::pair<const float*, const float*>> seq;  // (gamma, beta)
+  size_t next = 0;
+  bool valid = false;
+  int fused = 0;  // fused launches so far (the row-block counters grow by tiles_n with each)
+};
+// LayerNorm due now -> ws.xn (skipped when the previous residual GEMM produced it)
+int ln_step(hn_handle* h, LnPlan& lp, Workspace& ws, long rows, cudaStream_t st) {
+  const int D = h->d.l_d, sD = h->segD;
+  HN_REQUIRE(lp.next < lp.seq.size(), "hn_forward: LayerNorm plan out of sync");
+  if (!lp.valid)
+    HN_TRY(launch_layernorm_f16(ws.x, D, lp.seq[lp.next].first, lp.seq[lp.next].second, ws.xn, 2 * sD, sD, sD, rows, D, st));
+  lp.valid = false;
+  ++lp.next;
+  return 0;
+}
+// residual GEMM that also emits the next LayerNorm when the kernel can
+int residual_gemm(hn_handle* h, GemmArgs g, LnPlan& lp, Workspace& ws, cudaStream_t st) {
+  bool fuse = lp.next < lp.seq.size() && h->segD == h->d.l_d && gemm_can_fuse_ln(g);
+  if (fuse) {
+    g.ln_gamma = lp.seq[lp.next].first;
+    g.ln_beta = lp.seq[lp.next].second;
+    g.ln_out = ws.xn;
+    g.ln_ld = 2 * h->segD;
+    g.ln_seg = h->segD;
+    g.ln_counters = ws.ln_counters;
+    g.ln_epoch = lp.fused + 1;
+    fuse = (reinterpret_cast<uintptr_t>(g.ln_gamma) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.ln_beta) & 15) == 0;
+    if (!fuse) g.ln_out = nullptr;
+  }
+  HN_TRY(launch_gemm(g, st));
+  lp.valid = fuse;
+  if (fuse) ++lp.fused;
+  return 0;
+}
+
 int run_ff(hn_handle* h, const std::vector<const float*>& wf, const FFPacked& fp, Workspace& ws, long rows,
-           cudaStream_t st) {
+           LnPlan& lp, cudaStream_t st) {
   const hn_desc& d = h->d;
   const int D = d.l_d;
   const int sD = h->segD, s4 = h->seg4D;
-  HN_TRY(launch_layernorm_f16(ws.x, D, wf[0], wf[1], ws.xn, 2 * sD, sD, sD, rows, D, st));
+  int rc = ln_step(h, lp, ws, rows, st);
+  if (rc != 0) return rc;
   GemmArgs g1{ws.xn, fp.W1, static_cast<int>(rows), 8 * D, D, 2 * sD, 2 * sD, EPI_GATE_F16,
               d.snn ? ACT_SELU : ACT_GELU, fp.b1, ws.hid, 2 * s4, 3, sD, sD, s4};
   HN_TRY(launch_gemm(g1, st));
   GemmArgs g2{ws.hid, fp.W2, static_cast<int>(rows), D, 4 * D, 2 * s4, 2 * s4, EPI_RES, 0, wf[5], ws.x, D, 3, s4, s4, 0};
-  HN_TRY(launch_gemm(g2, st));
-  return 0;
+  return residual_gemm(h, g2, lp, ws, st);
 }
 
 }  // namespace
@@ -757,6 +797,26 @@ static int forward_impl(hn_handle* h, int batch, const void* const* modality_ptr
   // ---- x = repeat(latents, 'n d -> b n d')   (healnet.py:225)
   HN_TRY(launch_broadcast_rows(wl[0], ws.x, static_cast<long>(L) * D, batch, st));
 
+  // LayerNorm plan: same control flow as the loop below
+  LnPlan lp;
+  for (int l = 0; l < d.depth; ++l) {
+    for (int m = 0; m < M; ++m) {
+      if (ws.mod[m].present) {
+        const std::vector<const float*>& wa = h->w[slot_index(h, l, 2 * m)];
+        const std::vector<const float*>& wf = h->w[slot_index(h, l, 2 * m + 1)];
+        lp.seq.emplace_back(wa[0], wa[1]);
+        lp.seq.emplace_back(wf[0], wf[1]);
+      }
+      if (d.self_per_cross_attn && !(skip_latent_block != nullptr && skip_latent_block[m] != 0)) {
+        const std::vector<const float*>& wa = h->w[slot_index(h, l, 2 * M)];
+        const std::vector<const float*>& wf = h->w[slot_index(h, l, 2 * M + 1)];
+        lp.seq.emplace_back(wa[0], wa[1]);
+        lp.seq.emplace_back(wf[0], wf[1]);
+      }
+    }
+  }
+  HN_CHECK_CUDA(cudaMemsetAsync(ws.ln_counters, 0, sizeof(unsigned) * static_cast<size_t>((rows + 127) / 128), st));
+
   for (int l = 0; l < d.depth; ++l) {
     for (int m = 0; m < M; ++m) {
       ModPlan& mp = ws.mod[m];
@@ -771,7 +831,8 @@ static int forward_impl(hn_handle* h, int batch, const void* const* modality_ptr
         const FFPacked& fp = h->ff[l * (M + 1) + m];
         const int H = d.x_heads, HPx = h->hpx, ow = H * HPx;
         // PreNorm + to_q (split operands; the small-C Q' keeps its hi part only)
-        HN_TRY(launch_layernorm_f16(ws.x, D, wa[0], wa[1], ws.xn, 2 * sD, sD, sD, rows, D, st));
+        rc = ln_step(h, lp, ws, rows, st);
+        if (rc != 0) return rc;
         const int qw = mp.small ? H * mp.zw : H * HPx;
         const bool q_split = !mp.small && mp.precise;
         GemmArgs gq{ws.xn, mp.small ? ap.WqS : ap.Wq, static_cast<int>(rows), qw, D, 2 * sD, 2 * sD, EPI_F16, 0,
@@ -852,13 +913,14 @@ static int forward_impl(hn_handle* h, int batch, const void* const* modality_ptr
           const int kz = H * mp.zw, sHZ = seg_of(kz);
           GemmArgs go{ws.o, ap.WoS, static_cast<int>(rows), D, kz, 2 * sHZ, 2 * sHZ, EPI_RES_LEAKY, 0, ap.boS, ws.x,
                       D, 3, sHZ, sHZ, 0};
-          HN_TRY(launch_gemm(go, st));
+          rc = residual_gemm(h, go, lp, ws, st);
         } else {
           GemmArgs go{ws.o, ap.Wo, static_cast<int>(rows), D, ow, 2 * ow, 2 * ow, EPI_RES_LEAKY, 0, wa[7], ws.x, D,
                       3, ow, ow, 0};
-          HN_TRY(launch_gemm(go, st));
+          rc = residual_gemm(h, go, lp, ws, st);
         }
-        rc = run_ff(h, wf, fp, ws, rows, st);
+        if (rc != 0) return rc;
+        rc = run_ff(h, wf, fp, ws, rows, lp, st);
         if (rc != 0) return rc;
       }
       if (d.self_per_cross_attn && !(skip_latent_block != nullptr && skip_latent_block[m] != 0)) {
@@ -869,7 +931,8 @@ static int forward_impl(hn_handle* h, int batch, const void* const* modality_ptr
         const FFPacked& fp = h->ff[l * (M + 1) + M];
         const int lh = d.l_heads, HPl = h->hpl, ow = lh * HPl, qw = 3 * lh * HPl;
         const bool prec = ws.self_precise;
-        HN_TRY(launch_layernorm_f16(ws.x, D, wa[0], wa[1], ws.xn, 2 * sD, sD, sD, rows, D, st));
+        rc = ln_step(h, lp, ws, rows, st);
+        if (rc != 0) return rc;
         GemmArgs gq{ws.xn, ap.Wq, static_cast<int>(rows), qw, D, 2 * sD, 2 * sD, EPI_F16, 0, nullptr, ws.q,
                     prec ? 2 * qw : qw, 3, sD, sD, prec ? qw : 0};
         HN_TRY(launch_gemm(gq, st));
@@ -906,8 +969,9 @@ static int forward_impl(hn_handle* h, int batch, const void* const* modality_ptr
           HN_TRY(launch_combine_generic(ws.part_acc, ws.part_ml, batch, ws.self_nsplit, lh, L, ws.o, 2 * ow, ow, HPl, st));
         GemmArgs go{ws.o, ap.Wo, static_cast<int>(rows), D, ow, 2 * ow, 2 * ow, EPI_RES_LEAKY, 0, wa[5], ws.x, D,
                     3, ow, ow, 0};
-        HN_TRY(launch_gemm(go, st));
-        rc = run_ff(h, wf, fp, ws, rows, st);
+        rc = residual_gemm(h, go, lp, ws, st);
+        if (rc != 0) return rc;
+        rc = run_ff(h, wf, fp, ws, rows, lp, st);
         if (rc != 0) return rc;
       }
     }

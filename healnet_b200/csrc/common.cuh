@@ -100,8 +100,21 @@ struct GemmArgs {
   int terms = 1;
   int a_seg = 0, b_seg = 0;  // column offset of the lo segment inside A / B rows (multiple of 64, >= K)
   int out_seg = 0;           // fp16 epilogues: > 0 -> lo part of the output stored at column + out_seg
+  // Residual epilogues (EPI_RES / EPI_RES_LEAKY) whose output rows are complete rows of x (ldo == N <= 1024): also
+  // emit LayerNorm(x_new) * gamma + beta — the PreNorm of the NEXT module — as split fp16 (hi | lo at + ln_seg) into
+  // ln_out, so that module's separate LayerNorm launch disappears. Needs one tile per CTA (gemm_can_fuse_ln): every
+  // CTA publishes its tile on the row block's counter, waits for the block to be complete and normalises its share
+  // of the block's rows with the same two-pass arithmetic as layernorm_f16_kernel.
+  const float* ln_gamma = nullptr;
+  const float* ln_beta = nullptr;
+  __half* ln_out = nullptr;
+  int ln_ld = 0, ln_seg = 0;
+  unsigned* ln_counters = nullptr;  // ceil(M / 128) words, zero at the start of the forward
+  int ln_epoch = 0;                 // 1-based index of this launch among the forward's fused launches
 };
 int launch_gemm(const GemmArgs& a, cudaStream_t stream);
+// can this residual GEMM also emit the next LayerNorm (GemmArgs::ln_*)? (shape / alignment rules, HN_GEMM_LN switch)
+bool gemm_can_fuse_ln(const GemmArgs& a);
 
 // ------------------------------------------------------------------ row ops (rowops.cu)
 // y[r] = [hi | lo] split fp16 of LN(x[r]) * gamma + beta: hi in columns [0, seg), lo in [lo_seg, lo_seg + seg)

@@ -54,6 +54,12 @@ struct GemmDev {
   int out_seg;       // fp16 outputs: > 0 -> also store lo = fp16(v - hi) at column + out_seg
   int stages;        // depth of the operand ring (host: as many as fit the SM's shared memory, <= 8)
   int bias_vec;      // bias is 16-byte aligned -> float4 loads
+  const float* ln_gamma;  // fused LayerNorm of completed row blocks (see GemmArgs), ln_out == null: off
+  const float* ln_beta;
+  __half* ln_out;
+  int ln_ld, ln_seg;
+  unsigned* ln_counters;
+  int ln_epoch;  // fused launches so far in this forward, this one included
   int tiles_m, tiles_n;  // output tiles; with clusters: super-tiles of CN tiles along N (SHARE_A) or M (!SHARE_A)
 };
 
@@ -312,6 +318,74 @@ __global__ void __launch_bounds__((2 + EPI_WARPS) * 32, 1) gemm_kernel(const __g
     fence_before_sync();
     __syncwarp();
     if (lane == 0) mbar_arrive(&acc_empty[acc]);
+    if (p.ln_out != nullptr) {
+      // ---- fused PreNorm of the next module. Every CTA holds exactly one tile here (the host checks), so all tiles
+      // of a 128-row block are in flight together: each CTA publishes its tile on the block's counter, waits until
+      // the block is complete (counter == epoch * tiles_n; the counters only grow within a forward) and then
+      // normalises ITS share of the block's rows — the LayerNorm runs on every SM, like the separate kernel did.
+      __threadfence();
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+      if (threadIdx.x == 64) {
+        unsigned* ctr = p.ln_counters + m0 / BM;
+        atomicAdd(ctr, 1u);
+        const unsigned target = static_cast<unsigned>(p.ln_epoch) * static_cast<unsigned>(p.tiles_n);
+        unsigned seen;
+        int spins = 0;  // bounded (~1 s): a logic error must never hang the GPU
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+          if (seen < target) __nanosleep(40);
+        } while (seen < target && ++spins < (1 << 24));
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+      {
+        const int ew = warp - 2;                                    // 0 .. EPI_WARPS-1
+        const int share = (BM + p.tiles_n - 1) / p.tiles_n;         // rows of the block this CTA normalises
+        const int rbeg = (n0 / BN) * share, rend = rbeg + share < BM ? rbeg + share : BM;
+        constexpr int NQ = 4;  // float4 per lane: rows of up to 512 columns (the host checks)
+        for (int r0 = rbeg + ew; r0 < rend; r0 += EPI_WARPS) {
+          const int rr = m0 + r0;
+          if (rr >= p.M) break;
+          const float* xr = reinterpret_cast<const float*>(p.out) + static_cast<size_t>(rr) * p.ldo;
+          float4 xv[NQ];
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) {
+            const int c = (q * 32 + lane) * 4;
+            xv[q] = c < p.N ? __ldcg(reinterpret_cast<const float4*>(xr + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          float sum = 0.f;
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) sum += xv[q].x + xv[q].y + xv[q].z + xv[q].w;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+          const float mean = sum / p.N;
+          float qq = 0.f;
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) {
+            if ((q * 32 + lane) * 4 < p.N) {
+              const float d0 = xv[q].x - mean, d1 = xv[q].y - mean, d2 = xv[q].z - mean, d3 = xv[q].w - mean;
+              qq += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+            }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
+          const float rstd = rsqrtf(qq / p.N + 1e-5f);
+          __half* y = p.ln_out + static_cast<size_t>(rr) * p.ln_ld;
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) {
+            const int c = (q * 32 + lane) * 4;
+            if (c < p.N) {
+              const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + c));
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.ln_beta + c));
+              uint2 hi, lo;
+              hi.x = pack_hi2((xv[q].x - mean) * rstd * g4.x + b4.x, (xv[q].y - mean) * rstd * g4.y + b4.y, lo.x);
+              hi.y = pack_hi2((xv[q].z - mean) * rstd * g4.z + b4.z, (xv[q].w - mean) * rstd * g4.w + b4.w, lo.y);
+              *reinterpret_cast<uint2*>(y + c) = hi;
+              *reinterpret_cast<uint2*>(y + p.ln_seg + c) = lo;
+            }
+          }
+        }
+      }
+    }
     }  // tile
   }
   fence_before_sync();
@@ -342,7 +416,8 @@ int launch_t(const GemmArgs& a, cudaStream_t stream) {
   const int tiles_m = (a.M + BM - 1) / BM, tiles_n = (a.N + BN - 1) / BN;
   GemmDev p{a.M, a.N, a.K, a.epi, a.act, a.bias, a.out, a.ldo, vec_ok, a.terms, a.a_seg, a.b_seg,
             half_out ? a.out_seg : 0, stages,
-            (a.bias != nullptr && (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0) ? 1 : 0, tiles_m, tiles_n};
+            (a.bias != nullptr && (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0) ? 1 : 0,
+            a.ln_gamma, a.ln_beta, a.ln_out, a.ln_ld, a.ln_seg, a.ln_counters, a.ln_epoch, tiles_m, tiles_n};
   const int smem = stages * stage_bytes + 1024;
   int dev = 0, sms = 0;
   HN_CHECK_CUDA(cudaGetDevice(&dev));
@@ -359,6 +434,23 @@ int launch_t(const GemmArgs& a, cudaStream_t stream) {
 }
 }  // namespace
 
+bool gemm_can_fuse_ln(const GemmArgs& a) {
+  static int on = -1;  // HN_GEMM_LN=0 keeps the separate LayerNorm kernel (A/B measurements)
+  if (on < 0) {
+    const char* e = getenv("HN_GEMM_LN");
+    on = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  const bool resid = a.epi == EPI_RES || a.epi == EPI_RES_LEAKY;
+  if (!(on && resid && a.ldo == a.N && a.N <= 512 && a.N % 4 == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0))
+    return false;
+  // every CTA must hold exactly one 128 x 64 tile (they wait for each other): tile count <= SM count, no clusters
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    return false;
+  const long mt = (a.M + BM - 1) / BM;
+  return mt * ((a.N + 63) / 64) <= sms && a.M < 16384 && getenv("HN_GEMM_BN") == nullptr && getenv("HN_GEMM_BK") == nullptr;
+}
+
 int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   HN_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "gemm: empty problem");
   HN_REQUIRE(a.lda % 8 == 0 && a.ldb % 8 == 0, "gemm: operand pitches must be multiples of 8 elements");
@@ -366,6 +458,15 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
              "gemm: operands must be 16-byte aligned");
   if (a.epi == EPI_GATE_F16) HN_REQUIRE(a.N % 2 == 0, "gemm: gated epilogue needs even N");
   HN_REQUIRE(a.terms >= 1 && a.terms <= 3, "gemm: terms must be 1, 2 or 3");
+  if (a.ln_out != nullptr) {
+    const bool resid = a.epi == EPI_RES || a.epi == EPI_RES_LEAKY;
+    const bool aligned = (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.ln_out) & 7) == 0 &&
+                         a.ln_ld % 4 == 0 && a.ln_seg % 4 == 0 && (reinterpret_cast<uintptr_t>(a.ln_gamma) & 15) == 0 &&
+                         (reinterpret_cast<uintptr_t>(a.ln_beta) & 15) == 0;
+    HN_REQUIRE(resid && a.ldo == a.N && a.N <= 512 && a.N % 4 == 0 && aligned && a.ln_counters != nullptr &&
+                   a.ln_epoch >= 1 && gemm_can_fuse_ln(a),
+               "gemm: fused LayerNorm needs a residual epilogue over complete rows of <= 512 columns (see gemm_can_fuse_ln)");
+  }
   if (a.terms >= 2) HN_REQUIRE(a.b_seg % 64 == 0 && a.b_seg >= a.K, "gemm: B lo segment must start at a multiple of 64 >= K");
   if (a.terms == 3) HN_REQUIRE(a.a_seg % 64 == 0 && a.a_seg >= a.K, "gemm: A lo segment must start at a multiple of 64 >= K");
   // widest tile that still gives (nearly) every SM one
