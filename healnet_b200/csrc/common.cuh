@@ -41,14 +41,19 @@ const char* get_error();
 bool pdl_enabled();
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kc(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-                             unsigned cluster_x, Args... args) {
+                             unsigned cluster_x, bool cooperative, Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[3];
   int n = 0;
+  if (cooperative) {  // gang-scheduled grid: CTAs that wait for each other can never be starved by another stream
+    attr[n].id = cudaLaunchAttributeCooperative;
+    attr[n].val.cooperative = 1;
+    ++n;
+  }
   if (pdl_enabled()) {
     attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[n].val.programmaticStreamSerializationAllowed = 1;
@@ -68,7 +73,7 @@ inline cudaError_t launch_kc(void (*kernel)(KArgs...), dim3 grid, dim3 block, si
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                             Args... args) {
-  return launch_kc(kernel, grid, block, smem, stream, 1u, args...);
+  return launch_kc(kernel, grid, block, smem, stream, 1u, false, args...);
 }
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }

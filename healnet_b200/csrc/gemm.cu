@@ -428,8 +428,10 @@ int launch_t(const GemmArgs& a, cudaStream_t stream) {
   const long n_super = static_cast<long>(tiles_m) * tiles_n / CN;  // the caller guarantees divisibility
   const long max_clusters = sms / CN;
   const unsigned grid = static_cast<unsigned>((n_super < max_clusters ? n_super : max_clusters) * CN);
+  // the fused-LayerNorm epilogue makes the CTAs of the grid wait for each other: launch it cooperatively so that the
+  // whole grid is resident whatever else shares the GPU
   HN_CHECK_CUDA(launch_kc(gemm_kernel<BN, BK, CN, SHARE_A>, dim3(grid), dim3((2 + EPI_WARPS) * 32), smem, stream,
-                          static_cast<unsigned>(CN), tmA, tmB, p));
+                          static_cast<unsigned>(CN), a.ln_out != nullptr, tmA, tmB, p));
   return 0;
 }
 }  // namespace

@@ -513,16 +513,30 @@ __global__ void __launch_bounds__(256) combine_generic_kernel(const float* __res
   float a[4] = {0.f, 0.f, 0.f, 0.f};
   float den = 0.f;
   const int nv = hp / 32;
-  for (int s = 0; s < nsplit; ++s) {
-    const long base = part_row(pp, b, s, nsplit, H, h, L, l);
-    const float* pml = pp.world ? pp.ml[s] : part_ml;
-    const float* pac = pp.world ? pp.acc[s] : part_acc;
-    const float m = pml[base * 2], ls = pml[base * 2 + 1];
-    const float w = (m == -INFINITY) ? 0.f : exp2f(m - M);
+  // four splits per step with all their loads issued before the first use: the merge is a chain of L2 round trips
+  // otherwise (one warp per row, nothing else to hide them)
+  for (int s0 = 0; s0 < nsplit; s0 += 4) {
+    float m4[4], l4[4], v4[4][4];
 #pragma unroll
-    for (int v = 0; v < 4; ++v)
-      if (v < nv) a[v] += w * pac[base * hp + v * 32 + lane];
-    den += w * ls;
+    for (int u = 0; u < 4; ++u) {
+      const int s = s0 + u < nsplit ? s0 + u : nsplit - 1;
+      const long base = part_row(pp, b, s, nsplit, H, h, L, l);
+      const float* pml = pp.world ? pp.ml[s] : part_ml;
+      const float* pac = pp.world ? pp.acc[s] : part_acc;
+      m4[u] = pml[base * 2];
+      l4[u] = pml[base * 2 + 1];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) v4[u][v] = v < nv ? pac[base * hp + v * 32 + lane] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {  // fixed split order: the sum is the same whatever the unrolling
+      if (s0 + u < nsplit) {
+        const float w = (m4[u] == -INFINITY) ? 0.f : exp2f(m4[u] - M);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) a[v] += w * v4[u][v];
+        den += w * l4[u];
+      }
+    }
   }
   // small-context partials keep their denominator in accumulator column den_col (the column that met z's 1.0);
   // columns from there on are padding and leave as zeros
