@@ -50,6 +50,25 @@ WORKLOADS = {
 METRIC = "HealNet forward samples/sec (3-modality, latent 512x512)"
 
 
+def flops_per_sample(kwargs, shapes) -> float:
+    """As-written algorithmic FLOPs of one forward for one sample: K/V projection, Q, QK^T + PV,
+    output projection, cross feed-forward, and the latent self-attention + feed-forward after every modality.
+    `shapes` are the per-sample input shapes (*axes, channels); hyper-parameters default as HealNet.__init__ does."""
+    g = lambda k, dflt: kwargs.get(k, dflt)
+    L, D, depth = g("l_c", 128), g("l_d", 128), g("depth", 3)
+    I = g("x_heads", 8) * g("cross_dim_head", 64)
+    lI = g("l_heads", 8) * g("latent_dim_head", 64)
+    spc = 1 if g("self_per_cross_attn", 1) > 0 else 0
+    feats = 2 * g("num_freq_bands", 2) + 1 if g("fourier_encode_data", True) else 0
+    tot = 0.0
+    for m, s in enumerate(shapes):
+        n = _prod(s[:-1])
+        c = kwargs["channel_dims"][m] + kwargs["num_spatial_axes"][m] * feats
+        tot += 4 * n * c * I + 2 * L * D * I + 4 * L * n * I + 2 * L * I * D + 24 * L * D * D
+        tot += spc * (6 * L * D * lI + 4 * L * L * lI + 2 * L * lI * D + 24 * L * D * D)
+    return depth * tot + 2 * D * kwargs["out_dims"]
+
+
 def load_traffic():
     """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/), or None."""
     p = os.path.join(ROOT, "profiles", "r1_final_attn_small_kernel_summary.json")
@@ -257,7 +276,6 @@ def run_gpu_arm(args):
     import torch.distributed as dist
     from healnet_b200 import HealNet
     from healnet_b200.distributed import gather_rows
-    from oracle import healnet_oracle as O
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -337,7 +355,6 @@ def run_gpu_arm(args):
         e2e_s = float(t.item())
 
     if rank == 0:
-        cfg = O.OracleConfig(**{k: v for k, v in kwargs.items() if k in O.OracleConfig.__dataclass_fields__})
         ms_per_step = ms / args.steps
         value = global_batch / (ms_per_step * 1e-3)
         k_ms = kt["ms"] / max(kt["launches"], 1)
@@ -351,7 +368,8 @@ def run_gpu_arm(args):
             vs_baseline=None, dtype="f32" if io_dtype == torch.float32 else "bf16 I/O, fp16-split / fp32 arithmetic",
             data="synthetic",
             config=dict(workload=args.workload, batch_per_gpu=batch, global_batch=global_batch,
-                        shapes=[list(s) for s in shapes], depth=cfg.depth, l_c=cfg.l_c, l_d=cfg.l_d,
+                        shapes=[list(s) for s in shapes], depth=kwargs.get("depth", 3), l_c=kwargs["l_c"],
+                        l_d=kwargs["l_d"],
                         parallelism=(f"token-axis sharded x{world} (partials merged over NVLink peer memory)"
                                      if token_shard else f"batch-sharded x{world}"), operands="fp16 (split hi/lo on the latent side), fp32 accumulate",
                         l2="per-step working set (standardised context rows + inputs) exceeds the 126 MB L2"),
@@ -368,8 +386,8 @@ def run_gpu_arm(args):
                           kernel_share_of_step=kt["ms"] / ms_per_step if ms_per_step > 0 else None,
                           flops="executed (reassociated small-context form, padded tiles)",
                           exp_per_s=exp_rate, exp_frac_of_mufu=exp_rate / (148 * 16 * sm_hz)),
-            algorithmic=dict(tflop_per_sample=O.flops_per_sample(cfg, [s[:-1] for s in shapes]) / 1e12,
-                             tflops_as_written=value * O.flops_per_sample(cfg, [s[:-1] for s in shapes]) / 1e12),
+            algorithmic=dict(tflop_per_sample=flops_per_sample(kwargs, shapes) / 1e12,
+                             tflops_as_written=value * flops_per_sample(kwargs, shapes) / 1e12),
         )
         if world == 1 and not args.no_cpu:
             threads = len(os.sched_getaffinity(0))
