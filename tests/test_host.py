@@ -126,6 +126,40 @@ def test_hn_create_validation_and_workspace_sizing():
         assert len(lib.hn_last_error()) > 0
 
 
+def test_token_sharding_entry_points_validate_on_the_host():
+    """hn_exchange_bytes / hn_workspace_bytes_split / hn_set_exchange are pure host logic: sizes scale as documented
+    and bad arguments are refused with a message (no GPU needed)."""
+    lib = healnet_b200.load_library()
+    h = ctypes.c_void_p()
+    d = _desc()
+    assert lib.hn_create(ctypes.byref(d), ctypes.byref(h)) == 0
+    b1, b4 = lib.hn_exchange_bytes(h, 1), lib.hn_exchange_bytes(h, 4)
+    assert 256 < b1 < b4 and (b4 - 256) % 512 == 0            # header + two 256-byte-aligned slots
+    assert lib.hn_exchange_bytes(h, 0) == 0
+    sizes = (ctypes.c_int * (_lib.HN_MAX_MODALITIES * _lib.HN_MAX_AXES))()
+    sizes[0] = 1
+    sizes[4], sizes[5] = 200, 300                              # 60 000 tokens: streaming path, shardable
+    full = lib.hn_workspace_bytes(h, 4, sizes)
+    tc = (ctypes.c_long * _lib.HN_MAX_MODALITIES)()
+    tc[1] = 60000 // 8
+    part = lib.hn_workspace_bytes_split(h, 4, sizes, tc)
+    assert 0 < part < full                                     # an eighth of the context rows, same latent side
+    tc[1] = 60000                                              # "all tokens" = replicated: same plan as the full call
+    assert abs(lib.hn_workspace_bytes_split(h, 4, sizes, tc) - full) <= 4096
+    sizes[4], sizes[5] = 20, 30                                # 600 tokens: short axes are replicated, never sharded
+    tc[1] = 100
+    assert lib.hn_workspace_bytes_split(h, 4, sizes, tc) == 0
+    assert b"replicated" in lib.hn_last_error()
+    bufs = (ctypes.c_void_p * 9)(*[256 * (i + 1) for i in range(9)])
+    assert lib.hn_set_exchange(h, 0, 9, bufs, b4) != 0         # one node: at most 8 ranks
+    assert lib.hn_set_exchange(h, 3, 2, bufs, b4) != 0         # rank outside the world
+    bufs[1] = 257
+    assert lib.hn_set_exchange(h, 0, 2, bufs, b4) != 0         # unaligned peer buffer
+    assert b"aligned" in lib.hn_last_error()
+    assert lib.hn_set_exchange(h, 0, 1, None, 0) == 0          # world 1: sharding off
+    assert lib.hn_destroy(h) == 0
+
+
 def test_attention_split_heuristic_covers_the_chip():
     lib = healnet_b200.load_library()
     # cfg 1 volume modality: 4 samples x 8 heads x 4 latent tiles = 128 base CTAs -> must split the token axis
