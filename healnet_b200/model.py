@@ -273,6 +273,9 @@ class HealNet(nn.Module):
         # healnet.py:420). Off by default: (b*h, L, N) fp32 is 9.87 GB per sample and layer at the README shapes.
         self.export_attention_weights = False
         self.export_attention_max_bytes = 16 << 30
+        # serving loops: leave the result on the compute device even when the inputs came from the host, so the caller
+        # can read it back asynchronously (pinned buffer + event) and enqueue the next batch meanwhile
+        self.keep_output_on_device = False
         self.last_launch_count = 0
         self._warned = set()
 
@@ -487,6 +490,8 @@ class HealNet(nn.Module):
                                dev, stream, tok_begin, tok_count)
         if ret_dtype is not None and not ret_dtype.is_floating_point:
             ret_dtype = torch.float32
+        if self.keep_output_on_device:
+            return out.to(dtype=ret_dtype)
         return out.to(device=ret_dev, dtype=ret_dtype)
 
     def _stage_input(self, data: torch.Tensor, dev: torch.device):
