@@ -588,6 +588,10 @@ class HealNet(nn.Module):
         self._token_shard = (rank, world, max(int(min_tokens), 2049 * 1))
         self._exchange_group, self._exchange_max_batch = group, int(max_batch)
 
+    def disable_token_sharding(self) -> None:
+        """Back to the replicated forward (the exchange buffers stay mapped until the module is released)."""
+        self._token_shard = None
+
     def _ensure_exchange(self, lib, batch: int) -> None:
         """Allocates this rank's exchange buffer, swaps CUDA IPC handles with the peers (one all-gather of 64 bytes
         per rank on the host side) and registers the peer-mapped pointers with the native handle."""

@@ -68,7 +68,7 @@ def main():
             model.enable_token_sharding(min_tokens=2049)
             got_lat = model(list(xs), mask=mask, return_embeddings=True)
             got_log = model(list(xs), mask=mask)
-            model.enable_token_sharding(group=None, min_tokens=1 << 40)   # back to replicated
+            model.disable_token_sharding()
         torch.cuda.synchronize()
         err_lat = (got_lat - ref_lat).abs().max().item()
         err_log = (got_log - ref_log).abs().max().item()
