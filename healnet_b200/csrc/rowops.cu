@@ -323,6 +323,82 @@ __global__ void __launch_bounds__(256) build_z_large_kernel(const float* __restr
   for (int c = lane; c < seg; c += 32) store_split(zr, c, seg, lo_seg, c < C ? (feat(c) - mean) * rstd : 0.f);
 }
 
+// Wide-context fast path (WSI patch features: c_raw a multiple of 4, up to 1024 raw channels, at most 32 positional
+// features): the row is read ONCE with float4 loads and kept in registers for the two-pass statistics (the generic
+// kernel above walks it three times through scalar loads), and leaves as 8-byte stores. NQ = float4 per lane.
+template <int NQ>
+__global__ void __launch_bounds__(256) build_z_large_fast_kernel(const float* __restrict__ raw, __half* __restrict__ z,
+                                                                 int ldz, int seg, int lo_seg, long tokens_total, long N,
+                                                                 int c_raw, AxisInfo ax, int F,
+                                                                 const float* __restrict__ tab, long tok0) {
+  HN_PDL_LAUNCH();
+  HN_PDL_WAIT();
+  const int lane = threadIdx.x & 31;
+  const long t = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= tokens_total) return;
+  const int n_feat = F * ax.n_axes;
+  const int C = c_raw + n_feat;
+  const float4* r4 = reinterpret_cast<const float4*>(raw + t * c_raw);
+  float4 v[NQ];
+  float s = 0.f;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const int c = (q * 32 + lane) * 4;
+    v[q] = c < c_raw ? __ldg(r4 + q * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+    s += v[q].x + v[q].y + v[q].z + v[q].w;
+  }
+  // positional features: lane k < n_feat owns feature k (axis k / F, entry k % F)
+  float pf = 0.f;
+  if (lane < n_feat) {
+    unsigned rem = static_cast<unsigned>(t % N + tok0);
+    const int a_own = lane / F;
+    int row = 0;
+    for (int a = ax.n_axes - 1; a >= 0; --a) {
+      const unsigned sz = static_cast<unsigned>(ax.size[a]);
+      const unsigned qd = rem / sz;
+      if (a == a_own) row = ax.off[a] + static_cast<int>(rem - qd * sz);
+      rem = qd;
+    }
+    pf = __ldg(tab + static_cast<long>(row) * F + (lane - a_own * F));
+    s += pf;
+  }
+  const float mean = warp_sum(s) / C;
+  float qq = 0.f;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    if ((q * 32 + lane) * 4 < c_raw) {
+      const float d0 = v[q].x - mean, d1 = v[q].y - mean, d2 = v[q].z - mean, d3 = v[q].w - mean;
+      qq += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+    }
+  }
+  if (lane < n_feat) qq += (pf - mean) * (pf - mean);
+  const float rstd = rsqrtf(warp_sum(qq) / C + LN_EPS);
+  __half* zr = z + t * ldz;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const int c = (q * 32 + lane) * 4;
+    if (c < c_raw) {
+      uint2 hi, lo;
+      const float o0 = (v[q].x - mean) * rstd, o1 = (v[q].y - mean) * rstd, o2 = (v[q].z - mean) * rstd,
+                  o3 = (v[q].w - mean) * rstd;
+      const __half2 h01 = __floats2half2_rn(o0, o1), h23 = __floats2half2_rn(o2, o3);
+      hi.x = *reinterpret_cast<const uint32_t*>(&h01);
+      hi.y = *reinterpret_cast<const uint32_t*>(&h23);
+      *reinterpret_cast<uint2*>(zr + c) = hi;
+      if (lo_seg > 0) {
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn(o0 - f01.x, o1 - f01.y), l23 = __floats2half2_rn(o2 - f23.x, o3 - f23.y);
+        lo.x = *reinterpret_cast<const uint32_t*>(&l01);
+        lo.y = *reinterpret_cast<const uint32_t*>(&l23);
+        *reinterpret_cast<uint2*>(zr + lo_seg + c) = lo;
+      }
+    }
+  }
+  // positional features and the zero pad [C, seg)
+  for (int c = c_raw + lane; c < seg; c += 32)  // (feature k sits in lane k: only the first trip holds features)
+    store_split(zr, c, seg, lo_seg, (c < C) ? (pf - mean) * rstd : 0.f);
+}
+
 // ------------------------------------------------------------------ head: mean_L -> LN -> Linear
 // stage 1: pooled[b][d] = mean_l x[b][l][d]; block = (sample, 32 columns), 8 warps stride the rows
 __global__ void __launch_bounds__(256) pool_kernel(const float* __restrict__ x, int L, int D,
@@ -780,8 +856,22 @@ int launch_build_z_large(const float* raw, __half* z, int ldz, int lo_seg, int b
   AxisInfo ax = make_axis(axis_sizes, n_axes);
   const long total = static_cast<long>(batch) * N;
   const unsigned grid = static_cast<unsigned>((total + 7) / 8);
-  HN_CHECK_CUDA(launch_k(build_z_large_kernel, dim3(grid), dim3(256), 0, stream, raw, z, ldz, seg, lo_seg, total, N, c_raw,
-                         ax, F, tab, tok0));
+  const int n_feat = F * n_axes;
+  const bool fast = c_raw % 4 == 0 && c_raw >= 4 && c_raw <= 1024 && n_feat <= 32 && N < (1L << 31) &&
+                    (reinterpret_cast<uintptr_t>(raw) & 15) == 0 && ldz % 4 == 0 && lo_seg % 4 == 0 &&
+                    (reinterpret_cast<uintptr_t>(z) & 7) == 0;
+  if (fast && c_raw <= 256)
+    HN_CHECK_CUDA(launch_k(build_z_large_fast_kernel<2>, dim3(grid), dim3(256), 0, stream, raw, z, ldz, seg, lo_seg, total,
+                           N, c_raw, ax, F, tab, tok0));
+  else if (fast && c_raw <= 512)
+    HN_CHECK_CUDA(launch_k(build_z_large_fast_kernel<4>, dim3(grid), dim3(256), 0, stream, raw, z, ldz, seg, lo_seg, total,
+                           N, c_raw, ax, F, tab, tok0));
+  else if (fast)
+    HN_CHECK_CUDA(launch_k(build_z_large_fast_kernel<8>, dim3(grid), dim3(256), 0, stream, raw, z, ldz, seg, lo_seg, total,
+                           N, c_raw, ax, F, tab, tok0));
+  else
+    HN_CHECK_CUDA(launch_k(build_z_large_kernel, dim3(grid), dim3(256), 0, stream, raw, z, ldz, seg, lo_seg, total, N,
+                           c_raw, ax, F, tab, tok0));
   HN_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
