@@ -107,3 +107,16 @@ def test_flop_model_matches_survey():
     assert abs(O.flops_per_sample(cfg, shapes) / 1e12 - 2.200) < 2e-3
     cfg.l_c = cfg.l_d = 128
     assert abs(O.flops_per_sample(cfg, shapes) / 1e12 - 0.586) < 2e-3
+
+
+def test_bench_flop_model_agrees_with_the_oracle_and_survey():
+    """bench.py's GPU arm carries its own work model (it does not import the oracle): same numbers for every
+    BASELINE configuration, and the SURVEY.md section 8d values (cfg 2 0.0573, cfg 3 6.369, cfg 4 0.1162, cfg 5 0.4401)."""
+    import bench
+    want = {"cfg1": 2.200, "cfg2": 0.0573, "cfg3": 6.369, "cfg4": 0.1162, "cfg5": 0.4401}
+    for name, (kw, shapes, _) in bench.WORKLOADS.items():
+        cfg = O.OracleConfig(**{k: v for k, v in kw.items() if k in O.OracleConfig.__dataclass_fields__})
+        got = bench.flops_per_sample(kw, shapes)
+        assert abs(got - O.flops_per_sample(cfg, [s[:-1] for s in shapes])) < 1.0
+        if name in want:
+            assert abs(got / 1e12 - want[name]) < 2e-3 * max(1.0, want[name]), name
