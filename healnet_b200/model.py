@@ -585,7 +585,8 @@ class HealNet(nn.Module):
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         if world > 8:
             raise ValueError("token sharding covers the GPUs of one node (<= 8 ranks)")
-        self._token_shard = (rank, world, max(int(min_tokens), 2049 * 1))
+        # axes of up to 2048 tokens take the precise, replicated path in the library: never shard those
+        self._token_shard = (rank, world, max(int(min_tokens), 2049))
         self._exchange_group, self._exchange_max_batch = group, int(max_batch)
 
     def disable_token_sharding(self) -> None:
