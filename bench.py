@@ -2,7 +2,7 @@
 """bench.py — HealNet fusion forward throughput (samples/s) on B200, BASELINE.json's metric and config.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]                 this repo's CUDA path
-  python bench.py --impl reference [--gpus N --steps K --warmup W]    the reference's CPU forward (oracle port)
+  python bench.py --impl reference [--gpus N --steps K --warmup W]    the reference's own CPU forward (baseline/_ref)
   torchrun ... bench.py --gpus N ...                                   one rank per GPU, batch sharded (weak scaling)
 
 Workload (config.workload = "cfg1"): BASELINE.json configs[0] — README synthetic 3-modality example
@@ -12,7 +12,15 @@ A "step" is one forward over one batch of synthetic inputs (torch.rand, seed 0; 
 Prints ONE JSON line (see the task contract): `value` = samples/s with inputs resident in HBM; `e2e` = the same
 through the public module call with pinned HOST inputs (H2D + D2H inside the timed region); `roofline` for the
 dominant kernel (the volume modality's streaming cross-attention), timed live with CUDA events on its launch
-stream through the library's measurement hook; `cpu_baseline` = the oracle port timed on this box's host cores.
+stream through the library's measurement hook; `cpu_baseline` = the reference algorithm on this box's host cores, one
+WHOLE sample (no scaling), whose logits are also compared with the CUDA path's (`parity`).
+
+Reference arm: the UNMODIFIED reference module (healnet/models/healnet.py, copied by __graft_entry__.build() to the
+git-ignored baseline/_ref/healnet.py and loaded by path) on all host cores, one whole sample per counted step
+(the path is per-sample; cfg 1 needs ~54 GB per sample as written). When K such steps would not fit the time budget
+(HN_REF_BUDGET_S, default 300 s) the unmodified module is timed once (reported as `reference_unmodified`) and the K
+counted steps run the oracle port of the same algorithm two heads at a time (kind "port"), whose output on that
+sample is checked against the unmodified module's.
 """
 from __future__ import annotations
 
@@ -71,11 +79,12 @@ def flops_per_sample(kwargs, shapes) -> float:
 
 def load_traffic():
     """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/), or None."""
-    p = os.path.join(ROOT, "profiles", "r1_final_attn_small_kernel_summary.json")
-    try:
-        return float(json.load(open(p))["dram_bytes_per_launch"])
-    except (OSError, KeyError, ValueError):
-        return None
+    for name in ("r2_attn_small_kernel_summary.json", "r1_final_attn_small_kernel_summary.json"):
+        try:
+            return float(json.load(open(os.path.join(ROOT, "profiles", name)))["dram_bytes_per_launch"])
+        except (OSError, KeyError, ValueError):
+            continue
+    return None
 
 
 def load_peaks():
@@ -137,51 +146,66 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_forward_timed(kwargs, shapes, budget_s: float, threads: int, repeats: int = 1):
-    """Times the oracle port (reference algorithm: materialised K/V and attention matrices, torch CPU ops) on a
-    BOUNDED sample: one sample whose volume / image token axes are cut to the leading `frac` of their first
-    spatial axis so that one forward fits `budget_s`; the measured time is scaled to a full sample by the ratio of
-    the as-written algorithmic FLOPs (the cost is linear in the token count)."""
+REF_FILE = os.path.join(ROOT, "baseline", "_ref", "healnet.py")
+
+
+def load_reference_module():
+    """The unmodified reference model file (healnet/models/healnet.py; needs torch + einops only), loaded by path from
+    the git-ignored copy __graft_entry__.build() makes. None when it is not there."""
+    if not os.path.exists(REF_FILE):
+        return None
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("healnet_reference_model", REF_FILE)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _mem_available_gb() -> float:
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) / 2 ** 20
+    except OSError:
+        pass
+    return 0.0
+
+
+def _oracle_cfg(kwargs):
+    from oracle import healnet_oracle as O
+    return O.OracleConfig(**{k: v for k, v in kwargs.items() if k in O.OracleConfig.__dataclass_fields__})
+
+
+def cpu_port_sample(sd, kwargs, xs, threads: int):
+    """One forward of the oracle port (reference algorithm: materialised K/V and attention matrices, torch CPU ops, two
+    heads at a time) on whole, unscaled inputs -> (seconds, logits)."""
     import torch
     from oracle import healnet_oracle as O
     torch.set_num_threads(threads)
-    cfg = O.OracleConfig(**{k: v for k, v in kwargs.items() if k in O.OracleConfig.__dataclass_fields__})
-    torch.manual_seed(0)
-    from healnet_b200 import HealNet
-    sd = {k: v.detach() for k, v in HealNet(**kwargs).state_dict().items()}
-    full_flops = O.flops_per_sample(cfg, [s[:-1] for s in shapes])
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        out = O.forward(sd, _oracle_cfg(kwargs), [t.float() for t in xs], head_chunk=2)
+    return time.perf_counter() - t0, out
 
-    def run(sample_shapes):
-        g = torch.Generator().manual_seed(0)
-        xs = [torch.rand((1,) + tuple(s), generator=g) for s in sample_shapes]
-        t0 = time.perf_counter()
-        with torch.no_grad():
-            out = O.forward(sd, cfg, xs, head_chunk=2)
-        return time.perf_counter() - t0, out
 
-    # calibrate on a thin slab of the largest modality, then pick the largest slab that fits the budget
-    big = max(range(len(shapes)), key=lambda i: _prod(shapes[i][:-1]))
-    ax0 = shapes[big][0]
-    probe = [tuple(s) for s in shapes]
-    probe[big] = (1,) + tuple(shapes[big][1:])
-    t_probe, _ = run(probe)
-    f_probe = O.flops_per_sample(cfg, [s[:-1] for s in probe])
-    rate = f_probe / t_probe
-    keep = ax0
-    while keep > 1 and O.flops_per_sample(cfg, [s[:-1] for s in _cut(shapes, big, keep)]) / rate > budget_s:
-        keep -= 1
-    sample = _cut(shapes, big, keep)
-    f_sample = O.flops_per_sample(cfg, [s[:-1] for s in sample])
-    times = []
-    for _ in range(repeats):
-        t, out = run(sample)
-        times.append(t)
-    t_step = statistics.median(times)
-    t_full = t_step * full_flops / f_sample
-    desc = (f"1 sample, depth {cfg.depth}, modality {big} cut to {keep}/{ax0} of its first axis "
-            f"({f_sample / full_flops * 100:.1f}% of a full sample's FLOPs), time scaled by the FLOP ratio; "
-            f"oracle port, head_chunk=2, fp32")
-    return dict(samples_per_s=1.0 / t_full, step_s=t_step, sample=desc, frac=f_sample / full_flops, times=times)
+def cpu_reference_sample(model, mod, xs, threads: int):
+    """One forward of the UNMODIFIED reference module on whole inputs -> (seconds, logits). Hygiene of BASELINE.md
+    section 4: fresh list per call (the reference mutates it), attn_weights sentinel (the reference swallows every
+    exception inside its modality loop), matrices released afterwards."""
+    import torch
+    torch.set_num_threads(threads)
+    atts = [m for m in model.modules() if isinstance(m, mod.Attention)]
+    for a in atts:
+        a.attn_weights = None
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        out = model([t.clone() for t in xs])
+    dt = time.perf_counter() - t0
+    if any(a.attn_weights is None for a in atts):
+        raise RuntimeError("reference forward skipped an attention module (an exception was swallowed, e.g. out of memory)")
+    for a in atts:
+        a.attn_weights = None
+    return dt, out
 
 
 def _prod(t):
@@ -189,12 +213,6 @@ def _prod(t):
     for v in t:
         p *= v
     return p
-
-
-def _cut(shapes, big, keep):
-    out = [tuple(s) for s in shapes]
-    out[big] = (keep,) + tuple(shapes[big][1:])
-    return out
 
 
 def run_reference_gpu_eager(args):
@@ -246,31 +264,109 @@ def run_reference_arm(args):
         return 0
     if args.ref_device == "cuda":
         return run_reference_gpu_eager(args)
+    import torch
+    from healnet_b200 import HealNet
     kwargs, shapes, per_gpu = WORKLOADS[args.workload]
     threads = len(os.sched_getaffinity(0))
-    total = max(1, args.steps + args.warmup)
-    budget = max(2.0, min(30.0, 150.0 / total))
-    import torch
-    times, res = [], None
-    for i in range(total):
-        res = cpu_forward_timed(kwargs, shapes, budget, threads)
-        if i >= args.warmup:
-            times.append(res["step_s"] / res["frac"])
-    t_full = statistics.median(times) if times else res["step_s"] / res["frac"]
-    v = 1.0 / t_full
-    line = dict(metric=METRIC, value=v, unit="samples/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=t_full * 1e3 * per_gpu, higher_is_better=True, scaling="weak", vs_baseline=None,
+    torch.set_num_threads(threads)
+    budget = float(os.environ.get("HN_REF_BUDGET_S", "300"))
+    g = torch.Generator().manual_seed(0)
+    xs = [torch.rand((1,) + tuple(s), generator=g) for s in shapes]   # ONE whole sample per counted step
+    mod = load_reference_module()
+    note, unmodified = None, None
+    kind = "port"
+    ref_model = None
+    # as written the reference keeps (b*h, L, N) fp32 attention matrices alive: ~6.6 x the largest one per sample
+    need_gb = 6.6 * 4 * kwargs.get("x_heads", 8) * kwargs["l_c"] * max(_prod(s[:-1]) for s in shapes) / 2 ** 30 + 4
+    if mod is None:
+        note = "baseline/_ref/healnet.py absent (run __graft_entry__.build() where /root/reference exists): oracle port"
+    elif _mem_available_gb() < need_gb:
+        note = f"unmodified reference needs ~{need_gb:.0f} GB per sample, {_mem_available_gb():.0f} GB available: oracle port"
+    else:
+        torch.manual_seed(0)
+        ref_model = mod.HealNet(**kwargs).eval()
+        t_ref, out_ref = cpu_reference_sample(ref_model, mod, xs, threads)   # also serves as the warm-up
+        unmodified = dict(s_per_sample=t_ref, samples_per_s=1.0 / t_ref)
+        if t_ref * args.steps <= budget:
+            kind = "reference"
+        else:
+            note = (f"unmodified reference: {t_ref:.1f} s per sample, {args.steps} steps would take "
+                    f"{t_ref * args.steps:.0f} s > budget {budget:.0f} s: counted steps run the oracle port")
+    if kind == "reference":
+        step = lambda: cpu_reference_sample(ref_model, mod, xs, threads)
+    else:
+        if ref_model is not None:
+            sd = {k: v.detach().clone() for k, v in ref_model.state_dict().items()}
+        else:
+            torch.manual_seed(0)
+            sd = {k: v.detach() for k, v in HealNet(**kwargs).state_dict().items()}
+        ref_model = None
+        step = lambda: cpu_port_sample(sd, kwargs, xs, threads)
+        t_w, out_port = step()   # warm-up step of the port; doubles as its check against the unmodified module
+        if unmodified is not None:
+            unmodified["port_max_abs_diff"] = float((out_port - out_ref).abs().max())
+    steps = args.steps
+    times = []
+    t_begin = time.perf_counter()
+    for i in range(steps):
+        t, _ = step()
+        times.append(t)
+        if i + 1 < steps and (time.perf_counter() - t_begin) / (i + 1) * steps > 2.0 * budget:
+            steps = i + 1   # far over budget (very few cores): stop here and say so
+            note = (note + "; " if note else "") + f"stopped after {steps} of {args.steps} steps (time budget)"
+            break
+    total = sum(times)
+    v = steps / total
+    sample = (f"{steps} counted steps of 1 whole sample each (depth {kwargs.get('depth', 3)}, all modalities at full "
+              f"size, no scaling), fp32, {threads} threads; "
+              + ("unmodified healnet/models/healnet.py" if kind == "reference" else "oracle port, head_chunk=2"))
+    line = dict(metric=METRIC, value=v, unit="samples/s", n_gpus=args.gpus, steps=steps, warmup=1,
+                ms_per_step=total / steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f32", data="synthetic", impl="reference",
-                config=dict(workload=args.workload, batch_per_gpu=per_gpu, shapes=[list(s) for s in shapes],
-                            **{k: kwargs[k] for k in ("l_c", "l_d")}),
-                cpu_baseline=dict(value=v, unit="samples/s", cores=threads, kind="port", sample=res["sample"]),
+                config=_config(args.workload, kwargs, shapes, per_gpu, per_gpu, "cpu: one sample per counted step"),
+                cpu_baseline=dict(value=v, unit="samples/s", cores=threads, kind=kind, sample=sample),
                 e2e=dict(value=v, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
-                gpu_launches=0)
+                gpu_launches=0, samples_per_step=1, step_times_s=[round(t, 3) for t in times])
+    if unmodified is not None:
+        line["reference_unmodified"] = unmodified
+    if note:
+        line["note"] = note
     print(json.dumps(line), flush=True)
     return 0
 
 
+def _config(workload, kwargs, shapes, batch, global_batch, parallelism):
+    """config object shared by both arms (same keys, same workload values)."""
+    return dict(workload=workload, batch_per_gpu=batch, global_batch=global_batch, shapes=[list(s) for s in shapes],
+                depth=kwargs.get("depth", 3), l_c=kwargs["l_c"], l_d=kwargs["l_d"], parallelism=parallelism)
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
+def measure_token_sharded(model, shapes, batch, io_dtype, dev, rank, world, timed, ms_unsharded):
+    """Multi-GPU runs: the token-sharded forward (hn_forward_split) of ONE batch (rank 0's inputs on
+    every rank), timed like the main loop and checked against the unsharded forward of the same batch on this GPU
+    (itself oracle-checked by tests/test_gpu_fullsize.py) — so the driver's scaling record carries it."""
+    import torch
+    import torch.distributed as dist
+    g = torch.Generator().manual_seed(0)
+    xs = [torch.rand((batch,) + tuple(s), generator=g).to(io_dtype).to(dev) for s in shapes]
+    want = model(list(xs)).float()
+    model.enable_token_sharding(min_tokens=8192, max_batch=batch)
+    try:
+        for _ in range(3):
+            got = model(list(xs))
+        ms, got = timed(lambda: model(list(xs)), 10)
+        err = float((got.float() - want).abs().max())
+        model.check_token_sharding()
+    finally:
+        model.disable_token_sharding()
+    t = torch.tensor([err], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return dict(ms=ms / 10, ms_unsharded_1gpu=ms_unsharded, speedup=ms_unsharded / (ms / 10), max_err_vs_unsharded=float(t.item()),
+                batch=batch, ranks=world, what="one batch, every long token axis cut across the ranks, partials merged "
+                                               "over CUDA-IPC peer memory (no NCCL on the data path)")
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -352,10 +448,11 @@ def run_gpu_arm(args):
     for _ in range(max(args.warmup, 1)):
         step_resident()
     model.enable_kernel_timing(True)
-    big = max(range(len(shapes)), key=lambda i: _prod(shapes[i][:-1]))
     with ClockSampler(local_rank) as clocks:
         ms, out = timed(step_resident, args.steps)
-        kt = model.read_kernel_timing(big)
+        # the measurement hook brackets, per modality, the streaming cross-attention kernel (kind 0), the K/V
+        # projection GEMM of the wide-context path (kind 1) and the context-row build (kind 2) of the LAST forward
+        kts = {(k, m): model.read_kernel_timing(m, k) for m in range(len(shapes)) for k in (0, 1, 2)}
     model.enable_kernel_timing(False)
     launches = model.last_launch_count * args.steps
     run_e2e(2)
@@ -370,47 +467,86 @@ def run_gpu_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
 
+    # token-sharded forward of rank 0's batch on every multi-GPU run: checked against the unsharded result
+    token_sharded = None
+    if world > 1 and not token_shard and args.workload in ("cfg1", "cfg3", "cfg5", "tiny"):
+        token_sharded = measure_token_sharded(model, shapes, batch, io_dtype, dev, rank, world, timed, ms / args.steps)
+
     if rank == 0:
         ms_per_step = ms / args.steps
         value = global_batch / (ms_per_step * 1e-3)
-        k_ms = kt["ms"] / max(kt["launches"], 1)
-        achieved = kt["flops"] / max(kt["launches"], 1) / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+        (kind, big), kt = max(kts.items(), key=lambda kv: kv[1]["ms"])
+        n_l = max(kt["launches"], 1)
+        k_ms = kt["ms"] / n_l
+        rate = lambda fl: fl / n_l / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+        useful, padded = rate(kt["flops_useful"]), rate(kt["flops"])
         csum = clocks.summary()
         sm_hz = (csum["sm_mhz"] or peaks["sm_max_mhz"]) * 1e6
-        exp_rate = kt["exps"] / max(kt["ms"], 1e-9) / 1e-3
+        c_big = kwargs["channel_dims"][big] + (kwargs["num_spatial_axes"][big] * 5 if kwargs.get("fourier_encode_data", True) else 0)
+        n_big = _prod(shapes[big][:-1])
+        if kind == 0 and c_big <= 63 and n_big > 2048:
+            kname = (f"attn_small_kernel<{32 if c_big <= 31 else 64},{3 if c_big <= 31 else 2},6,split> "
+                     f"(modality {big} streaming cross-attention, xattn_small.cu)")
+            flops_note = ("achieved / frac = UNPADDED executed FLOPs of the reassociated small-context form "
+                          "(4 L H N C per sample, SURVEY.md 8d); *_padded counts the zero padding to the UMMA tile "
+                          "(context width 32 | 64, three score terms)")
+        elif kind == 0:
+            kname = f"attn_kernel<64,generic,precise> (modality {big} streaming cross-attention, xattn.cu)"
+            flops_note = "achieved / frac = unpadded 4 L H N dh per sample; *_padded = executed incl. split terms and padding"
+        elif kind == 1:
+            kname = f"gemm_kernel (modality {big} K/V projection, split precision, gemm.cu)"
+            flops_note = "achieved / frac = unpadded 4 N C I per sample; *_padded = executed incl. the three split terms"
+        else:
+            kname = f"build_z_* (modality {big} context rows, rowops.cu)"
+            flops_note = "HBM-bound row kernel: no tensor FLOPs"
+        roof = dict(bound="tensor", achieved=useful, peak=peaks["tflops"], unit="TFLOP/s", frac=useful / peaks["tflops"],
+                    achieved_padded=padded, frac_padded=padded / peaks["tflops"], frac_useful=useful / peaks["tflops"],
+                    traffic=load_traffic() if args.workload == "cfg1" and batch == 4 and kind == 0 else None,
+                    peak_source=peaks["src"], kernel=kname, kernel_ms=k_ms, launches_per_step=kt["launches"],
+                    kernel_share_of_step=kt["ms"] / ms_per_step if ms_per_step > 0 else None, flops=flops_note)
+        if kt["exps"] > 0:
+            exp_rate = kt["exps"] / max(kt["ms"], 1e-9) / 1e-3
+            roof.update(exp_per_s=exp_rate, exp_frac_of_mufu=exp_rate / (148 * 16 * sm_hz))
+        shares = {f"modality{m}_{('attention', 'kv_gemm', 'context_rows')[k]}": round(v["ms"] / ms_per_step, 4)
+                  for (k, m), v in kts.items() if v["launches"] > 0}
+        cfg = _config(args.workload, kwargs, shapes, batch, global_batch,
+                      (f"token-axis sharded x{world} (partials merged over NVLink peer memory)"
+                       if token_shard else f"batch-sharded x{world}"))
+        cfg.update(operands="fp16 split hi/lo (three-term products), fp32 accumulate",
+                   l2="per-step working set (standardised context rows + inputs) exceeds the 126 MB L2")
         line = dict(
             metric=METRIC, value=value, unit="samples/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
             ms_per_step=ms_per_step, higher_is_better=True, scaling="strong" if token_shard else "weak",
             vs_baseline=None, dtype="f32" if io_dtype == torch.float32 else "bf16 I/O, fp16-split / fp32 arithmetic",
-            data="synthetic",
-            config=dict(workload=args.workload, batch_per_gpu=batch, global_batch=global_batch,
-                        shapes=[list(s) for s in shapes], depth=kwargs.get("depth", 3), l_c=kwargs["l_c"],
-                        l_d=kwargs["l_d"],
-                        parallelism=(f"token-axis sharded x{world} (partials merged over NVLink peer memory)"
-                                     if token_shard else f"batch-sharded x{world}"), operands="fp16 (split hi/lo on the latent side), fp32 accumulate",
-                        l2="per-step working set (standardised context rows + inputs) exceeds the 126 MB L2"),
+            data="synthetic", config=cfg,
             clocks=dict(sm_mhz=csum["sm_mhz"], sm_max_mhz=csum["sm_max_mhz"], reasons=csum["reasons"]),
             e2e=dict(value=global_batch * args.steps / e2e_s, unit="samples/s",
                      h2d_bytes_per_step=sum(t.numel() * t.element_size() for t in host),
                      d2h_bytes_per_step=out_h.numel() * out_h.element_size(),
                      pipeline="depth 2: step i+1 is enqueued before step i's logits are read on the host"),
-            gpu_launches=launches,
-            roofline=dict(bound="tensor", achieved=achieved, peak=peaks["tflops"], unit="TFLOP/s",
-                          frac=achieved / peaks["tflops"],
-                          traffic=load_traffic() if args.workload == "cfg1" and batch == 4 else None,
-                          peak_source=peaks["src"],
-                          kernel="attn_small_kernel<32,3,6> (volume cross-attention, xattn_small.cu)", kernel_ms=k_ms,
-                          kernel_share_of_step=kt["ms"] / ms_per_step if ms_per_step > 0 else None,
-                          flops="executed (reassociated small-context form, padded tiles)",
-                          exp_per_s=exp_rate, exp_frac_of_mufu=exp_rate / (148 * 16 * sm_hz)),
+            gpu_launches=launches, roofline=roof, step_shares=shares,
             algorithmic=dict(tflop_per_sample=flops_per_sample(kwargs, shapes) / 1e12,
-                             tflops_as_written=value * flops_per_sample(kwargs, shapes) / 1e12),
+                             tflops_as_written=value * flops_per_sample(kwargs, shapes) / 1e12,
+                             frac_as_written=value * flops_per_sample(kwargs, shapes) / 1e12 / peaks["tflops"]),
         )
+        if token_sharded is not None:
+            line["token_sharded"] = token_sharded
         if world == 1 and not args.no_cpu:
+            # cpu_baseline: ONE whole sample (sample 0 of this step's batch, same weights) through the reference algorithm
+            # on this box's host cores; its logits are the parity check of the CUDA path at the benchmarked size
             threads = len(os.sched_getaffinity(0))
-            cb = cpu_forward_timed(kwargs, shapes, args.cpu_budget, threads)
-            line["cpu_baseline"] = dict(value=cb["samples_per_s"], unit="samples/s", cores=threads, kind="port",
-                                        sample=cb["sample"])
+            sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
+            xs0 = [t[:1].float() for t in host]
+            t_cpu, want = cpu_port_sample(sd, kwargs, xs0, threads)
+            got = model([t[:1] for t in resident]).float().cpu()
+            tol = dict(rtol=1e-3, atol=1e-4) if io_dtype == torch.float32 else dict(rtol=1e-2, atol=2e-2)
+            d = (got - want).abs()
+            line["cpu_baseline"] = dict(value=1.0 / t_cpu, unit="samples/s", cores=threads, kind="port",
+                                        sample=f"1 whole sample (sample 0 of the batch, depth {kwargs.get('depth', 3)}, "
+                                               f"no scaling), oracle port, head_chunk=2, fp32: {t_cpu:.2f} s")
+            line["parity"] = dict(max_abs=float(d.max()), max_rel=float((d / want.abs().clamp_min(1e-3)).max()),
+                                  ok=bool(torch.allclose(got, want, **tol)), tol=tol,
+                                  what="logits of sample 0: CUDA path vs the CPU oracle on the same inputs and weights")
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -430,7 +566,6 @@ def main():
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
                     help="--impl reference only: cpu (default, the driver's arm) or cuda (PyTorch eager on one GPU)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline sample")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -61,6 +61,8 @@ SIGNATURES = {
     "hn_exchange_free": (c_int, [c_void_p]),
     "hn_set_exchange": (c_int, [c_void_p, c_int, c_int, POINTER(c_void_p), c_size_t]),
     "hn_exchange_error": (c_int, [c_void_p, POINTER(c_int)]),
+    "hn_exchange_error_async": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "hn_set_exchange_timeout": (c_int, [c_void_p, ctypes.c_double]),
     "hn_workspace_bytes_split": (c_size_t, [c_void_p, c_int, POINTER(c_int), POINTER(c_long)]),
     "hn_forward_split": (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int), POINTER(c_long),
                                  POINTER(c_long), POINTER(c_int), c_void_p, c_long, c_void_p, c_void_p, c_void_p,
@@ -68,8 +70,8 @@ SIGNATURES = {
     "hn_last_launch_count": (c_int, [c_void_p]),
     "hn_set_attention_export": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "hn_profile_enable": (c_int, [c_void_p, c_int]),
-    "hn_profile_read": (c_int, [c_void_p, c_int, POINTER(c_float), POINTER(c_int), POINTER(ctypes.c_double),
-                                POINTER(ctypes.c_double)]),
+    "hn_profile_read": (c_int, [c_void_p, c_int, c_int, POINTER(c_float), POINTER(c_int), POINTER(ctypes.c_double),
+                                POINTER(ctypes.c_double), POINTER(ctypes.c_double)]),
     "hn_attention_workspace_bytes": (c_size_t, [c_int, c_int, c_long, c_int, c_int, c_int, c_int]),
     "hn_attention_forward": (c_int, [c_int, c_int, c_long, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -85,8 +87,6 @@ SIGNATURES = {
                                 c_int, c_long, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hn_op_combine": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
                               c_void_p, c_void_p, c_int, c_void_p]),
-    "hn_debug_probe": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
-                               c_void_p]),
 }
 
 _lib = None

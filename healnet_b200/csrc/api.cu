@@ -94,13 +94,16 @@ struct hn_handle {
   bool profile = false;
   std::vector<cudaEvent_t> ev;          // 2 per slot
   std::vector<int> ev_mod;              // modality of each recorded slot in the last forward
+  std::vector<int> ev_kind;             // 0 cross-attention kernel, 1 K/V projection GEMM, 2 context-row build
   std::vector<double> ev_flops;         // tensor-core FLOPs the launch executed (padded tiles included)
+  std::vector<double> ev_useful;        // unpadded algorithmic FLOPs of the same launch
   std::vector<double> ev_exps;          // softmax exponentials the launch evaluated
   // token-axis sharding across GPUs (hn_set_exchange): peer-mapped exchange buffers, own rank included
   int x_rank = 0, x_world = 0;
   char* x_bufs[HN_MAX_PEERS] = {};
   size_t x_bytes = 0;
   unsigned long long x_seq = 0;         // exchanges published so far (all ranks advance in lock step)
+  long long x_timeout_clk = 60000000000LL;  // peer-wait bound in SM clocks (hn_set_exchange_timeout)
 };
 
 namespace {
@@ -109,7 +112,9 @@ int slot_index(const hn_handle* h, int layer, int slot) { return (layer + 1) * h
 
 int ctx_ld(int C) { return round_up(C, 8); }
 int seg_of(int K) { return round_up(K, 64); }
-// token axes up to this length run the precise (split hi/lo) attention + K/V projection
+// Token axes up to this length are never streamed by the small-context kernel nor sharded across GPUs. (Round 1 also
+// used it as the limit of the precise — split hi/lo — attention; the full-size peaked-softmax parity cases showed that
+// single fp16 score operands are not enough on long axes either, so every attention now runs precise.)
 constexpr long PRECISE_MAX_TOKENS = 2048;
 
 // sizes (or carves, when arena.base != null) the packed store; dedupes tied layers by pointer identity
@@ -225,7 +230,7 @@ int plan_workspace(const hn_handle* h, int batch, const int* axis_sizes, const b
   int ow = d.self_per_cross_attn ? d.l_heads * h->hpl : 0;
   size_t part_acc_elems = 0, part_ml_elems = 0, kv_elems = 0, mask_words = 0;
   const int n_ltiles = (L + 127) / 128;
-  ws.self_precise = L <= PRECISE_MAX_TOKENS;
+  ws.self_precise = true;
   if (d.self_per_cross_attn) {
     ws.self_nsplit = attention_pick_nsplit(batch, L, d.l_heads, L);
     part_acc_elems = static_cast<size_t>(batch) * ws.self_nsplit * d.l_heads * n_ltiles * 128 * h->hpl;
@@ -262,10 +267,10 @@ int plan_workspace(const hn_handle* h, int batch, const int* axis_sizes, const b
     const int vd = mp.small ? (mp.C <= 31 ? 32 : 64) : h->hpx;
     if (mp.small) {
       mp.zw = vd;
-      mp.z = ar.take<__half>(static_cast<size_t>(batch) * mp.Nl * mp.zw);
+      mp.z = ar.take<__half>(static_cast<size_t>(batch) * mp.Nl * 2 * mp.zw);  // rows [hi | lo]
       qw = qw > d.x_heads * mp.zw ? qw : d.x_heads * mp.zw;
     } else {
-      mp.precise = mp.N <= PRECISE_MAX_TOKENS;
+      mp.precise = true;
       mp.segC = seg_of(mp.C);
       mp.ldz = mp.precise ? 2 * mp.segC : ctx_ld(mp.C);
       mp.z = ar.take<__half>(static_cast<size_t>(batch) * mp.Nl * mp.ldz);
@@ -302,7 +307,10 @@ int plan_workspace(const hn_handle* h, int batch, const int* axis_sizes, const b
     ++h->launches;            \
   } while (0)
 
-int profile_begin(hn_handle* h, int modality, const AttnArgs& a, cudaStream_t st) {
+// measurement hook: one CUDA event pair per bracketed launch; kind 0 = streaming cross-attention kernel, 1 = K/V
+// projection GEMM of the generic path, 2 = context-row build (Fourier tables + standardisation)
+int profile_begin_raw(hn_handle* h, int kind, int modality, double flops_exec, double flops_useful, double exps,
+                      cudaStream_t st) {
   if (!h->profile) return 0;
   const size_t slot = h->ev_mod.size();
   while (h->ev.size() < 2 * (slot + 1)) {
@@ -310,14 +318,26 @@ int profile_begin(hn_handle* h, int modality, const AttnArgs& a, cudaStream_t st
     HN_CHECK_CUDA(cudaEventCreate(&e));
     h->ev.push_back(e);
   }
-  const double rows = static_cast<double>((a.L + 127) / 128) * 128.0, toks = static_cast<double>((a.N + 63) / 64) * 64.0;
-  const double kd = a.shared_kv ? a.kd : 64.0;
-  const double passes = a.precise ? 5.0 : 2.0;  // S: 3 + PV: 2 products in precise mode, else 1 + 1
   h->ev_mod.push_back(modality);
-  h->ev_flops.push_back(static_cast<double>(a.batch) * a.H * rows * toks * 2.0 * kd * passes);
-  h->ev_exps.push_back(static_cast<double>(a.batch) * a.H * rows * toks);
+  h->ev_kind.push_back(kind);
+  h->ev_flops.push_back(flops_exec);
+  h->ev_useful.push_back(flops_useful);
+  h->ev_exps.push_back(exps);
   HN_CHECK_CUDA(cudaEventRecord(h->ev[2 * slot], st));
   return 0;
+}
+// cross-attention launch: executed FLOPs count the padded tiles (rows to 128, tokens to 64, operand width kd);
+// useful FLOPs are the unpadded contraction (context width C on the reassociated small-context path, dim_head on the
+// generic one), SURVEY.md section 8d
+int profile_begin(hn_handle* h, int modality, const AttnArgs& a, int useful_width, cudaStream_t st) {
+  if (!h->profile) return 0;
+  const double rows = static_cast<double>((a.L + 127) / 128) * 128.0, toks = static_cast<double>((a.N + 63) / 64) * 64.0;
+  const double kd = a.shared_kv ? a.kd : a.hp;
+  // products per tile: S + PV; precise generic: 3 + 2, split small-context: 3 + 1
+  const double passes = a.precise ? (a.shared_kv ? 4.0 : 5.0) : 2.0;
+  return profile_begin_raw(h, 0, modality, static_cast<double>(a.batch) * a.H * rows * toks * 2.0 * kd * passes,
+                           static_cast<double>(a.batch) * a.H * a.L * static_cast<double>(a.N) * 4.0 * useful_width,
+                           static_cast<double>(a.batch) * a.H * rows * toks, st);
 }
 void profile_end(hn_handle* h, cudaStream_t st) {
   if (!h->profile) return;
@@ -591,19 +611,22 @@ int hn_profile_enable(hn_handle* h, int on) {
   return 0;
 }
 
-int hn_profile_read(hn_handle* h, int modality, float* ms, int* launches, double* flops, double* exps) {
-  HN_REQUIRE(h != nullptr && ms && launches && flops && exps, "hn_profile_read: null argument");
+int hn_profile_read(hn_handle* h, int kind, int modality, float* ms, int* launches, double* flops,
+                    double* flops_useful, double* exps) {
+  HN_REQUIRE(h != nullptr && ms && launches && flops && flops_useful && exps, "hn_profile_read: null argument");
   *ms = 0.f;
   *launches = 0;
   *flops = 0.0;
+  *flops_useful = 0.0;
   *exps = 0.0;
   for (size_t i = 0; i < h->ev_mod.size(); ++i) {
-    if (h->ev_mod[i] != modality) continue;
+    if (h->ev_mod[i] != modality || h->ev_kind[i] != kind) continue;
     float t = 0.f;
     HN_CHECK_CUDA(cudaEventElapsedTime(&t, h->ev[2 * i], h->ev[2 * i + 1]));
     *ms += t;
     *launches += 1;
     *flops += h->ev_flops[i];
+    *flops_useful += h->ev_useful[i];
     *exps += h->ev_exps[i];
   }
   return 0;
@@ -703,6 +726,24 @@ int hn_set_exchange(hn_handle* h, int rank, int world, void* const* bufs, size_t
   h->x_world = world;
   h->x_bytes = bytes;
   h->x_seq = 0;
+  // sequence numbers restart at 0: stale flags / a stale error word in a re-registered buffer must not satisfy (or
+  // fail) the first waits. Every rank clears its OWN header; the caller's barrier orders this before any publish.
+  HN_CHECK_CUDA(cudaMemset(h->x_bufs[rank], 0, sizeof(XchgHeader)));
+  HN_CHECK_CUDA(cudaDeviceSynchronize());
+  return 0;
+}
+
+int hn_set_exchange_timeout(hn_handle* h, double seconds) {
+  HN_REQUIRE(h != nullptr && seconds > 0.0, "hn_set_exchange_timeout: bad argument");
+  h->x_timeout_clk = static_cast<long long>(seconds * 1.9e9);
+  return 0;
+}
+
+int hn_exchange_error_async(const hn_handle* h, int* pinned_host_out, void* cuda_stream) {
+  HN_REQUIRE(h != nullptr && pinned_host_out != nullptr && h->x_world > 1, "hn_exchange_error_async: no exchange registered");
+  const XchgHeader* hdr = reinterpret_cast<const XchgHeader*>(h->x_bufs[h->x_rank]);
+  HN_CHECK_CUDA(cudaMemcpyAsync(pinned_host_out, &hdr->error, sizeof(int), cudaMemcpyDeviceToHost,
+                                static_cast<cudaStream_t>(cuda_stream)));
   return 0;
 }
 
@@ -725,6 +766,7 @@ static int exchange_partials(hn_handle* h, const Workspace& ws, int batch, int n
   pp.world = h->x_world;
   pp.rank = h->x_rank;
   pp.seq = seq;
+  pp.timeout_clk = h->x_timeout_clk;
   for (int r = 0; r < h->x_world; ++r) {
     pp.hdr[r] = reinterpret_cast<XchgHeader*>(h->x_bufs[r]);
     pp.acc[r] = reinterpret_cast<const float*>(h->x_bufs[r] + off);
@@ -764,7 +806,9 @@ static int forward_impl(hn_handle* h, int batch, const void* const* modality_ptr
   HN_REQUIRE(ws.bytes <= workspace_bytes, "hn_forward: workspace too small (see hn_workspace_bytes)");
   h->launches = 0;
   h->ev_mod.clear();
+  h->ev_kind.clear();
   h->ev_flops.clear();
+  h->ev_useful.clear();
   h->ev_exps.clear();
 
   // ---- once per forward: positional tables + standardised context rows (shared by all layers)
@@ -780,14 +824,17 @@ static int forward_impl(hn_handle* h, int batch, const void* const* modality_ptr
     const float* raw = static_cast<const float*>(modality_ptrs[m]);
     if (modality_ready_events != nullptr && modality_ready_events[m] != nullptr)
       HN_CHECK_CUDA(cudaStreamWaitEvent(st, static_cast<cudaEvent_t>(modality_ready_events[m]), 0));
+    int prc = profile_begin_raw(h, 2, m, 0.0, 0.0, 0.0, st);
+    if (prc != 0) return prc;
     if (d.fourier_encode_data)
       HN_TRY(launch_axis_tables(mp.tab, mp.axes, mp.n_axes, d.num_freq_bands, d.max_freq, st));
     if (mp.small)
       HN_TRY(launch_build_z_small(raw, mp.z, mp.zw, batch, mp.Nl, mp.c_raw, mp.n_axes, mp.axes, d.num_freq_bands,
-                                  mp.tab, d.fourier_encode_data, st, mp.tok0));
+                                  mp.tab, d.fourier_encode_data, st, mp.tok0, 1));
     else
       HN_TRY(launch_build_z_large(raw, mp.z, mp.ldz, mp.precise ? mp.segC : 0, batch, mp.Nl, mp.c_raw, mp.n_axes,
                                   mp.axes, d.num_freq_bands, mp.tab, d.fourier_encode_data, st, mp.tok0));
+    profile_end(h, st);
     if (mp.masked && !mask_packed) {
       HN_TRY(launch_pack_mask(mask, ws.mask_bits, batch, mp.Nl, st));
       mask_packed = true;
@@ -830,11 +877,11 @@ static int forward_impl(hn_handle* h, int batch, const void* const* modality_ptr
         const AttnPacked& ap = h->attn[l * (M + 1) + m];
         const FFPacked& fp = h->ff[l * (M + 1) + m];
         const int H = d.x_heads, HPx = h->hpx, ow = H * HPx;
-        // PreNorm + to_q (split operands; the small-C Q' keeps its hi part only)
+        // PreNorm + to_q (split operands in, split Q / Q' out)
         rc = ln_step(h, lp, ws, rows, st);
         if (rc != 0) return rc;
         const int qw = mp.small ? H * mp.zw : H * HPx;
-        const bool q_split = !mp.small && mp.precise;
+        const bool q_split = true;
         GemmArgs gq{ws.xn, mp.small ? ap.WqS : ap.Wq, static_cast<int>(rows), qw, D, 2 * sD, 2 * sD, EPI_F16, 0,
                     nullptr, ws.q, q_split ? 2 * qw : qw, 3, sD, sD, q_split ? qw : 0};
         HN_TRY(launch_gemm(gq, st));
@@ -855,11 +902,13 @@ static int forward_impl(hn_handle* h, int batch, const void* const* modality_ptr
         aa.part_ml = ws.part_ml;
         if (mp.small) {
           aa.KV = mp.z;
-          aa.kv_ld = mp.zw;
+          aa.kv_ld = 2 * mp.zw;
           aa.shared_kv = 1;
           aa.kd = mp.zw;
           aa.c_ones = mp.C;
-          rc = profile_begin(h, m, aa, st);
+          aa.precise = 1;
+          aa.q_lo_off = qw;
+          rc = profile_begin(h, m, aa, mp.C, st);
           if (rc != 0) return rc;
           HN_TRY(launch_attention(aa, st));
           profile_end(h, st);
@@ -881,7 +930,11 @@ static int forward_impl(hn_handle* h, int batch, const void* const* modality_ptr
           GemmArgs gkv{mp.z, ap.Wkv, static_cast<int>(tok), kvw, mp.C, mp.ldz, 2 * mp.segC, EPI_F16, 0, ap.bkv,
                        ws.kv, mp.precise ? 2 * kvw : kvw, mp.precise ? 3 : 2, mp.segC, mp.segC,
                        mp.precise ? kvw : 0};
+          rc = profile_begin_raw(h, 1, m, 2.0 * tok * kvw * round_up(mp.C, 64) * gkv.terms,
+                                 2.0 * tok * 2.0 * h->I * mp.C, 0.0, st);
+          if (rc != 0) return rc;
           HN_TRY(launch_gemm(gkv, st));
+          profile_end(h, st);
           aa.KV = ws.kv;
           aa.kv_ld = mp.precise ? 2 * kvw : kvw;
           aa.k_col0 = 0;
@@ -898,7 +951,7 @@ static int forward_impl(hn_handle* h, int batch, const void* const* modality_ptr
             aa.out_ld = 2 * ow;
             aa.out_lo_seg = ow;
           }
-          rc = profile_begin(h, m, aa, st);
+          rc = profile_begin(h, m, aa, d.cross_dim_head, st);
           if (rc != 0) return rc;
           HN_TRY(launch_attention(aa, st));
           profile_end(h, st);
@@ -976,13 +1029,18 @@ static int forward_impl(hn_handle* h, int batch, const void* const* modality_ptr
       }
     }
   }
+  bool any_sharded = false;
+  for (int m = 0; m < M; ++m) any_sharded = any_sharded || (ws.mod[m].present && ws.mod[m].sharded);
+  const XchgHeader* my_hdr = any_sharded ? reinterpret_cast<const XchgHeader*>(h->x_bufs[h->x_rank]) : nullptr;
   if (latents_out != nullptr) {
     HN_CHECK_CUDA(cudaMemcpyAsync(latents_out, ws.x, sizeof(float) * rows * D, cudaMemcpyDeviceToDevice, st));
+    if (my_hdr != nullptr) HN_TRY(launch_poison_on_error(latents_out, rows * D, my_hdr, st));
   }
   if (logits_out != nullptr) {
     const std::vector<const float*>& wh = h->w[slot_index(h, -1, 1)];
     HN_TRY(launch_head(ws.x, batch, L, D, wh[0], wh[1], wh[2], wh[3], d.out_dims, ws.pooled, logits_out, st));
     ++h->launches;
+    if (my_hdr != nullptr) HN_TRY(launch_poison_on_error(logits_out, static_cast<long>(batch) * d.out_dims, my_hdr, st));
   }
   return 0;
 }
@@ -1003,7 +1061,7 @@ void plan_attn_ws(int batch, int n_q, long n_ctx, int qd, int cd, int heads, int
   ar.base = base;
   w.sq = seg_of(qd);
   w.sc = seg_of(cd);
-  w.prec = n_ctx <= PRECISE_MAX_TOKENS;
+  w.prec = true;
   const long rows = static_cast<long>(batch) * n_q, toks = static_cast<long>(batch) * n_ctx;
   const int hw = heads * head_pitch(dim_head);
   w.xh = ar.take<__half>(rows * 2 * w.sq);
@@ -1139,7 +1197,7 @@ int hn_op_build_context(const float* raw, void* z, int ldz, int small, int batch
   }
   if (small)
     return launch_build_z_small(raw, static_cast<__half*>(z), ldz, batch, N, c_raw, n_axes, axis_sizes, n_bands, tab,
-                                fourier, st);
+                                fourier, st, 0, small == 2 ? 1 : 0);
   return launch_build_z_large(raw, static_cast<__half*>(z), ldz, 0, batch, N, c_raw, n_axes, axis_sizes, n_bands,
                               tab, fourier, st);
 }
@@ -1152,7 +1210,9 @@ int hn_op_attention_nsplit(int batch, int L, int H, long N, int small_kd) {
 int hn_op_attention(const void* Q, int q_ld, const void* KV, long kv_ld, int k_col0, int v_col0, int shared_kv,
                     int c_ones, int head_pitch_cols, int batch, int L, int H, long N, int nsplit, const uint8_t* mask,
                     void* mask_bits_scratch, float* part_acc, float* part_ml, void* cuda_stream) {
-  // shared_kv: 0 generic, 1 small-context kernel (xattn_small.cu), 2 first-generation small-context kernel
+  // shared_kv: 0 generic, 1 small-context kernel (xattn_small.cu) on single fp16 operands, 3 the same on split
+  // operands (Q' rows [hi | lo at q_ld / 2], z rows [hi (kd) | lo (kd)], kv_ld = 2 kd) — the mode the forward uses
+  HN_REQUIRE(shared_kv == 0 || shared_kv == 1 || shared_kv == 3, "hn_op_attention: shared_kv must be 0, 1 or 3");
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   AttnArgs aa{};
   aa.Q = static_cast<const __half*>(Q);
@@ -1162,10 +1222,13 @@ int hn_op_attention(const void* Q, int q_ld, const void* KV, long kv_ld, int k_c
   aa.k_col0 = k_col0;
   aa.v_col0 = v_col0;
   aa.shared_kv = shared_kv ? 1 : 0;
-  aa.legacy_small = shared_kv == 2 ? 1 : 0;
   aa.c_ones = c_ones;
   aa.hp = head_pitch_cols > 0 ? head_pitch_cols : 64;
-  aa.kd = shared_kv ? static_cast<int>(kv_ld) : 64;
+  aa.kd = shared_kv == 3 ? static_cast<int>(kv_ld / 2) : (shared_kv ? static_cast<int>(kv_ld) : 64);
+  if (shared_kv == 3) {
+    aa.precise = 1;
+    aa.q_lo_off = q_ld / 2;
+  }
   aa.batch = batch;
   aa.L = L;
   aa.H = H;

@@ -129,11 +129,12 @@ int launch_layernorm_f16(const float* x, int ldx, const float* gamma, const floa
 // per-axis Fourier tables: tab[axis_off[a] + j][2B+1] (fp32)
 int launch_axis_tables(float* tab, const int* axis_sizes, int n_axes, int n_bands, float max_freq,
                        cudaStream_t stream);
-// standardised context rows, small-C layout: z[b][N][zw] fp16 = [(v-mean)*rstd (C values), 1, 0...], zw = 32 | 64
+// standardised context rows, small-C layout: z[b][N][zw] fp16 = [(v-mean)*rstd (C values), 1, 0...], zw = 32 | 64;
+// split != 0: z[b][N][2 zw] = [hi (zw) | lo (zw)]
 // (tok0: index of the first token of this buffer on the modality's full token axis; N = tokens in the buffer)
 int launch_build_z_small(const float* raw, __half* z, int zw, int batch, long N, int c_raw, int n_axes,
                          const int* axis_sizes /*host*/, int n_bands, const float* tab, int fourier,
-                         cudaStream_t stream, long tok0 = 0);
+                         cudaStream_t stream, long tok0 = 0, int split = 0);
 // standardised context rows, generic layout: z[b*N][ldz] fp16 (pad cols zero); lo_seg > 0: split [hi | lo]
 int launch_build_z_large(const float* raw, __half* z, int ldz, int lo_seg, int batch, long N, int c_raw, int n_axes,
                          const int* axis_sizes /*host*/, int n_bands, const float* tab, int fourier,
@@ -155,12 +156,13 @@ struct AttnArgs {
   const __half* KV;
   long kv_ld;
   int k_col0, v_col0;
-  // precise mode (generic path, short token axes whose rounding errors do not average out): Q, K, V rows also
-  // carry lo = fp16(x - hi) parts at these column offsets; S = Qh.Kh + Ql.Kh + Qh.Kl, U += P.Vh + P.Vl
+  // precise mode: Q, K, V rows also carry lo = fp16(x - hi) parts at these column offsets;
+  // S = Qh.Kh + Ql.Kh + Qh.Kl, U += P.Vh + P.Vl. Small-C path: Q' lo at q_lo_off, z rows [hi (kd) | lo (kd)] (kv_ld =
+  // 2 kd), S = Q'h.zh + Q'l.zh + Q'h.zl, U += P.zh. Single fp16 score operands are off by |s| 2^-11, which a peaked
+  // softmax does not average away (tests/test_gpu_fullsize.py), so the forward always runs precise.
   int precise = 0;
   int q_lo_off = 0, kv_lo_off = 0;
   int c_ones = 0;        // shared_kv only: index of the 1.0 column of z (= context width C)
-  int legacy_small = 0;  // shared_kv only: run the first-generation kernel (xattn.cu) instead of xattn_small.cu
   int shared_kv;  // 1 = small-C path
   int kd;         // operand width per head: 64 generic; 32 or 64 (= z row width) on the small-C path
   int hp = 64;    // generic path: head pitch in Q / K / V columns and accumulator width, 64 or 128 (dim_head > 64)
@@ -201,7 +203,10 @@ struct PeerParts {
   const float* ml[HN_MAX_PEERS];
   XchgHeader* hdr[HN_MAX_PEERS];   // header of every rank's buffer (own: hdr[rank])
   unsigned long long seq = 0;
+  long long timeout_clk = 60000000000LL;  // SM clocks a wait for a peer may last (~30 s) before it is given up
 };
+// overwrites out[0..n) with NaN when this rank's exchange header carries the time-out flag
+int launch_poison_on_error(float* out, long n, const XchgHeader* hdr, cudaStream_t stream);
 // local splits -> one partial in this rank's slot, then flag every peer (last block signals)
 int launch_merge_signal(const float* part_acc, const float* part_ml, int batch, int nsplit, int H, int L, int w,
                         float* slot_acc, float* slot_ml, const PeerParts& peers, cudaStream_t stream);

@@ -111,7 +111,7 @@ probe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
 
 // Q: [128][kd] fp16, K: [64][kd] fp16, V: [64][vd] fp16 (row-major, device). S_out [128][64], U_out [128][vd] fp32.
 // ov: optional 10 ints overriding {q_lbo,q_sbo,k_lbo,k_sbo,v_lbo,v_sbo,qk_kadv,v_kadv,q_layout,v_layout}; <0 keeps default.
-extern "C" int hn_debug_probe(const void* Q, const void* K, const void* V, int kd, int vd, float* S_out,
+extern "C" __attribute__((visibility("default"))) int hn_debug_probe(const void* Q, const void* K, const void* V, int kd, int vd, float* S_out,
                               float* U_out, const int* ov, void* stream) {
   if (!((kd == 32 || kd == 64) && (vd == 32 || vd == 64))) return -1;
   CUtensorMap tq, tk, tv;

@@ -152,12 +152,30 @@ __global__ void axis_tables_kernel(float* __restrict__ tab, AxisInfo ax, int B, 
   }
 }
 
+// eight consecutive values -> one 16-byte store of their fp16 hi parts and (lo_dst != null) one of the lo parts
+__device__ __forceinline__ void store_hi_lo8(uint4* hi_dst, uint4* lo_dst, const float* o) {
+  uint4 w, wl;
+  uint32_t* ph = reinterpret_cast<uint32_t*>(&w);
+  uint32_t* pl = reinterpret_cast<uint32_t*>(&wl);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const __half2 h = __floats2half2_rn(o[2 * k], o[2 * k + 1]);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(o[2 * k] - hf.x, o[2 * k + 1] - hf.y);
+    ph[k] = *reinterpret_cast<const uint32_t*>(&h);
+    pl[k] = *reinterpret_cast<const uint32_t*>(&l);
+  }
+  *hi_dst = w;
+  if (lo_dst != nullptr) *lo_dst = wl;
+}
+
 // ------------------------------------------------------------------ z rows, small-C layout (C <= ZW-1)
 // one thread per token: raw channels + table features -> standardise -> ZW fp16 = one 64/128-byte row
+// split != 0: rows are [hi (ZW) | lo (ZW)], lo = fp16(value - hi) (the streaming kernel's three-term score product)
 template <int ZW>
 __global__ void __launch_bounds__(256) build_z_small_kernel(const float* __restrict__ raw, __half* __restrict__ z,
                                                             long tokens_total, long N, int c_raw, AxisInfo ax,
-                                                            int F, const float* __restrict__ tab, long tok0) {
+                                                            int F, const float* __restrict__ tab, long tok0, int split) {
   HN_PDL_LAUNCH();
   HN_PDL_WAIT();
   const long t = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -207,20 +225,9 @@ __global__ void __launch_bounds__(256) build_z_small_kernel(const float* __restr
     if (i == C) val = 1.f;  // ones column: the PV UMMA accumulates the softmax denominator for free
     v[i] = val;
   }
-  uint4* dst = reinterpret_cast<uint4*>(z + t * ZW);
+  uint4* dst = reinterpret_cast<uint4*>(z + t * (split ? 2 * ZW : ZW));
 #pragma unroll
-  for (int i = 0; i < ZW / 8; ++i) {
-    uint4 w;
-    __half2 h0 = __floats2half2_rn(v[8 * i + 0], v[8 * i + 1]);
-    __half2 h1 = __floats2half2_rn(v[8 * i + 2], v[8 * i + 3]);
-    __half2 h2 = __floats2half2_rn(v[8 * i + 4], v[8 * i + 5]);
-    __half2 h3 = __floats2half2_rn(v[8 * i + 6], v[8 * i + 7]);
-    w.x = *reinterpret_cast<uint32_t*>(&h0);
-    w.y = *reinterpret_cast<uint32_t*>(&h1);
-    w.z = *reinterpret_cast<uint32_t*>(&h2);
-    w.w = *reinterpret_cast<uint32_t*>(&h3);
-    dst[i] = w;
-  }
+  for (int i = 0; i < ZW / 8; ++i) store_hi_lo8(dst + i, split ? dst + ZW / 8 + i : nullptr, v + 8 * i);
 }
 
 // Specialisation for the shapes the path is run on (image / volume: 1-4 raw channels, 1-3 axes, the default 2
@@ -229,7 +236,7 @@ __global__ void __launch_bounds__(256) build_z_small_kernel(const float* __restr
 template <int CRAW, int NAX>
 __global__ void __launch_bounds__(256) build_z_small32_fast_kernel(const float* __restrict__ raw, __half* __restrict__ z,
                                                                    long tokens_total, long N, AxisInfo ax,
-                                                                   const float* __restrict__ tab, long tok0) {
+                                                                   const float* __restrict__ tab, long tok0, int split) {
   HN_PDL_LAUNCH();
   HN_PDL_WAIT();
   constexpr int F = 5, ZW = 32, C = CRAW + NAX * F;
@@ -263,7 +270,7 @@ __global__ void __launch_bounds__(256) build_z_small32_fast_kernel(const float* 
     q += d * d;
   }
   const float rstd = rsqrtf(q / C + LN_EPS);
-  uint4* dst = reinterpret_cast<uint4*>(z + t * ZW);
+  uint4* dst = reinterpret_cast<uint4*>(z + t * (split ? 2 * ZW : ZW));
 #pragma unroll
   for (int g = 0; g < ZW / 8; ++g) {
     float o[8];
@@ -272,14 +279,7 @@ __global__ void __launch_bounds__(256) build_z_small32_fast_kernel(const float* 
       const int i = g * 8 + j;
       o[j] = i < C ? (v[i < C ? i : 0] - mean) * rstd : (i == C ? 1.f : 0.f);
     }
-    uint4 w;
-    __half2 h0 = __floats2half2_rn(o[0], o[1]), h1 = __floats2half2_rn(o[2], o[3]);
-    __half2 h2 = __floats2half2_rn(o[4], o[5]), h3 = __floats2half2_rn(o[6], o[7]);
-    w.x = *reinterpret_cast<uint32_t*>(&h0);
-    w.y = *reinterpret_cast<uint32_t*>(&h1);
-    w.z = *reinterpret_cast<uint32_t*>(&h2);
-    w.w = *reinterpret_cast<uint32_t*>(&h3);
-    dst[g] = w;
+    store_hi_lo8(dst + g, split ? dst + ZW / 8 + g : nullptr, o);
   }
 }
 
@@ -490,15 +490,16 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 // Block-wide wait until every rank has published exchange `seq` (its flag in OUR header, written by the peer over
-// NVLink). Bounded: after ~2 s the block gives up, records the error and carries on, so a dead peer can never hang
-// the GPU. Call with all threads of the block.
+// NVLink). Bounded: after pp.timeout_clk clocks (default ~30 s, hn_set_exchange_timeout) the block gives up and records
+// the error, so a dead peer can never hang the GPU; the forward then poisons its outputs with NaN
+// (poison_on_error_kernel) and the host raises at its next check (hn_exchange_error*). Call with all threads of the block.
 __device__ __forceinline__ void peers_wait(const PeerParts& pp) {
   if (pp.world == 0) return;
   if (threadIdx.x < pp.world) {
     const unsigned long long* f = &pp.hdr[pp.rank]->flags[threadIdx.x];
     const long long t0 = clock64();
     while (ld_acquire_sys(f) < pp.seq) {
-      if (clock64() - t0 > 4000000000LL) {
+      if (clock64() - t0 > pp.timeout_clk) {
         pp.hdr[pp.rank]->error = 1;
         break;
       }
@@ -563,6 +564,15 @@ __global__ void __launch_bounds__(256) merge_signal_kernel(const float* __restri
       for (int r = 0; r < pp.world; ++r) st_release_sys(&pp.hdr[r]->flags[pp.rank], pp.seq);
     }
   }
+}
+
+// a token-sharded forward whose peer wait timed out must not hand out plausible-looking numbers: NaN them
+__global__ void poison_on_error_kernel(float* __restrict__ out, long n, const XchgHeader* __restrict__ hdr) {
+  HN_PDL_LAUNCH();
+  HN_PDL_WAIT();
+  if (hdr->error == 0) return;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x)
+    out[i] = __int_as_float(0x7fc00000);
 }
 
 // ------------------------------------------------------------------ split combine
@@ -818,7 +828,7 @@ int launch_axis_tables(float* tab, const int* axis_sizes, int n_axes, int n_band
 
 int launch_build_z_small(const float* raw, __half* z, int zw, int batch, long N, int c_raw, int n_axes,
                          const int* axis_sizes, int n_bands, const float* tab, int fourier, cudaStream_t stream,
-                         long tok0) {
+                         long tok0, int split) {
   const int F = fourier ? 2 * n_bands + 1 : 0;
   const int C = c_raw + F * n_axes;
   HN_REQUIRE(zw == 32 || zw == 64, "small-C context rows are 32 or 64 wide");
@@ -830,7 +840,7 @@ int launch_build_z_small(const float* raw, __half* z, int zw, int batch, long N,
 #define HN_FAST(CR, NA)                                                                                      \
   if (c_raw == CR && n_axes == NA) {                                                                         \
     HN_CHECK_CUDA(launch_k(build_z_small32_fast_kernel<CR, NA>, dim3(grid), dim3(256), 0, stream, raw, z, total, N, ax, \
-                           tab, tok0));                                                                      \
+                           tab, tok0, split));                                                               \
     return 0;                                                                                                \
   }
     HN_FAST(1, 1) HN_FAST(1, 2) HN_FAST(1, 3) HN_FAST(2, 1) HN_FAST(2, 2) HN_FAST(2, 3)
@@ -839,10 +849,10 @@ int launch_build_z_small(const float* raw, __half* z, int zw, int batch, long N,
   }
   if (zw == 32)
     HN_CHECK_CUDA(launch_k(build_z_small_kernel<32>, dim3(grid), dim3(256), 0, stream, raw, z, total, N, c_raw, ax, F, tab,
-                           tok0));
+                           tok0, split));
   else
     HN_CHECK_CUDA(launch_k(build_z_small_kernel<64>, dim3(grid), dim3(256), 0, stream, raw, z, total, N, c_raw, ax, F, tab,
-                           tok0));
+                           tok0, split));
   HN_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -933,10 +943,18 @@ int launch_merge_signal(const float* part_acc, const float* part_ml, int batch, 
   return 0;
 }
 
+int launch_poison_on_error(float* out, long n, const XchgHeader* hdr, cudaStream_t stream) {
+  const unsigned grid = static_cast<unsigned>(n / 256 + 1 < 592 ? n / 256 + 1 : 592);
+  HN_CHECK_CUDA(launch_k(poison_on_error_kernel, dim3(grid), dim3(256), 0, stream, out, n, hdr));
+  HN_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int launch_attn_export(const AttnArgs& a, float* out, cudaStream_t stream) {
   HN_REQUIRE(out != nullptr, "attention export: null output");
   const dim3 grid(static_cast<unsigned>((a.N + 255) / 256), (a.L + 15) / 16, a.batch * a.H);
-  const int q_lo = a.precise ? a.q_lo_off : 0, k_lo = a.precise ? a.kv_lo_off : 0;
+  // (split small-context rows are [z_hi (kd) | z_lo (kd)])
+  const int q_lo = a.precise ? a.q_lo_off : 0, k_lo = a.precise ? (a.shared_kv ? a.kd : a.kv_lo_off) : 0;
   // small-context path: Q' heads are kd columns apart, every head reads the same z row, the denominator is the
   // accumulator column that met z's 1.0; generic path: heads hp apart in Q and K, denominator = tracked row sum
   const int kw = a.shared_kv ? a.kd : a.hp;
@@ -944,7 +962,7 @@ int launch_attn_export(const AttnArgs& a, float* out, cudaStream_t stream) {
   const int k_col0 = a.shared_kv ? 0 : a.k_col0;
   const int den_col = a.shared_kv ? a.c_ones : -1;
   // xattn_small.cu accumulates P' = 2^P_SHIFT * P (P_SHIFT = 10): its denominator column carries that factor
-  const float den_scale = (a.shared_kv && !a.legacy_small) ? 0.0009765625f : 1.f;
+  const float den_scale = a.shared_kv ? 0.0009765625f : 1.f;
 #define HN_EXPORT(KW)                                                                                              \
   attn_export_kernel<KW><<<grid, 256, 0, stream>>>(a.Q, a.q_ld, 0, q_lo, a.KV, a.kv_ld, k_col0, k_lo, q_pitch,      \
                                                    k_pitch, a.batch, a.H, a.L, a.N, a.nsplit, a.part_acc,          \

@@ -416,10 +416,6 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   HN_REQUIRE(a.N < (1L << 31), "attention: token axis too long");
   if (a.shared_kv) {
     HN_REQUIRE(a.kd == 32 || a.kd == 64, "attention: shared-context rows must be 32 or 64 wide");
-    HN_REQUIRE(a.kv_ld == a.kd, "attention: shared-context rows must be dense");
-    HN_REQUIRE(!a.precise, "attention: the precise mode exists on the generic path only");
-    if (a.legacy_small)
-      return a.kd == 32 ? launch_t<32, true, false, 1>(a, stream) : launch_t<64, true, false, 1>(a, stream);
     return launch_small_attention(a, stream);
   }
   HN_REQUIRE(a.hp == 64 || a.hp == 128, "attention: head pitch must be 64 or 128");

@@ -32,6 +32,13 @@
 // polling several groups' mbarriers (~150 clk per test) starved the groups, and letting a softmax warp issue
 // stretched that warp's tile and with it the whole group's; last warp = TMA producer (Q' tiles once, z tiles
 // through an 8-stage mbarrier ring). TMEM per group: S/P buffer 0 (64) | S/P buffer 1 (64) | U (KD).
+//
+// SPLIT (the product path): the score operands arrive as fp16 hi + lo pairs — Q' rows [hi | lo at q_lo_off], z rows
+// [hi (KD) | lo (KD)] — and S = Q'h.zh + Q'l.zh + Q'h.zl (three K blocks into the same TMEM accumulator). With single
+// fp16 operands the score error grows like |s| * 2^-11 and does not average out once the softmax is peaked (measured at
+// the full cfg 1 volume with to_q scaled x8 / x32: latent error 1e-3 / 9e-3, tests/test_gpu_fullsize.py); the split
+// makes the scores fp32-exact for two extra 32-clk UMMAs per tile on a tensor pipe that was 26 % busy. P.z (the value
+// side) keeps the hi part only: it is a convex combination whose fp16 rounding stays below 2^-11 relative.
 #include <cstdlib>
 #include <type_traits>
 
@@ -59,6 +66,7 @@ constexpr float RESCALE_THRESHOLD = 5.f;    // log2 units
 
 struct SmallDev {
   int L, H, batch, nsplit, n_ltiles, n_rb;  // n_rb = H * n_ltiles row blocks per (sample, split)
+  int q_lo_off;                              // SPLIT: column offset of the lo parts inside a Q' row
   int ctas_per_stream;                       // ceil(n_rb / G)
   int tiles_total;
   int mask_words;  // 64-token mask words per sample
@@ -73,7 +81,9 @@ struct SmallDev {
 // Debug timeline (tools/trace_attn.py): CTA 0 records clock64() at a few points of tiles [TR_T0, TR_T0 + TR_NT) for
 // the first softmax warp and the issuer of every group. Compiled into separate TRACE instantiations only.
 constexpr int TR_T0 = 64, TR_NT = 48, TR_NP = 8;
-long long* g_trace_buf = nullptr;  // set through hn_debug_set_trace (debug only)
+#ifdef HN_DEBUG
+long long* g_trace_buf = nullptr;  // set through hn_debug_set_trace
+#endif
 #define HN_TR(slot, tile, k)                                                                              \
   do {                                                                                                    \
     if (TRACE && p.trace != nullptr && blockIdx.x == 0 && lane == 0 && (tile) >= TR_T0 && (tile) < TR_T0 + TR_NT) \
@@ -118,16 +128,21 @@ __device__ __forceinline__ constexpr bool poly_slot(int j) {
          : PMODE == 3 ? ((j % 8) == 1 || (j % 8) == 4 || (j % 8) == 6)
                       : (j % 2) == 1;
 }
-// packed-pair variant: both exponentials of a column pair on the FMA / ALU pipes in half2 arithmetic (11
+// packed-pair variant: both exponentials of a column pair on the FMA / ALU pipes in half2 arithmetic (12
 // instructions per PAIR incl. the fp16 pack, vs 17 for two fp32 polynomials + pack). The argument already carries
 // +P_SHIFT (see above). n = rint(x) via the magic constant trick (fp16 ulp is 1 in [1024, 2048)): the integer lands in
 // the low mantissa bits and the exponent insert (a lane-wise integer add) builds 2^x — a normal fp16 for every
-// x >= -14, below which the argument is clamped (2^-24 of the reference weight). x above 15.5 overflows the exponent
-// field into inf / NaN / the sign bit: all of them read as "> 2^15" by the unsigned max check that triggers the exact
-// path. Relative error ~6e-4 rms (3x the fp16 rounding of P itself, zero-mean).
+// x >= -14. Below that the exponent field runs through 0 (a subnormal <= 2^-14, i.e. <= 2^-24 of the reference weight)
+// into the sign bit: the lane then reads as a NEGATIVE fp16 (or -inf / NaN), which the final max with +0 turns into an
+// exact zero — so tokens far below the reference contribute nothing, like MUFU's flush to zero. (Round 1 clamped the
+// argument at -14 instead, which gave every such token a weight of 2^-24: harmless for diffuse softmaxes, but over
+// 602 112 voxels a spurious mass of up to 1.8 % once the softmax is peaked — found by tests/test_gpu_fullsize.py.)
+// The argument is clamped at -30 only to keep the magic-constant sum inside [1024, 2048). x above 15.5 overflows the
+// exponent field into inf / NaN: read as "> 2^15" by the unsigned max check that triggers the exact path.
+// Relative error ~6e-4 rms (3x the fp16 rounding of P itself, zero-mean).
 __device__ __forceinline__ uint32_t ex2_pair_h2(float x0, float x1) {
   __half2 xh = __floats2half2_rn(x0, x1);
-  xh = __hmax2(xh, __float2half2_rn(-14.f));
+  xh = __hmax2(xh, __float2half2_rn(-30.f));
   const __half2 magic = __float2half2_rn(1536.f);
   const __half2 t = __hadd2(xh, magic);
   const __half2 f = __hsub2(xh, __hsub2(t, magic));  // t = 1536 + rint(x) exactly
@@ -138,7 +153,8 @@ __device__ __forceinline__ uint32_t ex2_pair_h2(float x0, float x1) {
   const uint32_t e = (*reinterpret_cast<const uint32_t*>(&t) << 10) & 0xFC00FC00u;
   uint32_t r;
   asm("add.u16x2 %0, %1, %2;" : "=r"(r) : "r"(*reinterpret_cast<const uint32_t*>(&p)), "r"(e));
-  return r;
+  const __half2 rz = __hmax2(*reinterpret_cast<const __half2*>(&r), __float2half2_rn(0.f));
+  return *reinterpret_cast<const uint32_t*>(&rz);
 }
 // PMODE >= 5: which column PAIRS take the half2 polynomial: 5 = 1/3, 6 = 1/2, 7 = 2/3, 8 = 3/4
 template <int PMODE>
@@ -154,12 +170,14 @@ __device__ __forceinline__ uint32_t swizzled_off(int row, int col) {
   return row * 128 + ((chunk ^ (static_cast<uint32_t>(row) & 7u)) << 4) + within;
 }
 
-template <int KD, int G, int PMODE, bool TRACE = false>
+template <int KD, int G, int PMODE, bool SPLIT, bool TRACE = false>
 __global__ void __launch_bounds__((5 * G + 1) * 32, 1)
 attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmZ, SmallDev p) {
   constexpr int VD = KD;
-  constexpr int Q_TILE = BM * KD * 2;
-  constexpr int Z_BYTES = BT * KD * 2;
+  constexpr int Q_TILE = BM * KD * 2;            // one [128][KD] operand tile (hi or lo)
+  constexpr int Q_GROUP = (SPLIT ? 2 : 1) * Q_TILE;   // per row block: [Q'h | Q'l]
+  constexpr int Z_BYTES = BT * KD * 2;           // one [64][KD] tile (hi or lo)
+  constexpr int Z_STAGE = (SPLIT ? 2 : 1) * Z_BYTES;  // per ring stage: [zh | zl]
   constexpr uint32_t LAYOUT = (KD == 64) ? SWZ_128B : SWZ_64B;
   constexpr uint32_t SBO = 8 * KD * 2;
   constexpr uint32_t V_KADV = 16 * VD * 2;
@@ -171,7 +189,7 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
-  uint8_t* sZ = smem + G * Q_TILE;
+  uint8_t* sZ = smem + G * Q_GROUP;
   __shared__ uint64_t q_full, z_full[NST], z_empty[NST];
   __shared__ uint64_t s_full[MAXG][2], p_ready[MAXG][2], u_done[MAXG], acc_done[MAXG];
   __shared__ uint32_t tmem_base_s;
@@ -235,16 +253,18 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     if (elect_one()) {
       tma_prefetch_desc(&tmQ);
       tma_prefetch_desc(&tmZ);
-      mbar_arrive_expect_tx(&q_full, n_active * Q_TILE);
+      mbar_arrive_expect_tx(&q_full, n_active * Q_GROUP);
       for (int g = 0; g < n_active; ++g) {
         const int rb = rb0 + g, h = rb / p.n_ltiles, lt = rb % p.n_ltiles;
-        tma_load_3d(sQ + g * Q_TILE, &tmQ, &q_full, h * KD, lt * BM, b);
+        tma_load_3d(sQ + g * Q_GROUP, &tmQ, &q_full, h * KD, lt * BM, b);
+        if (SPLIT) tma_load_3d(sQ + g * Q_GROUP + Q_TILE, &tmQ, &q_full, p.q_lo_off + h * KD, lt * BM, b);
       }
       for (int i = 0; i < n; ++i) {
         const int s = i % NST;
         mbar_wait_sleepy(&z_empty[s], ((i / NST) & 1) ^ 1, 20000);
-        mbar_arrive_expect_tx(&z_full[s], Z_BYTES);
-        tma_load_3d(sZ + s * Z_BYTES, &tmZ, &z_full[s], 0, (t_begin + i) * BT, b);
+        mbar_arrive_expect_tx(&z_full[s], Z_STAGE);
+        tma_load_3d(sZ + s * Z_STAGE, &tmZ, &z_full[s], 0, (t_begin + i) * BT, b);
+        if (SPLIT) tma_load_3d(sZ + s * Z_STAGE + Z_BYTES, &tmZ, &z_full[s], KD, (t_begin + i) * BT, b);
       }
     }
   } else if (warp >= 4 * G) {
@@ -255,16 +275,26 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const int g = warp - 4 * G;
     if (g < n_active && elect_one()) {
       const uint32_t tG = tmem + g * GCOLS;
-      const uint32_t q0 = smem_u32(sQ + g * Q_TILE);
+      const uint32_t q0 = smem_u32(sQ + g * Q_GROUP);
       auto issue_s = [&](int i) {
         const int s = i % NST;
         mbar_wait(&z_full[s], (i / NST) & 1);
         fence_after_sync();
-        const uint32_t z0 = smem_u32(sZ + s * Z_BYTES);
+        const uint32_t z0 = smem_u32(sZ + s * Z_STAGE);
 #pragma unroll
         for (int k = 0; k < KD / 16; ++k)
           umma_ss(tG + (i & 1) * 64, smem_desc(q0 + k * 32, 16, SBO, LAYOUT), smem_desc(z0 + k * 32, 16, SBO, LAYOUT),
                   idesc_s, k != 0);
+        if (SPLIT) {
+#pragma unroll
+          for (int k = 0; k < KD / 16; ++k)  // Q'_lo . z_hi
+            umma_ss(tG + (i & 1) * 64, smem_desc(q0 + Q_TILE + k * 32, 16, SBO, LAYOUT),
+                    smem_desc(z0 + k * 32, 16, SBO, LAYOUT), idesc_s, true);
+#pragma unroll
+          for (int k = 0; k < KD / 16; ++k)  // Q'_hi . z_lo
+            umma_ss(tG + (i & 1) * 64, smem_desc(q0 + k * 32, 16, SBO, LAYOUT),
+                    smem_desc(z0 + Z_BYTES + k * 32, 16, SBO, LAYOUT), idesc_s, true);
+        }
         umma_commit(&s_full[g][i & 1]);
       };
       mbar_wait(&q_full, 0);
@@ -278,7 +308,7 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         HN_TR(MAXG + g, i, 1);
         fence_after_sync();
         const int s = i % NST;
-        const uint32_t z0 = smem_u32(sZ + s * Z_BYTES);
+        const uint32_t z0 = smem_u32(sZ + s * Z_STAGE);
 #pragma unroll
         for (int k = 0; k < BT / 16; ++k)
           umma_ts(tG + 128, tG + (i & 1) * 64 + k * 8, smem_desc(z0 + k * V_KADV, 16, SBO, LAYOUT), idesc_u,
@@ -301,7 +331,7 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const uint32_t tG = tmem + g * GCOLS;  // group columns (lane field 0)
       const uint32_t tL = tmem_addr(tG, lane_base, 0);
       const uint32_t tU = tL + 128;
-      uint8_t* qrow_fold = sQ + g * Q_TILE;  // Q'[trow][C_ones] holds -m_ref (fp16): the UMMA subtracts the max for us
+      uint8_t* qrow_fold = sQ + g * Q_GROUP;  // Q'h[trow][C_ones] holds -m_ref (fp16): the UMMA subtracts the max for us
       float m_ref = -INFINITY;  // reference max (log2 units), always exactly representable in fp16
       float m_in0 = 0.f, m_in1 = 0.f;  // offset baked into S buffer 0 / 1 by the fold (0: none; else m_ref - P_SHIFT)
 
@@ -341,9 +371,12 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float x0 = __uint_as_float(s[2 * j]), x1 = __uint_as_float(s[2 * j + 1]);
-              if (PMODE == 9) {  // timing experiment only: no exponentials at all (skeleton cost)
+#ifdef HN_DEBUG
+              if (PMODE == 9) {  // timing experiment only (debug builds): no exponentials at all (skeleton cost)
                 pk[c * 16 + j] = pack_half2(x0, x1) & 0x3FFF3FFFu;
-              } else if (PMODE >= 5 && poly_pair<PMODE>(j)) {
+              } else
+#endif
+              if (PMODE >= 5 && poly_pair<PMODE>(j)) {
                 pk[c * 16 + j] = ex2_pair_h2(x0, x1);
               } else {
                 const float e0 = (PMODE < 5 && poly_slot<PMODE>(2 * j)) ? ex2_poly(x0) : ex2_mufu(x0);
@@ -485,7 +518,7 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 }
 
 
-template <int KD, int G, int PMODE>
+template <int KD, int G, int PMODE, bool SPLIT>
 int launch_small_t(const AttnArgs& a, cudaStream_t stream) {
   CUtensorMap tmQ, tmZ;
   const CUtensorMapSwizzle swz = KD == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -503,6 +536,7 @@ int launch_small_t(const AttnArgs& a, cudaStream_t stream) {
   p.nsplit = a.nsplit;
   p.n_ltiles = (a.L + BM - 1) / BM;
   p.n_rb = p.n_ltiles * a.H;
+  p.q_lo_off = a.q_lo_off;
   p.ctas_per_stream = (p.n_rb + G - 1) / G;
   p.tiles_total = static_cast<int>((a.N + BT - 1) / BT);
   p.N = a.N;
@@ -511,34 +545,43 @@ int launch_small_t(const AttnArgs& a, cudaStream_t stream) {
   p.part_acc = a.part_acc;
   p.part_ml = a.part_ml;
   // at least 120 KB so that a second CTA can never share the SM (each CTA allocates all 512 TMEM columns)
-  constexpr int SMEM_NEED = G * BM * KD * 2 + NST * BT * KD * 2 + 1024;
+  constexpr int SMEM_NEED = (SPLIT ? 2 : 1) * (G * BM * KD * 2 + NST * BT * KD * 2) + 1024;
   constexpr int SMEM = SMEM_NEED > 120 * 1024 ? SMEM_NEED : 120 * 1024;
-  HN_CHECK_CUDA(
-      cudaFuncSetAttribute(attn_small_kernel<KD, G, PMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
   const long grid = static_cast<long>(p.ctas_per_stream) * a.batch * a.nsplit;
   HN_REQUIRE(grid > 0 && grid < 2147483647L, "attention: grid too large");
   p.mask_words = p.tiles_total;
+  p.trace = nullptr;
+#ifdef HN_DEBUG
   p.trace = g_trace_buf;
   if (g_trace_buf != nullptr && (PMODE == 6 || PMODE == 9)) {
-    HN_CHECK_CUDA(cudaFuncSetAttribute(attn_small_kernel<KD, G, PMODE, true>,
+    HN_CHECK_CUDA(cudaFuncSetAttribute(attn_small_kernel<KD, G, PMODE, SPLIT, true>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    HN_CHECK_CUDA(launch_k(attn_small_kernel<KD, G, PMODE, true>, dim3(static_cast<unsigned>(grid)),
+    HN_CHECK_CUDA(launch_k(attn_small_kernel<KD, G, PMODE, SPLIT, true>, dim3(static_cast<unsigned>(grid)),
                            dim3((5 * G + 1) * 32), SMEM, stream, tmQ, tmZ, p));
-  } else
-    HN_CHECK_CUDA(launch_k(attn_small_kernel<KD, G, PMODE, false>, dim3(static_cast<unsigned>(grid)),
-                           dim3((5 * G + 1) * 32), SMEM, stream, tmQ, tmZ, p));
+    return 0;
+  }
+#endif
+  HN_CHECK_CUDA(cudaFuncSetAttribute(attn_small_kernel<KD, G, PMODE, SPLIT, false>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+  HN_CHECK_CUDA(launch_k(attn_small_kernel<KD, G, PMODE, SPLIT, false>, dim3(static_cast<unsigned>(grid)),
+                         dim3((5 * G + 1) * 32), SMEM, stream, tmQ, tmZ, p));
   HN_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 }  // namespace
 
 static int poly_mode() {
-  static int pmode = -1;  // tuning knob (HN_POLY_MODE=0..9): share of the exponentials on the FMA pipe
+#ifdef HN_DEBUG
+  static int pmode = -1;  // tuning knob of debug builds (HN_POLY_MODE): share of the exponentials on the FMA pipe
   if (pmode < 0) {
     const char* e = getenv("HN_POLY_MODE");
     pmode = (e != nullptr && e[0] >= '0' && e[0] <= '9') ? e[0] - '0' : 6;
   }
   return pmode;
+#else
+  return 6;  // every other column pair on the FMA pipe (half2 polynomial)
+#endif
 }
 
 int small_attention_groups(int kd) { return kd == 32 ? 3 : 2; }
@@ -571,29 +614,38 @@ int small_attention_pick_nsplit(int batch, int L, int H, long N, int kd) {
 
 template <int PMODE>
 static int launch_small_variant(const AttnArgs& a, cudaStream_t stream) {
-  if (a.kd == 64) return launch_small_t<64, 2, PMODE>(a, stream);
-  return launch_small_t<32, 3, PMODE>(a, stream);
+  if (a.precise) {
+    if (a.kd == 64) return launch_small_t<64, 2, PMODE, true>(a, stream);
+    return launch_small_t<32, 3, PMODE, true>(a, stream);
+  }
+  if (a.kd == 64) return launch_small_t<64, 2, PMODE, false>(a, stream);
+  return launch_small_t<32, 3, PMODE, false>(a, stream);
 }
 
 int launch_small_attention(const AttnArgs& a, cudaStream_t stream) {
   HN_REQUIRE(a.batch > 0 && a.L > 0 && a.H > 0 && a.N > 0 && a.nsplit > 0, "attention: empty problem");
   HN_REQUIRE(a.kd == 32 || a.kd == 64, "attention: shared-context rows must be 32 or 64 wide");
-  HN_REQUIRE(a.kv_ld == a.kd, "attention: shared-context rows must be dense");
+  HN_REQUIRE(a.kv_ld == (a.precise ? 2 * a.kd : a.kd), "attention: shared-context rows must be dense ([hi | lo] when split)");
+  HN_REQUIRE(!a.precise || a.q_lo_off >= a.H * a.kd, "attention: split Q' rows need the lo-part offset");
   HN_REQUIRE(a.q_ld % 8 == 0, "attention: row pitches must be multiples of 8 elements");
   HN_REQUIRE(a.N < (1L << 31), "attention: token axis too long");
   HN_REQUIRE(a.c_ones >= 1 && a.c_ones < a.kd, "attention: ones column must lie inside the context row");
   switch (poly_mode()) {
+#ifdef HN_DEBUG
     case 0: return launch_small_variant<0>(a, stream);
     case 5: return launch_small_variant<5>(a, stream);
     case 7: return launch_small_variant<7>(a, stream);
     case 9: return launch_small_variant<9>(a, stream);
+#endif
     default: return launch_small_variant<6>(a, stream);
   }
 }
 
 }  // namespace hn
 
-// debug hook (not part of include/healnet_b200.h): timeline buffer for tools/trace_attn.py, 2*MAXG*TR_NT*TR_NP int64
+#ifdef HN_DEBUG
+// debug builds only (make EXTRA=-DHN_DEBUG): timeline buffer for tools/trace_attn.py, 2*MAXG*TR_NT*TR_NP int64
 extern "C" __attribute__((visibility("default"))) void hn_debug_set_trace(void* dev_buf) {
   hn::g_trace_buf = static_cast<long long*>(dev_buf);
 }
+#endif

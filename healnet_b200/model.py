@@ -268,7 +268,10 @@ class HealNet(nn.Module):
         self._export_registered = False
         # token-axis sharding across GPUs (enable_token_sharding): (rank, world, min_tokens) or None
         self._token_shard = None
-        self._exchange = None   # (own device ptr, [peer ptrs], bytes, max batch)
+        self._exchange = None   # (own device ptr, [peer ptrs], bytes, max batch, handle)
+        self._exchange_group = None
+        self._xerr = None       # (pinned int32 flag, event): asynchronous read-back of the peer-wait time-out flag
+        self.token_sharding_timeout_s = 30.0
         # opt-in: materialise every Attention module's softmax matrix on each forward (reference: always on,
         # healnet.py:420). Off by default: (b*h, L, N) fp32 is 9.87 GB per sample and layer at the README shapes.
         self.export_attention_weights = False
@@ -281,7 +284,8 @@ class HealNet(nn.Module):
 
     # ------------------------------------------------------------------------------------------------ native
     _NATIVE_DEFAULTS = dict(_handle=None, _handle_dev=None, _weights_sig=None, _staged=(), _workspace=None,
-                            _copy_stream=None, _export_registered=False)
+                            _copy_stream=None, _export_registered=False, _exchange=None, _token_shard=None,
+                            _exchange_group=None, _xerr=None)
 
     def __getstate__(self):
         """copy.deepcopy / pickle / torch.save(model): the native handle, staged weights and workspace are
@@ -298,15 +302,21 @@ class HealNet(nn.Module):
         except Exception:
             pass
 
-    def _release(self):
+    def _release_exchange(self):
         if getattr(self, "_exchange", None) is not None:
             lib = load_library()
             mine, bufs = self._exchange[0], self._exchange[1]
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()   # no kernel of ours may still be reading a peer mapping
             for p in bufs:
                 if p != mine:
                     lib.hn_exchange_close(p)
             lib.hn_exchange_free(mine)
             self._exchange = None
+            self._xerr = None
+
+    def _release(self):
+        self._release_exchange()
         if getattr(self, "_handle", None) is not None:
             load_library().hn_destroy(self._handle)
             self._handle = None
@@ -479,8 +489,14 @@ class HealNet(nn.Module):
                         self._warn_once(("mask", i), f"modality {i}: mask has {mask_tokens} tokens, modality has "
                                         f"{n_tok}; its cross-attention is skipped (reference behaviour)")
                         staged[i] = None
-            if mask_tokens == 1 and any(t is not None and t.numel() // (batch * t.shape[-1]) != 1 for t in staged):
-                raise NotImplementedError("a single-token mask broadcast over longer modalities is not supported")
+        nan_rows = None
+        if mask_dev is not None and mask_tokens == 1:
+            # a (b, 1) mask broadcasts over the token axis of EVERY modality (healnet.py:411-415): True keeps all tokens
+            # (a no-op), False masks all of them, and a fully masked softmax row is NaN in the reference
+            # (-finfo.max / 0.5 = -inf), which then spreads over that sample's whole latent array. Same result here:
+            # run unmasked, NaN the samples whose mask is False.
+            nan_rows = mask_dev[:, 0] == 0
+            mask_dev, mask_tokens = None, 0
 
         want_latents = return_embeddings or not hp["final_classifier_head"]
         with torch.cuda.device(dev):
@@ -488,6 +504,8 @@ class HealNet(nn.Module):
             self._sync_native(dev, stream)
             out = self._launch(lib, staged, ready, axis_sizes, skip_self, mask_dev, mask_tokens, batch, want_latents,
                                dev, stream, tok_begin, tok_count)
+            if nan_rows is not None and any(t is not None for t in staged):
+                out = torch.where(nan_rows.view(-1, *([1] * (out.dim() - 1))), torch.full_like(out, float("nan")), out)
         if ret_dtype is not None and not ret_dtype.is_floating_point:
             ret_dtype = torch.float32
         if self.keep_output_on_device:
@@ -558,10 +576,12 @@ class HealNet(nn.Module):
             for i in range(M):
                 events[i] = ready[i].cuda_event if (ready[i] is not None and staged[i] is not None) else None
         if split:
+            self._poll_token_sharding(lib, None)      # an earlier forward's flag, if its read-back has landed
             check(lib.hn_forward_split(self._handle, batch, ptrs, events, sizes, tb, tc, skip,
                                        mask_dev.data_ptr() if mask_dev is not None else None,
                                        mask_tokens, lat_ptr, log_ptr, self._workspace.data_ptr(),
                                        self._workspace.numel(), stream), "hn_forward_split")
+            self._poll_token_sharding(lib, stream)    # enqueue the read-back of this forward's flag
         else:
             check(lib.hn_forward_ex(self._handle, batch, ptrs, events, sizes, skip,
                                     mask_dev.data_ptr() if mask_dev is not None else None,
@@ -593,12 +613,42 @@ class HealNet(nn.Module):
         """Back to the replicated forward (the exchange buffers stay mapped until the module is released)."""
         self._token_shard = None
 
+    def _poll_token_sharding(self, lib, stream, wait: bool = False) -> None:
+        """Raises if a combine kernel of an earlier token-sharded forward gave up waiting for a peer (its outputs were
+        overwritten with NaN). The flag travels back through a stream-ordered copy into pinned memory; `wait=False`
+        only looks at copies that have already completed, so the hot path never synchronises."""
+        if self._xerr is not None:
+            flag, ev = self._xerr
+            if wait:
+                ev.synchronize()
+            if ev.query():
+                self._xerr = None
+                if int(flag.item()) != 0:
+                    raise _lib.HealNetLibraryError(
+                        "token-sharded forward: a peer did not publish its attention partials within "
+                        f"{self.token_sharding_timeout_s:.0f} s (token_sharding_timeout_s); the outputs of that "
+                        "forward are NaN. All ranks must call forward() with the same inputs in the same order.")
+        if stream is not None and self._xerr is None and self._exchange is not None:
+            flag = torch.zeros(1, dtype=torch.int32).pin_memory()
+            check(lib.hn_exchange_error_async(self._handle, flag.data_ptr(), stream), "hn_exchange_error_async")
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            self._xerr = (flag, ev)
+
+    def check_token_sharding(self) -> None:
+        """Blocking form of the check every token-sharded forward performs lazily: waits for the outstanding forward
+        and raises HealNetLibraryError if a peer wait timed out."""
+        if self._exchange is None:
+            return
+        self._poll_token_sharding(load_library(), None, wait=True)
+
     def _ensure_exchange(self, lib, batch: int) -> None:
         """Allocates this rank's exchange buffer, swaps CUDA IPC handles with the peers (one all-gather of 64 bytes
         per rank on the host side) and registers the peer-mapped pointers with the native handle."""
         import torch.distributed as dist
         if self._exchange is not None and self._exchange[3] >= batch and self._exchange[4] is self._handle:
             return
+        self._release_exchange()   # a larger batch / a new handle: unmap and free the old buffers first
         rank, world, _ = self._token_shard
         cap = max(batch, self._exchange_max_batch)
         nbytes = lib.hn_exchange_bytes(self._handle, cap)
@@ -617,6 +667,7 @@ class HealNet(nn.Module):
                 check(lib.hn_exchange_open(raw, ctypes.byref(peer)), "hn_exchange_open")
                 bufs[r] = peer.value
         check(lib.hn_set_exchange(self._handle, rank, world, bufs, nbytes), "hn_set_exchange")
+        check(lib.hn_set_exchange_timeout(self._handle, float(self.token_sharding_timeout_s)), "hn_set_exchange_timeout")
         dist.barrier(group=self._exchange_group)   # nobody publishes before everybody has mapped everybody
         self._exchange = (mine.value, [bufs[r] for r in range(world)], nbytes, cap, self._handle)
 
@@ -671,14 +722,15 @@ class HealNet(nn.Module):
                 self._sync_native(dev, torch.cuda.current_stream(dev).cuda_stream)
         check(load_library().hn_profile_enable(self._handle, 1 if on else 0), "hn_profile_enable")
 
-    def read_kernel_timing(self, modality: int) -> dict:
-        """Device time / launches / executed tensor FLOPs / exponentials of modality `modality`'s cross-attention
-        kernels in the last forward. Synchronise the stream first."""
+    def read_kernel_timing(self, modality: int, kind: int = 0) -> dict:
+        """Device time / launches / executed and useful (unpadded) tensor FLOPs / exponentials of one class of launches
+        of modality `modality` in the last forward: kind 0 = streaming cross-attention kernel, 1 = K/V projection GEMM
+        (generic path), 2 = context-row build. Synchronise the stream first."""
         ms, n = ctypes.c_float(), ctypes.c_int()
-        fl, ex = ctypes.c_double(), ctypes.c_double()
-        check(load_library().hn_profile_read(self._handle, modality, ctypes.byref(ms), ctypes.byref(n),
-                                             ctypes.byref(fl), ctypes.byref(ex)), "hn_profile_read")
-        return dict(ms=ms.value, launches=n.value, flops=fl.value, exps=ex.value)
+        fl, fu, ex = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+        check(load_library().hn_profile_read(self._handle, kind, modality, ctypes.byref(ms), ctypes.byref(n),
+                                             ctypes.byref(fl), ctypes.byref(fu), ctypes.byref(ex)), "hn_profile_read")
+        return dict(ms=ms.value, launches=n.value, flops=fl.value, flops_useful=fu.value, exps=ex.value)
 
     def get_attention_weights(self) -> List[Optional[torch.Tensor]]:
         """One entry per Attention module, in module order (healnet.py:252-262): the (b*h, L, N) softmax matrix of

@@ -119,7 +119,8 @@ HN_API int hn_forward_ex(hn_handle* h, int batch, const void* const* modality_pt
  * Set-up, once per process group:  bytes = hn_exchange_bytes(h, max_batch); hn_exchange_alloc(bytes, &mine, handle);
  * all-gather the 64-byte handles; hn_exchange_open() the peers'; hn_set_exchange(h, rank, world, bufs, bytes).
  * All ranks must issue the same sequence of hn_forward_split calls. A peer that never shows up makes the waiting
- * kernels give up after ~2 s (hn_exchange_error reports it) instead of hanging the GPU. */
+ * kernels give up after the exchange time-out (~30 s, hn_set_exchange_timeout) instead of hanging the GPU: the outputs
+ * of that forward are NaN and hn_exchange_error* report it. */
 HN_API size_t hn_exchange_bytes(const hn_handle* h, int batch);
 HN_API int hn_exchange_alloc(size_t bytes, void** dev_ptr, unsigned char* ipc_handle_out /* 64 bytes */);
 HN_API int hn_exchange_open(const unsigned char* ipc_handle /* 64 bytes */, void** peer_ptr);
@@ -128,6 +129,11 @@ HN_API int hn_exchange_free(void* dev_ptr);
 HN_API int hn_set_exchange(hn_handle* h, int rank, int world, void* const* bufs /* [world], own buffer at [rank] */,
                            size_t bytes);
 HN_API int hn_exchange_error(const hn_handle* h, int* error_out);  /* synchronous read of the time-out flag */
+/* stream-ordered read of the flag into PINNED host memory (check it once a later event on the stream has completed) */
+HN_API int hn_exchange_error_async(const hn_handle* h, int* pinned_host_out, void* cuda_stream);
+/* how long a combine kernel waits for a peer's partials before giving up (default ~30 s). A forward whose wait timed
+ * out overwrites its outputs with NaN and leaves the flag set until hn_set_exchange is called again. */
+HN_API int hn_set_exchange_timeout(hn_handle* h, double seconds);
 HN_API size_t hn_workspace_bytes_split(const hn_handle* h, int batch, const int* axis_sizes, const long* tok_count);
 HN_API int hn_forward_split(hn_handle* h, int batch, const void* const* modality_ptrs,
                             void* const* modality_ready_events, const int* axis_sizes, const long* tok_begin,
@@ -147,12 +153,15 @@ HN_API int hn_last_launch_count(const hn_handle* h);
  * sample and layer at the README shapes), so export is off by default and the caller sizes the buffers. */
 HN_API int hn_set_attention_export(hn_handle* h, int layer, int module, float* dev_out);
 
-/* Measurement hook (bench.py roofline): when enabled, hn_forward brackets every cross-attention kernel launch
- * with CUDA events on its own stream. After the caller has synchronised the stream, hn_profile_read sums, for one
- * modality, the device time of those launches in the LAST forward, their count, the tensor-core FLOPs they executed
- * (padded tiles included) and the softmax exponentials they evaluated. */
+/* Measurement hook (bench.py roofline): when enabled, hn_forward brackets the heavy launches with CUDA event pairs on
+ * its own stream. kind 0 = the streaming cross-attention kernel of a modality, 1 = the K/V projection GEMM of the
+ * generic (wide-context) path, 2 = the context-row build (Fourier tables + standardisation). After the caller has
+ * synchronised the stream, hn_profile_read sums, for one (kind, modality), the device time of those launches in the
+ * LAST forward, their count, the tensor-core FLOPs they executed (padded tiles included), the unpadded algorithmic
+ * FLOPs of the same contractions (SURVEY.md section 8d accounting) and the softmax exponentials evaluated. */
 HN_API int hn_profile_enable(hn_handle* h, int on);
-HN_API int hn_profile_read(hn_handle* h, int modality, float* ms, int* launches, double* flops, double* exps);
+HN_API int hn_profile_read(hn_handle* h, int kind, int modality, float* ms, int* launches, double* flops_executed,
+                           double* flops_useful, double* exps);
 
 /* Replaces Attention.forward (healnet.py:400-426) for the stand-alone `Attention` module:
  *   out = LeakyReLU_0.01( softmax(2 q k^T / sqrt(dim_head)) v  Wo^T + bo ),  q = x Wq^T, [k,v] = ctx Wkv^T.
@@ -178,26 +187,26 @@ HN_API int hn_op_gemm(const void* A, const void* B, int M, int N, int K, int lda
 /* y rows = [hi (seg cols) | lo at column lo_seg (0: none)] of LayerNorm(x) * gamma + beta, zero padded to seg. */
 HN_API int hn_op_layernorm_f16(const float* x, int ldx, const float* gamma, const float* beta, void* y, int ldy,
                                int seg, int lo_seg, long rows, int D, void* cuda_stream);
-/* Fourier tables + standardised context rows z (fp16). small != 0: dense (batch, N, ldz) rows, ldz = 32 or 64,
- * with the ones column at index C < ldz; else (batch*N, ldz). tab: scratch of sum(axis sizes)*(2*bands+1) floats. */
+/* Fourier tables + standardised context rows z (fp16). small == 1: dense (batch, N, ldz) rows, ldz = 32 or 64,
+ * with the ones column at index C < ldz; small == 2: the same as split rows (batch, N, 2 ldz) = [hi | lo],
+ * lo = fp16(value - hi) (what the forward streams); small == 0: (batch*N, ldz).
+ * tab: scratch of sum(axis sizes)*(2*bands+1) floats. */
 HN_API int hn_op_build_context(const float* raw, void* z, int ldz, int small, int batch, int c_raw, int n_axes,
                         const int* axis_sizes, int n_bands, float max_freq, int fourier, float* tab,
                         void* cuda_stream);
 /* token-axis split count the library would choose; small_kd = 32 | 64 for the small-context kernel, 0 generic */
 HN_API int hn_op_attention_nsplit(int batch, int L, int H, long N, int small_kd);
-/* Streaming attention partials + combine. shared_kv != 0: small-C path (Q rows kv_ld = 32 | 64 wide per head,
- * KV = z rows whose column c_ones is 1.0; Q column c_ones must be 0); part_acc rows are kv_ld (small-C) or 64
- * (generic: head_pitch = 64 | 128) floats wide; head_pitch is the column pitch of one head in Q / K / V / O. */
+/* Streaming attention partials + combine. shared_kv == 1: small-C path (Q rows kd = kv_ld = 32 | 64 wide per head,
+ * KV = z rows whose column c_ones is 1.0; Q column c_ones must be 0); shared_kv == 3: the same on split operands —
+ * Q' rows [hi (H kd) | lo at column q_ld / 2], z rows [hi (kd) | lo (kd)] (kv_ld = 2 kd), scores from three fp16
+ * products (the forward's mode); part_acc rows are kd (small-C) or 64 (generic: head_pitch = 64 | 128) floats wide;
+ * head_pitch is the column pitch of one head in Q / K / V / O. */
 HN_API int hn_op_attention(const void* Q, int q_ld, const void* KV, long kv_ld, int k_col0, int v_col0, int shared_kv,
                            int c_ones, int head_pitch, int batch, int L, int H, long N, int nsplit, const uint8_t* mask,
                            void* mask_bits_scratch, float* part_acc, float* part_ml, void* cuda_stream);
 HN_API int hn_op_combine(const float* part_acc, const float* part_ml, int batch, int nsplit, int H, int L, int small_C,
                          int zw, int dh, int head_pitch, const float* Wv, const float* bv, void* O, int o_ld,
                          void* cuda_stream);
-/* test-only: one-tile UMMA/TMA/TMEM convention probe (probe.cu) */
-HN_API int hn_debug_probe(const void* Q, const void* K, const void* V, int kd, int vd, float* S_out, float* U_out,
-                   const int* overrides, void* cuda_stream);
-
 #ifdef __cplusplus
 }
 #endif

@@ -113,6 +113,13 @@ def test_build_context_matches_reference_encoding(axes, c):
                                    tab.data_ptr(), st) == 0
     torch.testing.assert_close(z[..., :C].float().cpu(), want, rtol=2e-3, atol=2e-3)  # fp16 storage
     assert bool((z[..., C] == 1).all()) and bool((z[..., C + 1:] == 0).all())
+    # split rows [hi | lo] (what the forward streams): hi + lo reproduces the fp32 standardisation
+    zs = torch.full((b, N, 2 * zw), float("nan"), dtype=torch.float16, device="cuda")
+    assert lib.hn_op_build_context(raw.data_ptr(), zs.data_ptr(), zw, 2, b, c, len(axes), sizes, bands, max_freq, 1,
+                                   tab.data_ptr(), st) == 0
+    assert torch.equal(zs[..., :zw], z)
+    torch.testing.assert_close((zs[..., :C].float() + zs[..., zw:zw + C].float()).cpu(), want, rtol=2e-5, atol=2e-5)
+    assert bool((zs[..., zw + C:] == 0).all())
     ldz = (C + 7) // 8 * 8
     z2 = torch.full((b * N, ldz), float("nan"), dtype=torch.float16, device="cuda")
     assert lib.hn_op_build_context(raw.data_ptr(), z2.data_ptr(), ldz, 0, b, c, len(axes), sizes, bands, max_freq, 1,
@@ -163,38 +170,59 @@ def test_generic_attention_kernel(b, H, L, N, nsplit, masked):
     torch.testing.assert_close(out.float(), want, rtol=3e-3, atol=3e-3)  # fp16 P and fp16 output
 
 
+def _split_cols(x):
+    """(..., w) fp32 -> (..., 2w) fp16 [hi | lo]."""
+    hi = x.half()
+    return torch.cat([hi, (x - hi.float()).half()], dim=-1)
+
+
 @pytest.mark.parametrize("kd,C", [(32, 18), (32, 31), (64, 50)])
 @pytest.mark.parametrize("b,H,L,N", [(1, 1, 128, 64), (2, 8, 512, 30000), (1, 3, 200, 4100), (2, 2, 130, 777)])
 @pytest.mark.parametrize("masked", [False, True])
 def test_small_context_attention_kernel(kd, C, b, H, L, N, masked):
     """xattn_small.cu: Q' (b, L, H*kd) with column C zero, z (b, N, kd) with column C one; accumulator column C
-    must come back as the softmax denominator. Also compares the first-generation kernel on the same inputs."""
+    must come back as the softmax denominator. Variant 1: single fp16 operands; variant 3 (the forward's mode):
+    split operands, whose scores must match an fp64 product of the UNROUNDED inputs much more tightly."""
     lib, st = _lib_stream()
     g = torch.Generator(device="cuda").manual_seed(N + C)
-    q = torch.zeros(b, L, H, kd, device="cuda")
-    q[..., :C] = torch.randn(b, L, H, C, device="cuda", generator=g) * 0.7
-    q = q.reshape(b, L, H * kd).half()
-    z = torch.zeros(b, N, kd, device="cuda")
-    z[..., :C] = torch.randn(b, N, C, device="cuda", generator=g)
-    z[..., C] = 1.0
-    z = z.half()
+    q32 = torch.zeros(b, L, H, kd, device="cuda")
+    q32[..., :C] = torch.randn(b, L, H, C, device="cuda", generator=g) * 0.7
+    z32 = torch.zeros(b, N, kd, device="cuda")
+    z32[..., :C] = torch.randn(b, N, C, device="cuda", generator=g)
+    z32[..., C] = 1.0
     mask = None
     if masked:
         mask = torch.rand(b, N, device="cuda", generator=g) > 0.4
         mask[:, :2] = True
         if N > 200:
             mask[0, 64:192] = False  # whole tiles masked out
-    qh = q.float().view(b, L, H, kd).permute(0, 2, 1, 3)
-    zz = z.float()[:, None].expand(b, H, N, kd)
-    want = _attention_ref(qh, zz, zz, mask)  # (b,H,L,kd): columns < C = sum p z, column C = 1
-    for variant in (1, 2):
-        nsplit = lib.hn_op_attention_nsplit(b, L, H, N, kd if variant == 1 else 0)
+    for variant in (1, 3):
+        if variant == 1:
+            q = q32.reshape(b, L, H * kd).half()
+            z = z32.half()
+            q_ld, kv_ld = H * kd, kd
+            q_ref, z_ref = q.float().view(b, L, H, kd), z.float()
+        else:
+            qs = _split_cols(q32)                                          # (b, L, H, 2kd)
+            q = torch.cat([qs[..., :kd].reshape(b, L, H * kd), qs[..., kd:].reshape(b, L, H * kd)], dim=-1).contiguous()
+            z = _split_cols(z32).contiguous()
+            q_ld, kv_ld = 2 * H * kd, 2 * kd
+            q_ref, z_ref = q32, z32
+        qh = q_ref.permute(0, 2, 1, 3)
+        zz = z_ref[:, None].expand(b, H, N, kd)
+        # values: the kernel contracts P with the hi part of z
+        zv = z32.half().float()[:, None].expand(b, H, N, kd)
+        s = qh.double() @ zz.double().transpose(-1, -2)
+        if mask is not None:
+            s = s.masked_fill(~mask[:, None, None, :], float("-inf"))
+        want = (torch.softmax(s * math.log(2.0), dim=-1) @ zv.double()).float()  # columns < C = sum p z, column C = 1
+        nsplit = lib.hn_op_attention_nsplit(b, L, H, N, kd)
         n_lt = (L + 127) // 128
         acc = torch.full((b * nsplit * H * n_lt * 128 * kd,), float("nan"), device="cuda")
         ml = torch.full((b * nsplit * H * n_lt * 128 * 2,), float("nan"), device="cuda")
         bits = torch.zeros(b * ((N + 63) // 64), dtype=torch.int64, device="cuda")
         mk = mask.to(torch.uint8).contiguous() if masked else None
-        rc = lib.hn_op_attention(q.data_ptr(), H * kd, z.data_ptr(), kd, 0, 0, variant, C, 64, b, L, H, N, nsplit,
+        rc = lib.hn_op_attention(q.data_ptr(), q_ld, z.data_ptr(), kv_ld, 0, 0, variant, C, 64, b, L, H, N, nsplit,
                                  mk.data_ptr() if masked else None, bits.data_ptr(), acc.data_ptr(), ml.data_ptr(), st)
         assert rc == 0, _lib.last_error()
         # combine with an identity V projection: Wv = I (C x C), bias 0 -> O[:, h*64 + d] = u_d / den for d < C
@@ -210,7 +238,49 @@ def test_small_context_attention_kernel(kd, C, b, H, L, N, masked):
         torch.testing.assert_close(got, want[..., :dh], rtol=3e-3, atol=3e-3)
 
 
-def test_small_context_attention_raises_reference_max():
+def test_small_context_split_scores_are_exact_for_peaked_softmax():
+    """Large-magnitude scores (|s| up to ~60 log2 units) over a long axis: with single fp16 operands the softmax
+    weights are off by |s| 2^-11; the split operands (variant 3) must reproduce the fp64 softmax of the unrounded
+    inputs an order of magnitude more tightly."""
+    lib, st = _lib_stream()
+    b, H, L, N, kd, C = 1, 2, 128, 40000, 32, 18
+    g = torch.Generator(device="cuda").manual_seed(7)
+    q32 = torch.zeros(b, L, H, kd, device="cuda")
+    q32[..., :C] = torch.randn(b, L, H, C, device="cuda", generator=g) * 3.5
+    z32 = torch.zeros(b, N, kd, device="cuda")
+    z32[..., :C] = torch.randn(b, N, C, device="cuda", generator=g)
+    z32[..., C] = 1.0
+    s = q32.permute(0, 2, 1, 3).double() @ z32[:, None].expand(b, H, N, kd).double().transpose(-1, -2)
+    p = torch.softmax(s * math.log(2.0), dim=-1)
+    want = (p @ z32.half().float()[:, None].expand(b, H, N, kd).double()).float()
+    errs = {}
+    for variant in (1, 3):
+        if variant == 1:
+            q, z, q_ld, kv_ld = q32.reshape(b, L, H * kd).half(), z32.half(), H * kd, kd
+        else:
+            qs = _split_cols(q32)
+            q = torch.cat([qs[..., :kd].reshape(b, L, H * kd), qs[..., kd:].reshape(b, L, H * kd)], dim=-1).contiguous()
+            z, q_ld, kv_ld = _split_cols(z32).contiguous(), 2 * H * kd, 2 * kd
+        nsplit = lib.hn_op_attention_nsplit(b, L, H, N, kd)
+        acc = torch.full((b * nsplit * H * 128 * kd,), float("nan"), device="cuda")
+        ml = torch.full((b * nsplit * H * 128 * 2,), float("nan"), device="cuda")
+        assert lib.hn_op_attention(q.data_ptr(), q_ld, z.data_ptr(), kv_ld, 0, 0, variant, C, 64, b, L, H, N, nsplit, None,
+                                   None, acc.data_ptr(), ml.data_ptr(), st) == 0, _lib.last_error()
+        Wv = torch.zeros(H * C, kd, device="cuda")
+        for h in range(H):
+            Wv[h * C:(h + 1) * C, :C] = torch.eye(C, device="cuda")
+        out = torch.zeros(b * L, 2 * H * 64, dtype=torch.float16, device="cuda")
+        assert lib.hn_op_combine(acc.data_ptr(), ml.data_ptr(), b, nsplit, H, L, C, kd, C, 64, Wv.data_ptr(),
+                                 torch.zeros(H * C, device="cuda").data_ptr(), out.data_ptr(), 2 * H * 64, st) == 0
+        got = out[:, :H * 64].float().view(b, L, H, 64).permute(0, 2, 1, 3)[..., :C]
+        errs[variant] = float((got - want[..., :C]).abs().max())
+    print("peaked softmax, max abs error of sum p z: single fp16", errs[1], "split", errs[3])
+    assert errs[3] < 2.5e-3            # fp16 P and fp16 output remain
+    assert errs[3] < 0.5 * errs[1] or errs[1] < 2.5e-3
+
+
+@pytest.mark.parametrize("variant", [1, 3])
+def test_small_context_attention_raises_reference_max(variant):
     """Scores that keep growing along the token axis force the lazy reference max to be raised many times
     (exact path, accumulator rescale, re-folded offset in Q') — result must still be the exact softmax."""
     lib, st = _lib_stream()
@@ -229,8 +299,13 @@ def test_small_context_attention_raises_reference_max():
     nsplit = 2
     acc = torch.full((b * nsplit * H * 128 * kd,), float("nan"), device="cuda")
     ml = torch.full((b * nsplit * H * 128 * 2,), float("nan"), device="cuda")
-    assert lib.hn_op_attention(q.data_ptr(), H * kd, z.data_ptr(), kd, 0, 0, 1, C, 64, b, L, H, N, nsplit, None, None,
-                               acc.data_ptr(), ml.data_ptr(), st) == 0
+    q_ld, kv_ld = H * kd, kd
+    if variant == 3:  # split layout of the same (already fp16-exact) operands: lo parts are zero
+        q = torch.cat([q, torch.zeros_like(q)], dim=-1).contiguous()
+        z = torch.cat([z, torch.zeros_like(z)], dim=-1).contiguous()
+        q_ld, kv_ld = 2 * H * kd, 2 * kd
+    assert lib.hn_op_attention(q.data_ptr(), q_ld, z.data_ptr(), kv_ld, 0, 0, variant, C, 64, b, L, H, N, nsplit, None,
+                               None, acc.data_ptr(), ml.data_ptr(), st) == 0
     Wv = torch.zeros(H * C, kd, device="cuda")
     for h in range(H):
         Wv[h * C:(h + 1) * C, :C] = torch.eye(C, device="cuda")

@@ -73,6 +73,21 @@ def test_golden_mask(golden):
     torch.testing.assert_close(lat.cpu(), outs["latents"], rtol=RTOL, atol=LAT_ATOL)
 
 
+def test_single_token_mask_broadcasts_over_every_modality():
+    """A (b, 1) mask broadcasts over the token axis of every modality (healnet.py:411-415): True is a no-op, False
+    masks all tokens of that sample -> NaN rows, as in the reference (oracle)."""
+    kw = dict(n_modalities=2, channel_dims=[40, 3], num_spatial_axes=[1, 2], out_dims=3, l_c=32, l_d=64, depth=1)
+    torch.manual_seed(5)
+    model = HealNet(**kw).eval()
+    xs = [torch.rand(3, 1, 40), torch.rand(3, 50, 60, 3)]
+    mask = torch.tensor([[True], [False], [True]])
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    want = O.forward(sd, _cfg(kw), xs, mask=mask)
+    got = model.cuda()([t.cuda() for t in xs], mask=mask.cuda()).cpu()
+    assert bool(torch.isnan(want[1]).all()) and bool(torch.isnan(got[1]).all())
+    torch.testing.assert_close(got[[0, 2]], want[[0, 2]], rtol=RTOL, atol=ATOL)
+
+
 def test_golden_attention_module(golden):
     meta, sd, ins, outs, extra = golden("attention")
     att = Attention(**meta["kwargs"])

@@ -1,0 +1,27 @@
+"""GPU (B200): the reference's OWN unit tests (healnet/tests/test_healnet.py:26-67), unmodified, against the drop-in
+classes — `healnet.models` is resolved to healnet_b200 through the import shim healnet_b200/compat. The test file is
+the copy __graft_entry__.build() places under the git-ignored baseline/_ref/ (the reference tree itself does not
+exist on the GPU box); when neither is present the test is skipped."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CANDIDATES = [os.path.join(ROOT, "baseline", "_ref", "test_healnet.py"),
+              "/root/reference/healnet/tests/test_healnet.py"]
+
+
+@pytest.mark.gpu
+def test_reference_unit_tests_run_unmodified():
+    path = next((p for p in CANDIDATES if os.path.exists(p)), None)
+    if path is None:
+        pytest.skip("reference test file not available (run __graft_entry__.build() where /root/reference exists)")
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([os.path.join(ROOT, "healnet_b200", "compat"), ROOT, env.get("PYTHONPATH", "")])
+    res = subprocess.run([sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", "--rootdir", os.path.dirname(path),
+                          "-c", os.devnull, path], capture_output=True, text=True, timeout=600, env=env,
+                         cwd=os.path.dirname(path))
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "2 passed" in res.stdout, res.stdout[-2000:]
