@@ -367,6 +367,56 @@ def measure_token_sharded(model, shapes, batch, io_dtype, dev, rank, world, time
                                                "over CUDA-IPC peer memory (no NCCL on the data path)")
 
 
+def run_train_step(args):
+    """--mode train: the reference's training step on the module — forward, cross-entropy, backward through the
+    library's hn_backward (healnet/main.py:426-467 without the optimizer) — inputs resident, one GPU. Extra line for
+    SURVEY.md 8 row f2; the headline metric stays the forward."""
+    import torch
+    import torch.nn.functional as F
+    from healnet_b200 import HealNet
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    kwargs, shapes, per_gpu = WORKLOADS[args.workload]
+    batch = args.batch or per_gpu
+    torch.manual_seed(0)
+    model = HealNet(**kwargs).to(dev).train()
+    g = torch.Generator().manual_seed(0)
+    xs = [torch.rand((batch,) + tuple(s), generator=g).to(dev) for s in shapes]
+    y = (torch.arange(batch) % kwargs["out_dims"]).to(dev)
+
+    def step():
+        model.zero_grad(set_to_none=True)
+        loss = F.cross_entropy(model(list(xs)), y)
+        loss.backward()
+        return loss
+
+    for _ in range(max(1, min(args.warmup, 3))):
+        step()
+    torch.cuda.synchronize(dev)
+    fwd0, fwd1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.no_grad():
+        model(list(xs))
+        fwd0.record()
+        for _ in range(args.steps):
+            model(list(xs))
+        fwd1.record()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / args.steps
+    line = dict(metric="HealNet training step (forward + backward) samples/sec", value=batch / (ms * 1e-3),
+                unit="samples/s", n_gpus=1, steps=args.steps, warmup=args.warmup, ms_per_step=ms,
+                ms_forward_only=fwd0.elapsed_time(fwd1) / args.steps, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f32", data="synthetic", loss=float(loss),
+                config=_config(args.workload, kwargs, shapes, batch, batch, "one GPU"),
+                peak_mem_gb=torch.cuda.max_memory_allocated(dev) / 2 ** 30)
+    print(json.dumps(line), flush=True)
+    return 0
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -384,6 +434,7 @@ def run_gpu_arm(args):
     batch = args.batch or per_gpu
     peaks = load_peaks()
 
+    torch.set_grad_enabled(False)   # inference benchmark (a forward under autograd would also record the backward's tape)
     torch.manual_seed(0)
     model = HealNet(**kwargs).eval().to(dev)
     io_dtype = torch.bfloat16 if args.workload == "cfg3" else torch.float32
@@ -566,10 +617,14 @@ def main():
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
                     help="--impl reference only: cpu (default, the driver's arm) or cuda (PyTorch eager on one GPU)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--mode", default="forward", choices=["forward", "train"],
+                    help="forward (the benchmarked metric) or train (forward + backward step, extra line)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.mode == "train":
+        return run_train_step(args)
     return run_gpu_arm(args)
 
 

@@ -67,6 +67,13 @@ SIGNATURES = {
     "hn_forward_split": (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int), POINTER(c_long),
                                  POINTER(c_long), POINTER(c_int), c_void_p, c_long, c_void_p, c_void_p, c_void_p,
                                  c_size_t, c_void_p]),
+    "hn_tape_bytes": (c_size_t, [c_void_p, c_int, POINTER(c_int)]),
+    "hn_backward_scratch_bytes": (c_size_t, [c_void_p, c_int, POINTER(c_int)]),
+    "hn_forward_train": (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int), POINTER(c_int),
+                                 c_void_p, c_long, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
+    "hn_set_grads": (c_int, [c_void_p, c_int, c_int, POINTER(c_void_p), c_int]),
+    "hn_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p, c_size_t,
+                            c_void_p]),
     "hn_last_launch_count": (c_int, [c_void_p]),
     "hn_set_attention_export": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "hn_profile_enable": (c_int, [c_void_p, c_int]),

@@ -10,6 +10,8 @@
 
 #include "../../include/healnet_b200.h"
 #include "common.cuh"
+#include "bwd.cuh"
+#include "handle.cuh"
 #include "pack.cuh"
 
 namespace hn {
@@ -19,103 +21,11 @@ thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
 const char* get_error() { return g_error.c_str(); }
 
-namespace {
-
-// head pitch: every head occupies 64 (dim_head <= 64) or 128 columns of Q / K / V / O, zero padded
-constexpr int MAX_DIM_HEAD = 128;
-inline int head_pitch(int dim_head) { return dim_head <= 64 ? 64 : 128; }
-constexpr float LOG2E = 1.4426950408889634074f;
-
-// bump allocator over a caller-provided (or handle-owned) device buffer; 256-byte aligned pieces
-struct Arena {
-  char* base = nullptr;
-  size_t off = 0;
-  template <typename T>
-  T* take(size_t count) {
-    off = (off + 255) & ~size_t(255);
-    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
-    off += count * sizeof(T);
-    return p;
-  }
-};
-
-struct AttnPacked {     // one PreNorm(Attention) module
-  bool small = false;   // reassociated small-context path (cross-attention with C <= 63)
-  int zw = 0;           // small path: width of a z row (32 or 64)
-  int C = 0;            // context width (cross) or D (self)
-  // generic / self
-  // all fp16 weight rows are split [hi (seg cols) | lo (seg cols)], seg = round_up(K, 64)
-  __half* Wq = nullptr;     // cross generic: [H*64][2 segD] scaled;  self: [3*lH*64][2 segD] (Q scaled | K | V)
-  __half* Wkv = nullptr;    // cross generic: [2*H*64][2 segC], context-LN gamma folded
-  float* bkv = nullptr;     // cross generic: [2*H*64], context-LN beta folded (K part zero: it cancels in softmax)
-  // small (used when the token axis is long; short axes take the generic precise path whatever C is)
-  __half* WqS = nullptr;    // [H*zw][2 segD]  Wk^T Wq reassociated, gamma and scale folded
-  float* Wv = nullptr;      // [I][zw]  gamma folded
-  float* bv = nullptr;      // [I]      beta folded
-  __half* WoS = nullptr;    // [D][2 seg(H*zw)]  Wo . Wv' folded (split hi | lo): the small path's out-projection weight
-  float* boS = nullptr;     // [D]      bo + Wo . bv
-  __half* Wo = nullptr;     // [D][2 * H*64] head-padded columns
-};
-struct FFPacked {
-  __half* W1 = nullptr;  // [8D][2 segD] rows interleaved (a_j, g_j)
-  float* b1 = nullptr;   // [8D] interleaved
-  __half* W2 = nullptr;  // [D][2 seg4D]
-};
-struct SlotKey {
-  std::vector<const void*> ptrs;
-  bool operator<(const SlotKey& o) const { return ptrs < o.ptrs; }
-};
-
-}  // namespace
 }  // namespace hn
 
 using namespace hn;
 
-struct hn_handle {
-  hn_desc d;
-  int M = 0, I = 0, lI = 0;
-  int hpx = 64, hpl = 64;         // head pitch of the cross / latent attention (64 or 128 columns per head)
-  int segD = 0, seg4D = 0;        // hi/lo segment widths of D-wide / 4D-wide split operands (multiples of 64)
-  int C[HN_MAX_MODALITIES];       // context width per modality
-  // registered fp32 parameters: index (layer + 1) * slots_per_layer + slot
-  int slots_per_layer = 0;
-  std::vector<std::vector<const float*>> w;
-  // packed store
-  void* packed = nullptr;
-  size_t packed_bytes = 0;
-  bool packed_valid = false;
-  std::vector<AttnPacked> attn;   // [layer][M + 1] (index M = latent self-attention)
-  std::vector<FFPacked> ff;       // [layer][M + 1]
-  int launches = 0;
-  // optional per-launch timing of the cross-attention kernels (bench.py roofline): CUDA event pairs on the
-  // forward's own stream, one pair per (layer, modality), read back after the caller synchronises
-  // opt-in attention-weight export buffers, index layer * (M + 1) + module (M = latent self-attention); null = off
-  std::vector<float*> export_ptrs;
-  bool profile = false;
-  std::vector<cudaEvent_t> ev;          // 2 per slot
-  std::vector<int> ev_mod;              // modality of each recorded slot in the last forward
-  std::vector<int> ev_kind;             // 0 cross-attention kernel, 1 K/V projection GEMM, 2 context-row build
-  std::vector<double> ev_flops;         // tensor-core FLOPs the launch executed (padded tiles included)
-  std::vector<double> ev_useful;        // unpadded algorithmic FLOPs of the same launch
-  std::vector<double> ev_exps;          // softmax exponentials the launch evaluated
-  // token-axis sharding across GPUs (hn_set_exchange): peer-mapped exchange buffers, own rank included
-  int x_rank = 0, x_world = 0;
-  char* x_bufs[HN_MAX_PEERS] = {};
-  size_t x_bytes = 0;
-  unsigned long long x_seq = 0;         // exchanges published so far (all ranks advance in lock step)
-  long long x_timeout_clk = 60000000000LL;  // peer-wait bound in SM clocks (hn_set_exchange_timeout)
-};
-
 namespace {
-
-int slot_index(const hn_handle* h, int layer, int slot) { return (layer + 1) * h->slots_per_layer + slot; }
-
-int ctx_ld(int C) { return round_up(C, 8); }
-int seg_of(int K) { return round_up(K, 64); }
-// Token axes up to this length are never streamed by the small-context kernel nor sharded across GPUs. (Round 1 also
-// used it as the limit of the precise — split hi/lo — attention; the full-size peaked-softmax parity cases showed that
-// single fp16 score operands are not enough on long axes either, so every attention now runs precise.)
-constexpr long PRECISE_MAX_TOKENS = 2048;
 
 // sizes (or carves, when arena.base != null) the packed store; dedupes tied layers by pointer identity
 int plan_packed(hn_handle* h, Arena& ar) {
@@ -179,46 +89,11 @@ int plan_packed(hn_handle* h, Arena& ar) {
   return 0;
 }
 
-struct ModPlan {
-  bool present = false;
-  bool small = false;
-  int zw = 0;       // small: z row width
-  int ldz = 0;      // generic: z row pitch
-  bool precise = false;  // generic: short token axis -> split z / K / V / Q and the precise attention kernel
-  int segC = 0;
-  int C = 0, c_raw = 0, n_axes = 0;
-  int axes[HN_MAX_AXES];
-  long N = 0;       // tokens of the modality (decides the path, so every rank of a token-sharded run agrees)
-  long Nl = 0;      // tokens held by this rank (== N unless the token axis is sharded across GPUs)
-  long tok0 = 0;    // first local token on the full axis
-  bool sharded = false;
-  int nsplit = 1;
-  bool masked = false;
-  float* tab = nullptr;
-  __half* z = nullptr;
-};
-
-struct Workspace {
-  ModPlan mod[HN_MAX_MODALITIES];
-  float* x = nullptr;        // [b*L][D] fp32 residual stream
-  __half* xn = nullptr;      // [b*L][2 segD]       split
-  __half* q = nullptr;       // [b*L][2 qw]         split (small-C Q': hi only)
-  __half* o = nullptr;       // [b*L][2 ow]         split
-  __half* hid = nullptr;     // [b*L][2 seg4D]      split
-  __half* kv = nullptr;      // [b*Nmax][2*H*64] (x2 when precise)   (generic cross-attention only)
-  bool self_precise = false;
-  float* part_acc = nullptr;
-  float* part_ml = nullptr;
-  uint64_t* mask_bits = nullptr;
-  float* pooled = nullptr;   // [b][D] mean over latents (head)
-  unsigned* ln_counters = nullptr;  // per 128-row block arrival counters of the fused LayerNorm (gemm.cu)
-  int self_nsplit = 1;
-  size_t bytes = 0;
-};
+}  // namespace
 
 // Lays the forward workspace out over `base` (null: sizing pass). present[m] tells which modalities are given.
-int plan_workspace(const hn_handle* h, int batch, const int* axis_sizes, const bool* present, long mask_tokens,
-                   char* base, Workspace& ws, const long* tok_begin = nullptr, const long* tok_count = nullptr) {
+int hn::plan_workspace(const hn_handle* h, int batch, const int* axis_sizes, const bool* present, long mask_tokens,
+                       char* base, Workspace& ws, const long* tok_begin, const long* tok_count) {
   const hn_desc& d = h->d;
   const int M = h->M, L = d.l_c, D = d.l_d;
   Arena ar;
@@ -299,6 +174,8 @@ int plan_workspace(const hn_handle* h, int batch, const int* axis_sizes, const b
   ws.bytes = ar.off + 256;
   return 0;
 }
+
+namespace {
 
 #define HN_TRY(expr)          \
   do {                        \
@@ -383,16 +260,30 @@ int residual_gemm(hn_handle* h, GemmArgs g, LnPlan& lp, Workspace& ws, cudaStrea
   return 0;
 }
 
+// training-mode forward: copy a buffer onto the tape (stream-ordered device-to-device copy)
+int tape_put(hn_handle* h, size_t off, const void* src, size_t bytes, cudaStream_t st) {
+  if (h->tape == nullptr) return 0;
+  HN_CHECK_CUDA(cudaMemcpyAsync(h->tape + off, src, bytes, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
 int run_ff(hn_handle* h, const std::vector<const float*>& wf, const FFPacked& fp, Workspace& ws, long rows,
-           LnPlan& lp, cudaStream_t st) {
+           LnPlan& lp, const BlockRec* rec, cudaStream_t st) {
   const hn_desc& d = h->d;
   const int D = d.l_d;
   const int sD = h->segD, s4 = h->seg4D;
-  int rc = ln_step(h, lp, ws, rows, st);
+  int rc = 0;
+  if (rec != nullptr) rc = tape_put(h, rec->x_in, ws.x, sizeof(float) * rows * D, st);
+  if (rc != 0) return rc;
+  rc = ln_step(h, lp, ws, rows, st);
+  if (rc != 0) return rc;
+  if (rec != nullptr) rc = tape_put(h, rec->xn, ws.xn, sizeof(__half) * rows * 2 * sD, st);
   if (rc != 0) return rc;
   GemmArgs g1{ws.xn, fp.W1, static_cast<int>(rows), 8 * D, D, 2 * sD, 2 * sD, EPI_GATE_F16,
               d.snn ? ACT_SELU : ACT_GELU, fp.b1, ws.hid, 2 * s4, 3, sD, sD, s4};
   HN_TRY(launch_gemm(g1, st));
+  if (rec != nullptr) rc = tape_put(h, rec->o, ws.hid, sizeof(__half) * rows * 2 * s4, st);
+  if (rc != 0) return rc;
   GemmArgs g2{ws.hid, fp.W2, static_cast<int>(rows), D, 4 * D, 2 * s4, 2 * s4, EPI_RES, 0, wf[5], ws.x, D, 3, s4, s4, 0};
   return residual_gemm(h, g2, lp, ws, st);
 }
@@ -639,11 +530,6 @@ int hn_forward(hn_handle* h, int batch, const void* const* modality_ptrs, const 
                        logits_out, workspace, workspace_bytes, cuda_stream);
 }
 
-static int forward_impl(hn_handle* h, int batch, const void* const* modality_ptrs, void* const* modality_ready_events,
-                        const int* axis_sizes, const long* tok_begin, const long* tok_count,
-                        const int* skip_latent_block, const uint8_t* mask, long mask_tokens, float* latents_out,
-                        float* logits_out, void* workspace, size_t workspace_bytes, void* cuda_stream);
-
 int hn_forward_ex(hn_handle* h, int batch, const void* const* modality_ptrs, void* const* modality_ready_events,
                   const int* axis_sizes, const int* skip_latent_block, const uint8_t* mask, long mask_tokens,
                   float* latents_out, float* logits_out, void* workspace, size_t workspace_bytes,
@@ -776,10 +662,12 @@ static int exchange_partials(hn_handle* h, const Workspace& ws, int batch, int n
   return launch_merge_signal(ws.part_acc, ws.part_ml, batch, nsplit, H, L, w, my_acc, my_acc + rows * w, pp, st);
 }
 
-static int forward_impl(hn_handle* h, int batch, const void* const* modality_ptrs, void* const* modality_ready_events,
-                        const int* axis_sizes, const long* tok_begin, const long* tok_count,
-                        const int* skip_latent_block, const uint8_t* mask, long mask_tokens, float* latents_out,
-                        float* logits_out, void* workspace, size_t workspace_bytes, void* cuda_stream) {
+}  // extern "C"
+
+int hn::forward_impl(hn_handle* h, int batch, const void* const* modality_ptrs, void* const* modality_ready_events,
+                     const int* axis_sizes, const long* tok_begin, const long* tok_count,
+                     const int* skip_latent_block, const uint8_t* mask, long mask_tokens, float* latents_out,
+                     float* logits_out, void* workspace, size_t workspace_bytes, void* cuda_stream) {
   HN_REQUIRE(h != nullptr && modality_ptrs != nullptr && axis_sizes != nullptr, "hn_forward: null argument");
   HN_REQUIRE(batch >= 1, "hn_forward: batch must be >= 1");
   HN_REQUIRE(h->packed_valid, "hn_forward: call hn_pack_weights after registering / changing weights");
@@ -864,12 +752,23 @@ static int forward_impl(hn_handle* h, int batch, const void* const* modality_ptr
   }
   HN_CHECK_CUDA(cudaMemsetAsync(ws.ln_counters, 0, sizeof(unsigned) * static_cast<size_t>((rows + 127) / 128), st));
 
+  // training-mode forward (hn_forward_train): every block leaves what hn_backward needs on the tape
+  const bool taping = h->tape != nullptr;
+  size_t bi = 0;  // index of the next block record
+  auto next_rec = [&]() -> const BlockRec* { return taping ? &h->train.blocks[bi++] : nullptr; };
+
   for (int l = 0; l < d.depth; ++l) {
     for (int m = 0; m < M; ++m) {
       ModPlan& mp = ws.mod[m];
       if (mp.present) {
         if (l == 0) {
           rc = build_context(m);
+          if (rc != 0) return rc;
+        }
+        const BlockRec* rec = next_rec();
+        if (rec != nullptr) {
+          HN_REQUIRE(!mp.sharded, "hn_forward_train: token-sharded training is not supported");
+          rc = tape_put(h, rec->x_in, ws.x, sizeof(float) * rows * D, st);
           if (rc != 0) return rc;
         }
         const std::vector<const float*>& wa = h->w[slot_index(h, l, 2 * m)];
@@ -880,6 +779,10 @@ static int forward_impl(hn_handle* h, int batch, const void* const* modality_ptr
         // PreNorm + to_q (split operands in, split Q / Q' out)
         rc = ln_step(h, lp, ws, rows, st);
         if (rc != 0) return rc;
+        if (rec != nullptr) {
+          rc = tape_put(h, rec->xn, ws.xn, sizeof(__half) * rows * 2 * sD, st);
+          if (rc != 0) return rc;
+        }
         const int qw = mp.small ? H * mp.zw : H * HPx;
         const bool q_split = true;
         GemmArgs gq{ws.xn, mp.small ? ap.WqS : ap.Wq, static_cast<int>(rows), qw, D, 2 * sD, 2 * sD, EPI_F16, 0,
@@ -918,8 +821,15 @@ static int forward_impl(hn_handle* h, int batch, const void* const* modality_ptr
           const int sHZ = seg_of(H * mp.zw);
           if (sHZ != H * mp.zw)
             HN_CHECK_CUDA(cudaMemsetAsync(ws.o, 0, sizeof(__half) * rows * 2 * sHZ, st));
+          if (rec != nullptr)  // merged row statistics: P'(t) = 2^(s_t - M + P_SHIFT), denominator column C
+            HN_TRY(launch_row_stats(ws.part_acc, ws.part_ml, batch, mp.nsplit, H, L, mp.zw, mp.C, 0.0009765625f,
+                                    reinterpret_cast<float*>(h->tape + rec->stats), st));
           HN_TRY(launch_combine_generic(ws.part_acc, ws.part_ml, batch, mp.nsplit, H, L, ws.o, 2 * sHZ, sHZ, mp.zw, st,
                                         mp.sharded ? &pp : nullptr, mp.C));
+          if (rec != nullptr) {
+            rc = tape_put(h, rec->o, ws.o, sizeof(__half) * rows * 2 * sHZ, st);
+            if (rc != 0) return rc;
+          }
         } else {
           // K/V projection of the standardised context (context LayerNorm affine folded into the weights).
           // Weights are always split (their rounding would not average out over tokens); z, K and V are split
@@ -957,9 +867,16 @@ static int forward_impl(hn_handle* h, int batch, const void* const* modality_ptr
           profile_end(h, st);
           if (h->export_ptrs[l * (M + 1) + m] != nullptr) HN_TRY(launch_attn_export(aa, h->export_ptrs[l * (M + 1) + m], st));
           if (mp.sharded) HN_TRY(exchange_partials(h, ws, batch, mp.nsplit, H, L, HPx, pp, st));
+          if (rec != nullptr)
+            HN_TRY(launch_row_stats(ws.part_acc, ws.part_ml, batch, mp.nsplit, H, L, HPx, -1, 1.f,
+                                    reinterpret_cast<float*>(h->tape + rec->stats), st));
           if (!direct)
             HN_TRY(launch_combine_generic(ws.part_acc, ws.part_ml, batch, mp.nsplit, H, L, ws.o, 2 * ow, ow, HPx, st,
                                           mp.sharded ? &pp : nullptr));
+          if (rec != nullptr) {
+            rc = tape_put(h, rec->o, ws.o, sizeof(__half) * rows * 2 * ow, st);
+            if (rc != 0) return rc;
+          }
         }
         // x = LeakyReLU(O Wo^T + bo) + x   (healnet.py:383-386, 426, 236)
         if (mp.small) {
@@ -973,7 +890,7 @@ static int forward_impl(hn_handle* h, int batch, const void* const* modality_ptr
           rc = residual_gemm(h, go, lp, ws, st);
         }
         if (rc != 0) return rc;
-        rc = run_ff(h, wf, fp, ws, rows, lp, st);
+        rc = run_ff(h, wf, fp, ws, rows, lp, next_rec(), st);
         if (rc != 0) return rc;
       }
       if (d.self_per_cross_attn && !(skip_latent_block != nullptr && skip_latent_block[m] != 0)) {
@@ -984,8 +901,17 @@ static int forward_impl(hn_handle* h, int batch, const void* const* modality_ptr
         const FFPacked& fp = h->ff[l * (M + 1) + M];
         const int lh = d.l_heads, HPl = h->hpl, ow = lh * HPl, qw = 3 * lh * HPl;
         const bool prec = ws.self_precise;
+        const BlockRec* rec = next_rec();
+        if (rec != nullptr) {
+          rc = tape_put(h, rec->x_in, ws.x, sizeof(float) * rows * D, st);
+          if (rc != 0) return rc;
+        }
         rc = ln_step(h, lp, ws, rows, st);
         if (rc != 0) return rc;
+        if (rec != nullptr) {
+          rc = tape_put(h, rec->xn, ws.xn, sizeof(__half) * rows * 2 * sD, st);
+          if (rc != 0) return rc;
+        }
         GemmArgs gq{ws.xn, ap.Wq, static_cast<int>(rows), qw, D, 2 * sD, 2 * sD, EPI_F16, 0, nullptr, ws.q,
                     prec ? 2 * qw : qw, 3, sD, sD, prec ? qw : 0};
         HN_TRY(launch_gemm(gq, st));
@@ -1018,16 +944,28 @@ static int forward_impl(hn_handle* h, int batch, const void* const* modality_ptr
         }
         HN_TRY(launch_attention(aa, st));
         if (h->export_ptrs[l * (M + 1) + M] != nullptr) HN_TRY(launch_attn_export(aa, h->export_ptrs[l * (M + 1) + M], st));
+        if (rec != nullptr)
+          HN_TRY(launch_row_stats(ws.part_acc, ws.part_ml, batch, ws.self_nsplit, lh, L, HPl, -1, 1.f,
+                                  reinterpret_cast<float*>(h->tape + rec->stats), st));
         if (!direct)
           HN_TRY(launch_combine_generic(ws.part_acc, ws.part_ml, batch, ws.self_nsplit, lh, L, ws.o, 2 * ow, ow, HPl, st));
+        if (rec != nullptr) {
+          rc = tape_put(h, rec->o, ws.o, sizeof(__half) * rows * 2 * ow, st);
+          if (rc != 0) return rc;
+        }
         GemmArgs go{ws.o, ap.Wo, static_cast<int>(rows), D, ow, 2 * ow, 2 * ow, EPI_RES_LEAKY, 0, wa[5], ws.x, D,
                     3, ow, ow, 0};
         rc = residual_gemm(h, go, lp, ws, st);
         if (rc != 0) return rc;
-        rc = run_ff(h, wf, fp, ws, rows, lp, st);
+        rc = run_ff(h, wf, fp, ws, rows, lp, next_rec(), st);
         if (rc != 0) return rc;
       }
     }
+  }
+  if (taping) {
+    HN_REQUIRE(bi == h->train.blocks.size(), "hn_forward_train: tape plan out of sync with the forward");
+    rc = tape_put(h, h->train.x_final, ws.x, sizeof(float) * rows * D, st);
+    if (rc != 0) return rc;
   }
   bool any_sharded = false;
   for (int m = 0; m < M; ++m) any_sharded = any_sharded || (ws.mod[m].present && ws.mod[m].sharded);
@@ -1045,7 +983,10 @@ static int forward_impl(hn_handle* h, int batch, const void* const* modality_ptr
   return 0;
 }
 
+extern "C" {
+
 // ------------------------------------------------------------------------------------ stand-alone Attention
+}  // extern "C"
 namespace {
 struct AttnWs {
   __half *xh, *ch, *wq, *wkv, *wo, *q, *kv, *o;
@@ -1080,6 +1021,8 @@ void plan_attn_ws(int batch, int n_q, long n_ctx, int qd, int cd, int heads, int
   w.bytes = ar.off + 256;
 }
 }  // namespace
+
+extern "C" {
 
 size_t hn_attention_workspace_bytes(int batch, int n_q, long n_ctx, int query_dim, int context_dim, int heads,
                                     int dim_head) {

@@ -121,6 +121,27 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream);
 // can this residual GEMM also emit the next LayerNorm (GemmArgs::ln_*)? (shape / alignment rules, HN_GEMM_LN switch)
 bool gemm_can_fuse_ln(const GemmArgs& a);
 
+// ------------------------------------------------------------------ strided batched fp32 contraction (sgemm.cu)
+// C[b1][b2][m][n] (+)= alpha * sum_k A(m, k) * B(k, n); operands fp32 (type 0) or split fp16 pairs as the forward
+// stores them (type 1: value = p[i] + p[i + lo_off]); all strides in elements of the operand's storage type.
+struct SgOperand {
+  const void* p = nullptr;
+  int type = 0;
+  int lo_off = 0;
+  long s_row = 0, s_col = 0;   // A: (m, k) strides; B: (k, n) strides
+  long s_b1 = 0, s_b2 = 0;
+};
+struct SgArgs {
+  int M = 0, N = 0, K = 0;
+  SgOperand A, B;
+  float* C = nullptr;
+  long c_row = 0, c_col = 1, c_b1 = 0, c_b2 = 0;
+  int nb1 = 1, nb2 = 1;
+  float alpha = 1.f;
+  int accumulate = 0;
+};
+int launch_sgemm(const SgArgs& a, cudaStream_t stream);
+
 // ------------------------------------------------------------------ row ops (rowops.cu)
 // y[r] = [hi | lo] split fp16 of LN(x[r]) * gamma + beta: hi in columns [0, seg), lo in [lo_seg, lo_seg + seg)
 // (lo_seg == 0: hi only); pad columns [D, seg) are zero-filled in both segments.

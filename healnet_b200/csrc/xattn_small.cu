@@ -128,7 +128,7 @@ __device__ __forceinline__ constexpr bool poly_slot(int j) {
          : PMODE == 3 ? ((j % 8) == 1 || (j % 8) == 4 || (j % 8) == 6)
                       : (j % 2) == 1;
 }
-// packed-pair variant: both exponentials of a column pair on the FMA / ALU pipes in half2 arithmetic (12
+// packed-pair variant: both exponentials of a column pair on the FMA / ALU pipes in half2 arithmetic (13
 // instructions per PAIR incl. the fp16 pack, vs 17 for two fp32 polynomials + pack). The argument already carries
 // +P_SHIFT (see above). n = rint(x) via the magic constant trick (fp16 ulp is 1 in [1024, 2048)): the integer lands in
 // the low mantissa bits and the exponent insert (a lane-wise integer add) builds 2^x — a normal fp16 for every
@@ -137,12 +137,15 @@ __device__ __forceinline__ constexpr bool poly_slot(int j) {
 // exact zero — so tokens far below the reference contribute nothing, like MUFU's flush to zero. (Round 1 clamped the
 // argument at -14 instead, which gave every such token a weight of 2^-24: harmless for diffuse softmaxes, but over
 // 602 112 voxels a spurious mass of up to 1.8 % once the softmax is peaked — found by tests/test_gpu_fullsize.py.)
-// The argument is clamped at -30 only to keep the magic-constant sum inside [1024, 2048). x above 15.5 overflows the
-// exponent field into inf / NaN: read as "> 2^15" by the unsigned max check that triggers the exact path.
+// The argument is clamped to [-30, 16]: that keeps the magic-constant sum inside [1024, 2048) and the exponent field
+// of an overflowing result at 30 | 31 (>= 2^15.5, inf or NaN with the sign bit CLEAR), which the unsigned max check
+// reads as "> 2^15" and sends to the exact path; the zeroing of negative lanes is a SIGNED INTEGER max for the same
+// reason (a floating-point max would also erase the NaN). (Round 1 had no upper clamp: a jump of the row max by more
+// than 2^38 on a polynomial column could wrap the 6-bit exponent add all the way round and go unnoticed.)
 // Relative error ~6e-4 rms (3x the fp16 rounding of P itself, zero-mean).
 __device__ __forceinline__ uint32_t ex2_pair_h2(float x0, float x1) {
   __half2 xh = __floats2half2_rn(x0, x1);
-  xh = __hmax2(xh, __float2half2_rn(-30.f));
+  xh = __hmin2(__hmax2(xh, __float2half2_rn(-30.f)), __float2half2_rn(16.f));
   const __half2 magic = __float2half2_rn(1536.f);
   const __half2 t = __hadd2(xh, magic);
   const __half2 f = __hsub2(xh, __hsub2(t, magic));  // t = 1536 + rint(x) exactly
@@ -153,8 +156,8 @@ __device__ __forceinline__ uint32_t ex2_pair_h2(float x0, float x1) {
   const uint32_t e = (*reinterpret_cast<const uint32_t*>(&t) << 10) & 0xFC00FC00u;
   uint32_t r;
   asm("add.u16x2 %0, %1, %2;" : "=r"(r) : "r"(*reinterpret_cast<const uint32_t*>(&p)), "r"(e));
-  const __half2 rz = __hmax2(*reinterpret_cast<const __half2*>(&r), __float2half2_rn(0.f));
-  return *reinterpret_cast<const uint32_t*>(&rz);
+  asm("max.s16x2 %0, %1, %2;" : "=r"(r) : "r"(r), "r"(0u));
+  return r;
 }
 // PMODE >= 5: which column PAIRS take the half2 polynomial: 5 = 1/3, 6 = 1/2, 7 = 2/3, 8 = 3/4
 template <int PMODE>

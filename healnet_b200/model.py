@@ -167,6 +167,26 @@ def _f32_dev(p: torch.Tensor, dev: torch.device) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------------------------------------
+class _FusedForward(torch.autograd.Function):
+    """autograd node of the fused forward: forward = hn_forward_train (records a tape), backward = hn_backward
+    (reference training step: healnet/main.py:426-467 calls loss.backward() through HealNet.forward). The parameters
+    are passed as inputs so that autograd routes their gradients; the data tensors get none (the reference never
+    asks for them)."""
+
+    @staticmethod
+    def forward(ctx, model, call, *params):
+        out, state = model._launch_train(call, params)
+        ctx.model, ctx.state = model, state
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        grads = ctx.model._backward(ctx.state, grad_out)
+        ctx.state = None
+        return (None, None, *grads)
+
+
+# ----------------------------------------------------------------------------------------------------------
 class HealNet(nn.Module):
     """HEALNet fusion model — same constructor, parameters and forward contract as the reference
     (healnet/models/healnet.py:14-262); the forward pass runs as sm_100a kernels through the C ABI.
@@ -175,7 +195,8 @@ class HealNet(nn.Module):
       * forward does not mutate the caller's list (the reference does, :222);
       * the attention matrices are never materialised, so `get_attention_weights()` returns `None`
         entries (the reference keeps b*h*L*N floats per Attention module, :420);
-      * forward-only: outputs carry no autograd graph.
+      * with gradients enabled the forward records a tape and `loss.backward()` runs the library's backward
+        (hn_backward): parameter gradients only, fp32 CUDA parameters, dropout 0.
     Quirks that ARE reproduced: softmax temperature 0.5 on top of dim_head**-0.5 (:375,:419); the latent
     self-attention block runs after every modality (:228-245); a missing / mismatching modality skips only
     its cross-attention + cross-FF unless `verbose=True` (:229-239); layer-0 weights are never tied (:161).
@@ -281,6 +302,7 @@ class HealNet(nn.Module):
         self.keep_output_on_device = False
         self.last_launch_count = 0
         self._warned = set()
+        self._train_seq = 0      # training-mode forwards so far: only the latest one can be back-propagated
 
     # ------------------------------------------------------------------------------------------------ native
     _NATIVE_DEFAULTS = dict(_handle=None, _handle_dev=None, _weights_sig=None, _staged=(), _workspace=None,
@@ -502,8 +524,29 @@ class HealNet(nn.Module):
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             self._sync_native(dev, stream)
-            out = self._launch(lib, staged, ready, axis_sizes, skip_self, mask_dev, mask_tokens, batch, want_latents,
-                               dev, stream, tok_begin, tok_count)
+            params = [p for p in self.parameters()]
+            differentiable = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+            if differentiable:
+                # the library's backward covers fp32 parameters resident on the compute device; anything else runs the
+                # plain forward and says (once) that its output carries no autograd graph
+                why = None
+                if any(p.device != dev or p.dtype != torch.float32 for p in params):
+                    why = "parameters are not fp32 tensors on the CUDA device"
+                elif tok_count is not None and any(c > 0 for c in tok_count):
+                    why = "the token axis is sharded across GPUs"
+                elif self.export_attention_weights:
+                    why = "export_attention_weights is on"
+                if why is not None:
+                    self._warn_once(("nograd", why), f"HealNet forward under autograd, but {why}: the output carries "
+                                    "no autograd graph (use torch.no_grad() for inference to silence this)")
+                    differentiable = False
+            if differentiable:
+                call = dict(lib=lib, staged=staged, ready=ready, axis_sizes=axis_sizes, skip_self=skip_self,
+                            mask_dev=mask_dev, mask_tokens=mask_tokens, batch=batch, want_latents=want_latents, dev=dev)
+                out = _FusedForward.apply(self, call, *params)
+            else:
+                out = self._launch(lib, staged, ready, axis_sizes, skip_self, mask_dev, mask_tokens, batch,
+                                   want_latents, dev, stream, tok_begin, tok_count)
             if nan_rows is not None and any(t is not None for t in staged):
                 out = torch.where(nan_rows.view(-1, *([1] * (out.dim() - 1))), torch.full_like(out, float("nan")), out)
         if ret_dtype is not None and not ret_dtype.is_floating_point:
@@ -591,6 +634,79 @@ class HealNet(nn.Module):
         for module, tensor in exported:   # later calls of a tied / repeated module win, as in the reference
             module.attn_weights = tensor
         return out
+
+    # ------------------------------------------------------------------------------ training step (row f2)
+    def _launch_train(self, call, params):
+        """hn_forward_train on a workspace + tape owned by this call (they must outlive later forwards until the
+        backward runs). Returns (output, state for _backward)."""
+        lib, dev, batch = call["lib"], call["dev"], call["batch"]
+        hp, M = self._hparams, self.modalities
+        staged, ready = call["staged"], call["ready"]
+        ptrs = (ctypes.c_void_p * HN_MAX_MODALITIES)()
+        sizes = (ctypes.c_int * (HN_MAX_MODALITIES * HN_MAX_AXES))(*call["axis_sizes"])
+        for i in range(M):
+            ptrs[i] = staged[i].data_ptr() if staged[i] is not None else None
+            if staged[i] is None:
+                for a in range(HN_MAX_AXES):
+                    sizes[i * HN_MAX_AXES + a] = max(1, sizes[i * HN_MAX_AXES + a])
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            need = lib.hn_workspace_bytes(self._handle, batch, sizes)
+            tape_need = lib.hn_tape_bytes(self._handle, batch, sizes)
+            if need == 0 or tape_need == 0:
+                raise _lib.HealNetLibraryError(f"sizing the training forward failed: {_lib.last_error()}")
+            workspace = torch.empty(need, device=dev, dtype=torch.uint8)
+            tape = torch.empty(tape_need, device=dev, dtype=torch.uint8)
+            if call["want_latents"]:
+                out = torch.empty(batch, hp["l_c"], hp["l_d"], device=dev, dtype=torch.float32)
+                lat_ptr, log_ptr = out.data_ptr(), None
+            else:
+                out = torch.empty(batch, hp["out_dims"], device=dev, dtype=torch.float32)
+                lat_ptr, log_ptr = None, out.data_ptr()
+            skip_self = call["skip_self"]
+            skip = (ctypes.c_int * HN_MAX_MODALITIES)(*[1 if f else 0 for f in skip_self]) if any(skip_self) else None
+            events = None
+            if any(e is not None for e in ready):
+                events = (ctypes.c_void_p * HN_MAX_MODALITIES)()
+                for i in range(M):
+                    events[i] = ready[i].cuda_event if (ready[i] is not None and staged[i] is not None) else None
+            mask_dev = call["mask_dev"]
+            check(lib.hn_forward_train(self._handle, batch, ptrs, events, sizes, skip,
+                                       mask_dev.data_ptr() if mask_dev is not None else None, call["mask_tokens"],
+                                       lat_ptr, log_ptr, workspace.data_ptr(), workspace.numel(), tape.data_ptr(),
+                                       tape.numel(), stream), "hn_forward_train")
+        self.last_launch_count = lib.hn_last_launch_count(self._handle)
+        self._train_seq += 1
+        state = dict(seq=self._train_seq, workspace=workspace, tape=tape, sizes=sizes, batch=batch, dev=dev,
+                     want_latents=call["want_latents"], params=params, keep=(staged, mask_dev))
+        return out, state
+
+    def _backward(self, state, grad_out):
+        """hn_backward: gradients of every parameter (zeros for parameters the forward did not use), in the order of
+        `state['params']`."""
+        lib = load_library()
+        if state is None or state["seq"] != self._train_seq:
+            raise RuntimeError("only the most recent training-mode forward of a HealNet module can be back-propagated "
+                               "(one tape per native handle); call backward() before the next forward()")
+        dev, batch, params = state["dev"], state["batch"], state["params"]
+        grads = {id(p): torch.zeros(p.shape, device=dev, dtype=torch.float32) for p in params}
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            for layer, slot, ps in self._slot_params():
+                arr = (ctypes.c_void_p * len(ps))(*[grads[id(p)].data_ptr() for p in ps])
+                check(lib.hn_set_grads(self._handle, layer, slot, arr, len(ps)), "hn_set_grads")
+            need = lib.hn_backward_scratch_bytes(self._handle, batch, state["sizes"])
+            if need == 0:
+                raise _lib.HealNetLibraryError(f"hn_backward_scratch_bytes failed: {_lib.last_error()}")
+            scratch = torch.empty(need, device=dev, dtype=torch.uint8)
+            g = grad_out.detach().to(device=dev, dtype=torch.float32).contiguous()
+            ws, tape = state["workspace"], state["tape"]
+            check(lib.hn_backward(self._handle, g.data_ptr() if state["want_latents"] else None,
+                                  None if state["want_latents"] else g.data_ptr(), ws.data_ptr(), ws.numel(),
+                                  tape.data_ptr(), tape.numel(), scratch.data_ptr(), scratch.numel(), stream),
+                  "hn_backward")
+            scratch.record_stream(torch.cuda.current_stream(dev))
+        return [grads[id(p)] if p.requires_grad else None for p in params]
 
     # ------------------------------------------------------------------------------ token-axis sharding (row f4)
     def enable_token_sharding(self, group=None, min_tokens: int = 8192, max_batch: int = 8) -> None:

@@ -141,6 +141,33 @@ HN_API int hn_forward_split(hn_handle* h, int batch, const void* const* modality
                             long mask_tokens, float* latents_out, float* logits_out, void* workspace,
                             size_t workspace_bytes, void* cuda_stream);
 
+/* ---- training step ---------------------------------------------------------------
+ * Replaces what torch.autograd does for the reference's training loop (healnet/main.py:426-467: logits = model(x);
+ * loss.backward()): the gradient of the forward with respect to every parameter. The loss, the L1 regulariser
+ * (healnet/utils/train_utils.py:5-14) and the optimizer stay with the caller.
+ *   hn_forward_train : hn_forward_ex that also records, per PreNorm(module) block, what the backward needs (the fp32
+ *                      residual stream, its LayerNorm, the normalised attention output / gated hidden rows, softmax row
+ *                      statistics) on a caller-owned tape of hn_tape_bytes() bytes. Nothing of size tokens x latents
+ *                      is stored: attention probabilities are recomputed by hn_backward. One recording per handle.
+ *   hn_set_grads     : registers fp32 gradient buffers, same (layer, slot) layout and tensor order as hn_set_weights
+ *                      (register the weights first). hn_backward ACCUMULATES into them (+=): zero them per step; tied
+ *                      layers register the same buffers again and the contributions add up.
+ *   hn_backward      : given d loss / d logits (batch, out_dims) OR d loss / d latents (batch, l_c, l_d) of the recorded
+ *                      forward, the SAME workspace that forward used (it still holds the standardised context rows),
+ *                      its tape and hn_backward_scratch_bytes() bytes of scratch: accumulates every parameter gradient.
+ *                      No gradient is produced for the inputs (the reference's data tensors never require grad).
+ * Token-sharded forwards and dropout (reference default 0) are not supported in training mode. */
+HN_API size_t hn_tape_bytes(const hn_handle* h, int batch, const int* axis_sizes);
+HN_API size_t hn_backward_scratch_bytes(const hn_handle* h, int batch, const int* axis_sizes);
+HN_API int hn_forward_train(hn_handle* h, int batch, const void* const* modality_ptrs, void* const* modality_ready_events,
+                            const int* axis_sizes, const int* skip_latent_block, const uint8_t* mask, long mask_tokens,
+                            float* latents_out, float* logits_out, void* workspace, size_t workspace_bytes, void* tape,
+                            size_t tape_bytes, void* cuda_stream);
+HN_API int hn_set_grads(hn_handle* h, int layer, int slot, void* const* dev_ptrs, int n);
+HN_API int hn_backward(hn_handle* h, const float* grad_latents, const float* grad_logits, void* workspace,
+                       size_t workspace_bytes, const void* tape, size_t tape_bytes, void* scratch, size_t scratch_bytes,
+                       void* cuda_stream);
+
 /* Number of kernels hn_forward enqueued on its last call for this handle (for bench accounting). */
 HN_API int hn_last_launch_count(const hn_handle* h);
 

@@ -1,0 +1,201 @@
+"""GPU (B200): the backward pass — d loss / d parameter of the CUDA path through
+`loss.backward()` on the drop-in module (torch.autograd.Function -> hn_forward_train / hn_backward through the C ABI)
+against gradients produced by the UNMODIFIED reference's autograd (tests/golden/grads_*.npz: cross-entropy of the
+logits, healnet/main.py:436-440), every parameter, tied layers included; and the reference's training step
+(healnet/main.py:426-467, healnet/utils/train_utils.py:5-14: loss + L1 regulariser, backward, Adam step) run on the
+module and compared with the same steps taken by the oracle under torch autograd on the CPU.
+Tolerance: rtol 2e-3 per parameter tensor against the tensor's own scale (atol = 2e-3 * max|grad|, floor 2e-6) —
+the forward it differentiates is itself held to rtol 1e-3 — widened, per tensor, to twice the REFERENCE ALGORITHM'S OWN
+sensitivity to a 1e-4 relative perturbation of the weights (oracle autograd, three seeds). Why: LeakyReLU(0.01) after
+every attention output projection (healnet.py:383-386) has a kink at 0; the tiny fixtures have pre-activations as
+close to it as 1.8e-5 (omic_wsi_tied), where a forward that differs from the reference by 1e-5 — well inside its
+tolerance — picks the other slope, and with only 34 latent rows that one element moves a bias gradient by 0.8 %
+(measured: the oracle itself jumps by exactly that amount under 3e-5 weight noise). Where the reference is smooth the
+widening is nil (sensitivity ~1e-4 relative) and the strict tolerance applies."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import GOLDEN
+from healnet_b200 import HealNet
+from oracle import healnet_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_grads(sd, kw, xs, loss_fn, mask=None, noise=0.0, seed=0):
+    """d loss / d parameter from the oracle under torch autograd (CPU), keyed like named_parameters(): tied aliases
+    (bit-identical tensors of the state_dict) share one leaf, optionally perturbed by relative Gaussian noise."""
+    cfg = O.OracleConfig(**{k: v for k, v in kw.items() if k in O.OracleConfig.__dataclass_fields__})
+    gen = torch.Generator().manual_seed(seed)
+    groups = {}
+    for k, v in sd.items():
+        groups.setdefault((tuple(v.shape), v.numpy().tobytes()), []).append(k)
+    params = {}
+    for ks in groups.values():
+        v = sd[ks[0]].clone()
+        if noise > 0:
+            v = v * (1 + noise * torch.randn(v.shape, generator=gen))
+        v.requires_grad_(True)
+        for k in ks:
+            params[k] = v
+    loss_fn(O.forward(params, cfg, xs, mask=mask)).backward()
+    return {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in params.items()}
+
+
+def _sensitivity(sd, kw, xs, loss_fn, mask=None):
+    """per tensor: largest change of the oracle's gradient under a 1e-4 relative weight perturbation (3 seeds)"""
+    base = _oracle_grads(sd, kw, xs, loss_fn, mask)
+    sens = {k: 0.0 for k in base}
+    for seed in (1, 2, 3):
+        pert = _oracle_grads(sd, kw, xs, loss_fn, mask, noise=1e-4, seed=seed)
+        for k in base:
+            sens[k] = max(sens[k], float((pert[k] - base[k]).abs().max()))
+    return sens
+
+
+def _check_grads(model, want_grads, rtol=2e-3, sens=None):
+    checked, worst, widened = 0, (0.0, None), []
+    named = dict(model.named_parameters())
+    for key, want in want_grads.items():
+        p = named[key]
+        assert p.grad is not None, key
+        got = p.grad.detach().float().cpu()
+        scale = float(want.abs().max())
+        err = float((got - want).abs().max())
+        rel = err / max(scale, 1e-12)
+        if rel > worst[0]:
+            worst = (rel, key)
+        atol = max(rtol * scale, 2e-6)
+        if sens is not None and 2.0 * sens[key] > atol:
+            atol = 2.0 * sens[key]
+            widened.append(key)
+        torch.testing.assert_close(got, want, rtol=rtol, atol=atol, msg=lambda m: f"{key}: {m}")
+        checked += 1
+    print("worst relative-to-scale gradient error %.2e (%s) over %d tensors; tolerance widened by the reference's own "
+          "sensitivity for %d" % (worst[0], worst[1], checked, len(widened)))
+    return checked
+
+
+@pytest.mark.parametrize("name", ["tri_small", "omic_wsi_tied", "wide_heads"])
+def test_gradients_match_reference_autograd(golden, name):
+    """Generic / precise attention paths, odd head sizes, GELU gate, tied layers (gradients of shared parameters are
+    the sum over their uses)."""
+    meta, sd, ins, outs, _ = golden(name)
+    g = np.load(os.path.join(GOLDEN, f"grads_{name}.npz"))
+    model = HealNet(**meta["kwargs"])
+    model.load_state_dict(sd)
+    model = model.cuda().train()
+    xs = [ins[str(i)].cuda() for i in range(meta["kwargs"]["n_modalities"])]
+    logits = model(xs)
+    assert logits.requires_grad
+    loss = F.cross_entropy(logits, torch.from_numpy(g["targets"]).cuda())
+    assert abs(loss.item() - float(g["loss"])) < 2e-4
+    loss.backward()
+    want = {k[5:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("grad/")}
+    tgt = torch.from_numpy(g["targets"])
+    sens = _sensitivity(sd, meta["kwargs"], [t.cpu() for t in xs], lambda lg: F.cross_entropy(lg, tgt))
+    assert _check_grads(model, want, sens=sens) >= 50
+
+
+@pytest.mark.parametrize("name", ["grads_stream_tri", "grads_stream_masked"])
+def test_gradients_streaming_small_context_path(name):
+    """Token axes > 2048 with narrow contexts (image / volume): the streaming cross-attention backward, incl. a token
+    mask, a ragged last tile, 64-wide context rows and peaked attention."""
+    meta = json.load(open(os.path.join(GOLDEN, "index.json")))[name]
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}
+    model = HealNet(**meta["kwargs"])
+    model.load_state_dict(sd)
+    model = model.cuda().train()
+    xs = [torch.from_numpy(z[f"in/{i}"]).cuda() for i in range(meta["kwargs"]["n_modalities"])]
+    mask = torch.from_numpy(z["in/mask"]).cuda() if "in/mask" in z.files else None
+    logits = model(xs, mask=mask)
+    torch.testing.assert_close(logits.detach().cpu(), torch.from_numpy(z["logits"]), rtol=1e-3, atol=1e-4)
+    loss = F.cross_entropy(logits, torch.from_numpy(z["targets"]).cuda())
+    loss.backward()
+    want = {k[5:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("grad/")}
+    tgt = torch.from_numpy(z["targets"])
+    sens = _sensitivity(sd, meta["kwargs"], [t.cpu() for t in xs], lambda lg: F.cross_entropy(lg, tgt),
+                        mask=mask.cpu() if mask is not None else None)
+    assert _check_grads(model, want, sens=sens) >= 50
+
+
+def test_gradient_of_the_latent_array_and_missing_modality():
+    """return_embeddings=True (gradient enters at the latent array) with a missing modality: parameters of the skipped
+    cross-attention get zero gradients; everything else matches the oracle's autograd."""
+    kw = dict(n_modalities=2, channel_dims=[20, 3], num_spatial_axes=[1, 2], out_dims=3, l_c=20, l_d=32, depth=2,
+              x_heads=2, cross_dim_head=8, l_heads=2, latent_dim_head=8)
+    torch.manual_seed(3)
+    model = HealNet(**kw)
+    xs = [None, torch.rand(2, 7, 9, 3)]
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    cfg = O.OracleConfig(**{k: v for k, v in kw.items() if k in O.OracleConfig.__dataclass_fields__})
+    wgt = torch.randn(2, 20, 32)
+    (O.forward(sd, cfg, xs, return_embeddings=True) * wgt).sum().backward()
+    model = model.cuda().train()
+    lat = model([None, xs[1].cuda()], return_embeddings=True)
+    (lat * wgt.cuda()).sum().backward()
+    want = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in sd.items()}
+    _check_grads(model, want)
+    assert float(dict(model.named_parameters())["layers.0.0.fn.to_q.weight"].grad.abs().max()) == 0.0
+
+
+def test_reference_training_step_runs_on_the_module():
+    """healnet/main.py:426-467 + train_utils.py:5-14, three optimisation steps: zero_grad, forward, cross-entropy + L1
+    regulariser over model.parameters(), backward, Adam step — on the CUDA module and, as the checker, on the oracle under
+    torch autograd (CPU). Losses and final parameters must agree."""
+    kw = dict(n_modalities=2, channel_dims=[24, 3], num_spatial_axes=[1, 2], out_dims=4, l_c=32, l_d=64, depth=2,
+              x_heads=2, cross_dim_head=16, l_heads=2, latent_dim_head=16)
+    torch.manual_seed(9)
+    model = HealNet(**kw)
+    g = torch.Generator().manual_seed(10)
+    xs = [torch.rand(4, 1, 24, generator=g), torch.rand(4, 50, 50, 3, generator=g)]   # 2500 tokens: streaming path
+    y = torch.tensor([0, 1, 2, 3])
+    l1 = 1e-4
+    # checker: oracle parameters as leaves, same optimiser
+    ref = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    cfg = O.OracleConfig(**{k: v for k, v in kw.items() if k in O.OracleConfig.__dataclass_fields__})
+    opt_ref = torch.optim.Adam(list(ref.values()), lr=1e-3)
+    ref_losses = []
+    for _ in range(3):
+        opt_ref.zero_grad()
+        loss = F.cross_entropy(O.forward(ref, cfg, xs), y) + l1 * sum(p.abs().sum() for p in ref.values())
+        loss.backward()
+        opt_ref.step()
+        ref_losses.append(loss.item())
+    model = model.cuda().train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    dev_xs, dev_y = [t.cuda() for t in xs], y.cuda()
+    losses = []
+    for _ in range(3):
+        opt.zero_grad()
+        logits = model.forward(dev_xs)
+        loss = F.cross_entropy(logits, dev_y) + float(l1) * sum(p.abs().sum() for p in model.parameters())
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+        losses.append(loss.item())
+    assert losses[-1] < losses[0]
+    torch.testing.assert_close(torch.tensor(losses), torch.tensor(ref_losses), rtol=2e-4, atol=2e-4)
+    for k, v in model.state_dict().items():
+        # Adam's first steps move every weight by ~lr whatever the gradient's size: compare on that scale
+        torch.testing.assert_close(v.cpu(), ref[k].detach(), rtol=1e-3, atol=2e-4, msg=lambda m: f"{k}: {m}")
+
+
+def test_only_the_latest_forward_can_be_backpropagated():
+    kw = dict(n_modalities=1, channel_dims=[8], num_spatial_axes=[1], out_dims=2, l_c=8, l_d=16, depth=1, x_heads=1,
+              cross_dim_head=8, l_heads=1, latent_dim_head=8)
+    model = HealNet(**kw).cuda().train()
+    x = torch.rand(2, 5, 8, device="cuda")
+    a = model([x]).sum()
+    b = model([x]).sum()
+    with pytest.raises(RuntimeError):
+        a.backward()
+    b.backward()
+    with torch.no_grad():
+        assert not model([x]).requires_grad

@@ -9,7 +9,7 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CANDIDATES = [os.path.join(ROOT, "baseline", "_ref", "test_healnet.py"),
+CANDIDATES = [os.path.join(ROOT, "baseline", "_ref", "tests", "test_healnet.py"),
               "/root/reference/healnet/tests/test_healnet.py"]
 
 
