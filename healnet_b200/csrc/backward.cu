@@ -242,12 +242,11 @@ int attention_core_backward(int batch, int H, int L, long N, int dh, int hp, flo
                             const float* stats, const uint64_t* mask_bits, BwdScratch& s, cudaStream_t st) {
   const int I = H * dh;
   const long LN_ = static_cast<long>(L) * N, HLN = static_cast<long>(H) * LN_;
-  const long total = static_cast<long>(batch) * HLN;
   const int n = static_cast<int>(N);
   // S = Q K^T (log2 units)
   BW(sg(st, L, n, hp, H16(Q, q_lo, q_ld, 1, static_cast<long>(L) * q_ld, hp),
         H16(KV + k_col0, kv_lo, 1, kv_ld, N * kv_ld, hp), s.S, N, 1.f, 0, batch, HLN, H, LN_));
-  BW(launch_softmax_recompute(s.S, stats, H, L, N, mask_bits, total, st));
+  BW(launch_softmax_recompute(s.S, stats, H, L, N, mask_bits, static_cast<long>(batch) * H * L, st));
   // dV[n][h, d] = sum_l P[l][n] dO[l][h, d]
   BW(sg(st, n, dh, L, F32(s.S, 1, N, HLN, LN_), F32(s.dO, I, 1, static_cast<long>(L) * I, dh), s.dKV + I, 2 * I, 1.f, 0,
         batch, N * 2 * I, H, dh));

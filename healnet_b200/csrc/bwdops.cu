@@ -266,22 +266,31 @@ __global__ void row_stats_kernel(const float* __restrict__ part_acc, const float
 }
 
 // ------------------------------------------------------------------ generic attention backward (materialised)
-// S [bh][L][N] (log2 units) -> P = 2^(S - M) / den in place, masked / out-of-range tokens -> 0
-__global__ void softmax_recompute_kernel(float* __restrict__ S, const float* __restrict__ stats, int H, int L, long N,
-                                         const uint64_t* __restrict__ mask_bits, long total) {
+// S [bh][L][N] (log2 units) -> P = 2^(S - M) / sum_n 2^(S - M) in place (one warp per row); masked tokens -> 0.
+// M (the forward's reference max) only keeps the exponentials in range; the row is normalised by ITS OWN sum rather
+// than the forward's denominator, so that the recomputed probabilities sum to one exactly (a one-token axis gives
+// P = 1 and, downstream, dt = 0 exactly — see softmax_bwd_kernel).
+__global__ void __launch_bounds__(256) softmax_recompute_kernel(float* __restrict__ S, const float* __restrict__ stats,
+                                                                int H, int L, long N,
+                                                                const uint64_t* __restrict__ mask_bits, long n_rows) {
   HN_PDL_LAUNCH();
   HN_PDL_WAIT();
+  const int lane = threadIdx.x & 31;
+  const long row = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);  // (b*H + h)*L + l
+  if (row >= n_rows) return;
   const long words = (N + 63) / 64;
-  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
-    const long row = i / N;      // (b*H + h)*L + l
-    const long n = i - row * N;
-    bool keep = true;
-    if (mask_bits != nullptr) {
-      const long b = row / (static_cast<long>(H) * L);
-      keep = (mask_bits[b * words + n / 64] >> (n % 64)) & 1ull;
-    }
-    S[i] = keep ? exp2f(S[i] - stats[2 * row]) / stats[2 * row + 1] : 0.f;
+  const uint64_t* mb = mask_bits != nullptr ? mask_bits + (row / (static_cast<long>(H) * L)) * words : nullptr;
+  float* s = S + row * N;
+  const float M = stats[2 * row];
+  float sum = 0.f;
+  for (long n = lane; n < N; n += 32) {
+    const bool keep = mb == nullptr || ((mb[n / 64] >> (n % 64)) & 1ull);
+    const float e = keep ? exp2f(s[n] - M) : 0.f;
+    s[n] = e;
+    sum += e;
   }
+  const float inv = 1.f / warp_sum(sum);
+  for (long n = lane; n < N; n += 32) s[n] *= inv;
 }
 // dP [bh][L][N] -> dt = P * (dP - D) in place, D = sum_n P dP of the row (one warp per row). D is formed from the
 // very P and dP it is subtracted from (not as dO . O): a single-token axis (the tabular modality) then gives dt = 0
@@ -572,8 +581,9 @@ int launch_row_stats(const float* part_acc, const float* part_ml, int batch, int
   return 0;
 }
 int launch_softmax_recompute(float* S, const float* stats, int H, int L, long N, const uint64_t* mask_bits, long total,
-                             cudaStream_t st) {
-  HN_CHECK_CUDA(launch_k(softmax_recompute_kernel, dim3(ew_grid(total)), dim3(256), 0, st, S, stats, H, L, N, mask_bits, total));
+                             cudaStream_t st) {  // total = number of rows (b * H * L)
+  HN_CHECK_CUDA(launch_k(softmax_recompute_kernel, dim3(static_cast<unsigned>((total + 7) / 8)), dim3(256), 0, st, S, stats, H, L,
+                         N, mask_bits, total));
   HN_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
