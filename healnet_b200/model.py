@@ -764,7 +764,12 @@ class HealNet(nn.Module):
         import torch.distributed as dist
         if self._exchange is not None and self._exchange[3] >= batch and self._exchange[4] is self._handle:
             return
-        self._release_exchange()   # a larger batch / a new handle: unmap and free the old buffers first
+        if self._exchange is not None:
+            # a larger batch / a new handle: unmap and free the old buffers first — once every rank has finished the
+            # forwards that may still be reading them
+            torch.cuda.synchronize()
+            dist.barrier(group=self._exchange_group)
+            self._release_exchange()
         rank, world, _ = self._token_shard
         cap = max(batch, self._exchange_max_batch)
         nbytes = lib.hn_exchange_bytes(self._handle, cap)

@@ -2,8 +2,11 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 \
         tools/run_split_check.py [--bench]
 Every rank runs (a) the plain single-GPU forward and (b) the token-sharded forward of the same inputs, checks that
-(b) matches (a) to fp32 merge-order noise and that all ranks hold bit-identical results, and optionally times both.
-Exit code 0 = all checks passed.
+(b) matches (a) to fp32 merge-order noise, that (b) matches the CPU ORACLE (oracle/healnet_oracle.py) at the north-star
+tolerance, and that all ranks hold bit-identical results; then (c) one rank is held back on the host for a few seconds
+before a sharded forward (the peers' combine kernels must wait, not merge stale partials) and (d) with a 1 s exchange
+time-out the same delay must surface as NaN outputs + HealNetLibraryError, never as silently wrong logits.
+Optionally times (a) against (b). Exit code 0 = all checks passed.
 """
 import argparse
 import os
@@ -13,7 +16,8 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
-from healnet_b200 import HealNet  # noqa: E402
+from healnet_b200 import HealNet, HealNetLibraryError  # noqa: E402
+from oracle import healnet_oracle as O  # noqa: E402  (the checker; test infrastructure only)
 
 CASES = {
     # name: (constructor kwargs, input shapes (without batch), batch)
@@ -76,11 +80,62 @@ def main():
         dist.all_gather(gathered, got_lat.contiguous())
         identical = all(torch.equal(gathered[0], t) for t in gathered)
         scale = ref_lat.abs().max().item()
-        good = err_lat <= 2e-4 * max(scale, 1.0) and err_log <= 1e-4 and identical
+        cfg = O.OracleConfig(**{k: v for k, v in kw.items() if k in O.OracleConfig.__dataclass_fields__})
+        sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        with torch.no_grad():
+            want = O.forward(sd, cfg, [t.cpu() for t in xs], mask=mask.cpu() if mask is not None else None)
+        oracle_ok = torch.allclose(got_log.cpu(), want, rtol=1e-3, atol=1e-4)
+        err_oracle = (got_log.cpu() - want).abs().max().item()
+        good = err_lat <= 2e-4 * max(scale, 1.0) and err_log <= 1e-4 and identical and oracle_ok
         ok = ok and good
         if rank == 0:
             print(f"{name}: sharded vs single-GPU max|err| latents {err_lat:.3e} (max |ref| {scale:.2f}) logits "
-                  f"{err_log:.3e}; ranks bit-identical: {identical} -> {'OK' if good else 'FAIL'}", flush=True)
+                  f"{err_log:.3e}; sharded vs CPU oracle logits {err_oracle:.3e}; ranks bit-identical: {identical} "
+                  f"-> {'OK' if good else 'FAIL'}", flush=True)
+        if name == "tri_small_ctx":
+            import time
+            # (c) host-side skew: the last rank enters the forward 3 s late; everybody must still get the right result
+            with torch.no_grad():
+                model.enable_token_sharding(min_tokens=2049)
+                model(list(xs))
+                torch.cuda.synchronize()
+                dist.barrier()
+                if rank == world - 1:
+                    time.sleep(3.0)
+                late = model(list(xs))
+                torch.cuda.synchronize()
+                model.check_token_sharding()
+                skew_ok = torch.equal(late, got_log)
+                # (d) same skew with a 1 s time-out: the early ranks must get NaN + an exception, not stale numbers
+                model.disable_token_sharding()
+                model.token_sharding_timeout_s = 1.0
+                dist.barrier()               # nobody unmaps a buffer a peer's kernels may still be reading
+                model._release_exchange()
+                model.enable_token_sharding(min_tokens=2049)
+                model(list(xs))
+                torch.cuda.synchronize()
+                dist.barrier()
+                if rank == world - 1:
+                    time.sleep(4.0)
+                out = model(list(xs))
+                torch.cuda.synchronize()
+                raised = False
+                try:
+                    model.check_token_sharding()
+                except HealNetLibraryError:
+                    raised = True
+                timeout_ok = (rank == world - 1) or (raised and bool(torch.isnan(out).all()))
+                model.disable_token_sharding()
+                model.token_sharding_timeout_s = 30.0
+                dist.barrier()
+                model._release_exchange()
+            flags = torch.tensor([int(skew_ok), int(timeout_ok)], device="cuda")
+            dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+            good2 = bool(flags[0].item()) and bool(flags[1].item())
+            ok = ok and good2
+            if rank == 0:
+                print(f"delayed rank: 3 s host skew tolerated = {bool(flags[0].item())}; 1 s time-out surfaces as NaN + "
+                      f"HealNetLibraryError = {bool(flags[1].item())} -> {'OK' if good2 else 'FAIL'}", flush=True)
         del model
     if args.bench:
         for name, (kw, shapes) in BENCH.items():
