@@ -70,25 +70,12 @@ struct SmallDev {
   int ctas_per_stream;                       // ceil(n_rb / G)
   int tiles_total;
   int mask_words;  // 64-token mask words per sample
-  long long* trace;  // debug timeline buffer or null
   int c_ones;  // column of z that is 1.0 (= context width C): Q' carries -m_ref there
   long N;
   const uint64_t* mask_bits;
   float* part_acc;
   float* part_ml;
 };
-
-// Debug timeline (tools/trace_attn.py): CTA 0 records clock64() at a few points of tiles [TR_T0, TR_T0 + TR_NT) for
-// the first softmax warp and the issuer of every group. Compiled into separate TRACE instantiations only.
-constexpr int TR_T0 = 64, TR_NT = 48, TR_NP = 8;
-#ifdef HN_DEBUG
-long long* g_trace_buf = nullptr;  // set through hn_debug_set_trace
-#endif
-#define HN_TR(slot, tile, k)                                                                              \
-  do {                                                                                                    \
-    if (TRACE && p.trace != nullptr && blockIdx.x == 0 && lane == 0 && (tile) >= TR_T0 && (tile) < TR_T0 + TR_NT) \
-      p.trace[(static_cast<long>(slot) * TR_NT + ((tile) - TR_T0)) * TR_NP + (k)] = clock64();            \
-  } while (0)
 
 __device__ __forceinline__ float ex2_mufu(float x) {
   float y;
@@ -159,10 +146,10 @@ __device__ __forceinline__ uint32_t ex2_pair_h2(float x0, float x1) {
   asm("max.s16x2 %0, %1, %2;" : "=r"(r) : "r"(r), "r"(0u));
   return r;
 }
-// PMODE >= 5: which column PAIRS take the half2 polynomial: 5 = 1/3, 6 = 1/2, 7 = 2/3, 8 = 3/4
+// PMODE >= 5: which column PAIRS take the half2 polynomial: 5 = 1/3, 6 = 1/2, 7 = 2/3, 8 = 1/4
 template <int PMODE>
 __device__ __forceinline__ constexpr bool poly_pair(int j) {
-  return PMODE == 5 ? (j % 3) == 1 : PMODE == 6 ? (j % 2) == 1 : PMODE == 7 ? (j % 3) != 1 : false;
+  return PMODE == 5 ? (j % 3) == 1 : PMODE == 6 ? (j % 2) == 1 : PMODE == 7 ? (j % 3) != 1 : PMODE == 8 ? (j % 4) == 1 : false;
 }
 // byte offset of element (row, col) inside a TMA-swizzled [rows][KD] fp16 tile (64-byte rows -> SWIZZLE_64B,
 // 128-byte rows -> SWIZZLE_128B): the 16-byte chunk index is XORed with the low bits of (row-pair | row)
@@ -173,8 +160,234 @@ __device__ __forceinline__ uint32_t swizzled_off(int row, int col) {
   return row * 128 + ((chunk ^ (static_cast<uint32_t>(row) & 7u)) << 4) + within;
 }
 
-template <int KD, int G, int PMODE, bool SPLIT, bool TRACE = false>
-__global__ void __launch_bounds__((5 * G + 1) * 32, 1)
+// ---------------------------------------------------------------- softmax warps, 16 rows each (SW = 8)
+// Warp wg (0..7) of row block g owns TMEM lanes [32 (wg & 3) + 16 (wg >> 2), +16): the .16x256b fragment gives thread t
+// rows t/4 and t/4 + 8 of those, and of each 32-column chunk the column pairs 8k + 2(t%4) + {0, 1}, k = 0..3 — which
+// packed to fp16x2 are exactly the .16x128b fragment of P. Row state (reference max, folded offsets) is therefore
+// replicated across the four threads of a quad and agreed on with two shuffles; everything else is the algorithm of the
+// SW = 4 variant (lazily raised reference, fold in Q', steady-state path without max pass).
+template <int KD, int G, int PMODE, bool SPLIT>
+__device__ __forceinline__ void softmax_rows16(const SmallDev& p, uint8_t* sQ, uint64_t* s_full_all, uint64_t* p_ready_all,
+                                               uint64_t* u_done_all, uint64_t* acc_done_all, uint32_t tmem, int warp,
+                                               int lane, int rb0, int n_active, int b, int split, int t_begin,
+                                               int t_end) {
+  constexpr int VD = KD;
+  constexpr int Q_GROUP = (SPLIT ? 2 : 1) * BM * KD * 2;
+  constexpr int GCOLS = 2 * 64 + VD;
+  const int g = warp >> 3;
+  if (g >= n_active) return;
+  const int n = t_end - t_begin;
+  const int wg = warp & 7;
+  const int rb = rb0 + g, h = rb / p.n_ltiles, lt = rb % p.n_ltiles;
+  const uint32_t lane_off = (wg & 3) * 32 + (wg >> 2) * 16;
+  const int qd = lane >> 2, qc = lane & 3;
+  const int trow0 = lane_off + qd;                  // rows inside the 128-row block: trow0 and trow0 + 8
+  const uint32_t tG = tmem + g * GCOLS;
+  const uint32_t tL = tmem_addr(tG, lane_off, 0);
+  const uint32_t tU = tL + 128;
+  uint64_t* s_full = s_full_all + g * 2;
+  uint64_t* p_ready = p_ready_all + g * 2;
+  uint64_t* u_done = u_done_all + g;
+  uint64_t* acc_done = acc_done_all + g;
+  uint8_t* qrow_fold = sQ + g * Q_GROUP;
+  float m_ref[2] = {-INFINITY, -INFINITY};
+  float m_in0[2] = {0.f, 0.f}, m_in1[2] = {0.f, 0.f};
+
+  const int n_full = (t_end == p.tiles_total && (p.N % BT) != 0) ? n - 1 : n;
+  const bool has_mask = p.mask_bits != nullptr;
+  const int n_steady = has_mask ? 0 : n_full;
+  bool stale = true;
+  bool ready = false;
+
+  auto tile = [&](const int i, auto buf_c, const uint32_t ph) {
+    constexpr int buf = decltype(buf_c)::value;
+    const uint32_t tS = tL + buf * 64;
+    if (!ready) mbar_wait(&s_full[buf], ph);
+    fence_after_sync();
+    ready = false;
+
+    bool exact = stale || i >= n_steady;
+    stale = false;
+    uint32_t pk[16];  // P(i): register 2K + a = row a, packed column 4K + qc  (K = 0..7)
+    if (!exact) {
+      uint32_t pmax = 0;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t s[16];
+        tmem_ld_16x256b_x4(tS + c * 32, s);
+        tmem_wait_ld();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+          for (int a = 0; a < 2; ++a) {
+            const float x0 = __uint_as_float(s[4 * k + 2 * a]), x1 = __uint_as_float(s[4 * k + 2 * a + 1]);
+            const int o = c * 8 + 2 * k + a;
+            // PMODE 6: every other pair of every row on the FMA pipe; other shares by running pair index
+            if (PMODE == 6 ? ((k + a) & 1) : (PMODE >= 5 && poly_pair<PMODE>(c * 8 + 2 * k + a + (a ? 1 : 0)))) {
+              pk[o] = ex2_pair_h2(x0, x1);
+            } else {
+              pk[o] = pack_half2(ex2_mufu(x0), ex2_mufu(x1));
+            }
+            pmax = vmaxu2(pmax, pk[o]);
+          }
+        }
+        if (c == 0) ready = mbar_try_wait(&s_full[buf ^ 1], buf ? (ph ^ 1) : ph);
+      }
+      const bool big = ((pmax & 0xFFFFu) > P_RAISE_BITS) || ((pmax >> 16) > P_RAISE_BITS);
+      exact = __any_sync(0xffffffffu, big);
+    }
+    if (exact) {
+      const int tile_idx = t_begin + i;
+      uint64_t bits = ~0ull;
+      if (has_mask) bits = p.mask_bits[static_cast<long>(b) * p.tiles_total + tile_idx];
+      const long rem = p.N - static_cast<long>(tile_idx) * BT;
+      if (rem < BT) bits &= (1ull << rem) - 1ull;
+      const uint64_t mybits = bits >> (2 * qc);  // bit (8k + e) of the shifted word = my column 8k + 2 qc + e
+      float m_in[2] = {buf ? m_in1[0] : m_in0[0], buf ? m_in1[1] : m_in0[1]};
+      float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t s[16];
+        tmem_ld_16x256b_x4(tS + c * 32, s);
+        tmem_wait_ld();
+        const uint32_t mb = static_cast<uint32_t>(mybits >> (32 * c));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+          for (int a = 0; a < 2; ++a) {
+            const float v0 = ((mb >> (8 * k)) & 1u) ? __uint_as_float(s[4 * k + 2 * a]) : -INFINITY;
+            const float v1 = ((mb >> (8 * k + 1)) & 1u) ? __uint_as_float(s[4 * k + 2 * a + 1]) : -INFINITY;
+            mx[a] = fmax3(mx[a], v0, v1);
+          }
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], 1));
+        mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], 2));
+        mx[a] += m_in[a];
+      }
+      const bool raise = __any_sync(0xffffffffu, mx[0] > m_ref[0] + RESCALE_THRESHOLD || mx[1] > m_ref[1] + RESCALE_THRESHOLD);
+      if (raise) {
+        __half fold_h[2];
+        float m_new[2], sc[2];
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          fold_h[a] = __float2half_rn(P_SHIFT - fmaxf(m_ref[a], mx[a]));
+          m_new[a] = (mx[a] == -INFINITY && m_ref[a] == -INFINITY) ? -INFINITY : P_SHIFT - __half2float(fold_h[a]);
+          sc[a] = (m_new[a] == -INFINITY || m_ref[a] == m_new[a]) ? 1.f : ex2_mufu(m_ref[a] - m_new[a]);
+        }
+        if (i > 0) {
+          mbar_wait(u_done, (i - 1) & 1);  // PV(i-1) landed; PV(i) cannot start before our p_ready arrive
+          fence_after_sync();
+          if (__any_sync(0xffffffffu, sc[0] != 1.f || sc[1] != 1.f)) {
+#pragma unroll
+            for (int c = 0; c < VD; c += 32) {
+              uint32_t u[16];
+              tmem_ld_16x256b_x4(tU + c, u);
+              tmem_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) u[j] = __float_as_uint(__uint_as_float(u[j]) * sc[(j >> 1) & 1]);
+              tmem_st_16x256b_x4(tU + c, u);
+            }
+          }
+        }
+        if (i + 1 < n) {  // S(i+1) may still be reading Q': wait for it before changing the folded offset
+          mbar_wait(&s_full[buf ^ 1], buf ? (ph ^ 1) : ph);
+          ready = true;
+        }
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          m_ref[a] = m_new[a];
+          if (qc == 0)
+            *reinterpret_cast<__half*>(qrow_fold + swizzled_off<KD>(trow0 + 8 * a, p.c_ones)) =
+                (m_ref[a] == -INFINITY) ? __float2half_rn(0.f) : fold_h[a];
+        }
+        fence_proxy_async_smem();
+        stale = true;
+      }
+      float m_cur[2], delta[2];
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        m_cur[a] = (m_ref[a] == -INFINITY) ? 0.f : m_ref[a] - P_SHIFT;
+        delta[a] = m_in[a] - m_cur[a];
+      }
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t s[16];
+        tmem_ld_16x256b_x4(tS + c * 32, s);
+        tmem_wait_ld();
+        const uint32_t mb = static_cast<uint32_t>(mybits >> (32 * c));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+          for (int a = 0; a < 2; ++a) {
+            const float v0 = ((mb >> (8 * k)) & 1u) ? __uint_as_float(s[4 * k + 2 * a]) : -INFINITY;
+            const float v1 = ((mb >> (8 * k + 1)) & 1u) ? __uint_as_float(s[4 * k + 2 * a + 1]) : -INFINITY;
+            pk[c * 8 + 2 * k + a] = pack_half2(ex2_mufu(v0 + delta[a]), ex2_mufu(v1 + delta[a]));
+          }
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        if (buf) m_in1[a] = m_cur[a]; else m_in0[a] = m_cur[a];
+      }
+    }
+    tmem_st_16x128b_x8(tS, pk);  // P(i) over S columns 0..31 of my 16 lanes (all 64 of them have been read)
+    tmem_wait_st();
+    fence_before_sync();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&p_ready[buf]);
+    __syncwarp();
+  };
+  {
+    int i = 0;
+    uint32_t ph = 0;
+    for (; i + 1 < n; i += 2, ph ^= 1) {
+      tile(i, std::integral_constant<int, 0>{}, ph);
+      tile(i + 1, std::integral_constant<int, 1>{}, ph);
+    }
+    if (i < n) tile(i, std::integral_constant<int, 0>{}, ph);
+  }
+  // ---- epilogue: un-normalised accumulator rows + reference max
+  mbar_wait(acc_done, 0);
+  fence_after_sync();
+#pragma unroll
+  for (int c = 0; c < VD; c += 32) {
+    uint32_t u[16];
+    tmem_ld_16x256b_x4(tU + c, u);
+    tmem_wait_ld();
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int row = lt * BM + trow0 + 8 * a;
+      if (row < p.L) {
+        const long part_row = ((static_cast<long>(b) * p.nsplit + split) * p.H + h) * p.L + row;
+        float* dst = p.part_acc + part_row * VD + c + 2 * qc;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          *reinterpret_cast<float2*>(dst + 8 * k) =
+              make_float2(__uint_as_float(u[4 * k + 2 * a]), __uint_as_float(u[4 * k + 2 * a + 1]));
+      }
+    }
+    __syncwarp();
+  }
+  if (qc == 0) {
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int row = lt * BM + trow0 + 8 * a;
+      if (row < p.L) {
+        const long part_row = ((static_cast<long>(b) * p.nsplit + split) * p.H + h) * p.L + row;
+        *reinterpret_cast<float2*>(p.part_ml + part_row * 2) = make_float2(m_ref[a], 0.f);
+      }
+    }
+  }
+}
+
+// SW = softmax warps per row block: 4 (thread = latent row, .32x32b TMEM fragments) or 8 (each warp owns 16 rows of
+// the block and sees all 64 columns of them through the .16x256b / .16x128b fragments: twice the warps per scheduler to
+// hide the per-tile TMEM / mbarrier latencies, half the registers per thread).
+template <int KD, int G, int PMODE, bool SPLIT, int SW>
+__global__ void __launch_bounds__(((SW + 1) * G + 1) * 32, 1)
 attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmZ, SmallDev p) {
   constexpr int VD = KD;
   constexpr int Q_TILE = BM * KD * 2;            // one [128][KD] operand tile (hi or lo)
@@ -235,14 +448,14 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     for (int g = 0; g < MAXG; ++g) {
       mbar_init(&s_full[g][0], 1);
       mbar_init(&s_full[g][1], 1);
-      mbar_init(&p_ready[g][0], 4);
-      mbar_init(&p_ready[g][1], 4);
+      mbar_init(&p_ready[g][0], SW);
+      mbar_init(&p_ready[g][1], SW);
       mbar_init(&u_done[g], 1);
       mbar_init(&acc_done[g], 1);
     }
     fence_mbar_init();
   }
-  constexpr int PRODUCER_WARP = 5 * G;
+  constexpr int PRODUCER_WARP = (SW + 1) * G;
   if (warp == PRODUCER_WARP) tmem_alloc<512>(&tmem_base_s);
   fence_before_sync();
   __syncthreads();
@@ -270,12 +483,12 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         if (SPLIT) tma_load_3d(sZ + s * Z_STAGE + Z_BYTES, &tmZ, &z_full[s], KD, (t_begin + i) * BT, b);
       }
     }
-  } else if (warp >= 4 * G) {
+  } else if (warp >= SW * G) {
     // ------------------------------------------------------------ UMMA issuers: one warp (one elected thread) per
     // group, each on its own scheduler. Once all four softmax warps have published P(i) the thread issues PV(i)
     // and, right behind it, S(i+2) into the buffer P(i) occupied — so S(i+1) is always complete before the
     // softmax needs it and no tensor-pipe or issue latency sits on the softmax warps' critical path.
-    const int g = warp - 4 * G;
+    const int g = warp - SW * G;
     if (g < n_active && elect_one()) {
       const uint32_t tG = tmem + g * GCOLS;
       const uint32_t q0 = smem_u32(sQ + g * Q_GROUP);
@@ -304,11 +517,9 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       issue_s(0);
       if (n > 1) issue_s(1);
       for (int i = 0; i < n; ++i) {
-        // all four warps: S(i) consumed, P(i) in TMEM, Q' fold up to date. Two alternating barriers: a warp may run
+        // all softmax warps of the group: S(i) consumed, P(i) in TMEM, Q' fold up to date. Two alternating barriers: a warp may run
         // one tile ahead of its group but never two, so it cannot arrive twice in one phase of either.
-        HN_TR(MAXG + g, i, 0);
         mbar_wait_sleepy(&p_ready[g][i & 1], (i >> 1) & 1, 20000);
-        HN_TR(MAXG + g, i, 1);
         fence_after_sync();
         const int s = i % NST;
         const uint32_t z0 = smem_u32(sZ + s * Z_STAGE);
@@ -318,12 +529,13 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                   (i | k) != 0);
         umma_commit(&z_empty[s]);
         umma_commit(&u_done[g]);
-        HN_TR(MAXG + g, i, 2);
         if (i + 2 < n) issue_s(i + 2);
-        HN_TR(MAXG + g, i, 3);
         if (i + 1 == n) umma_commit(&acc_done[g]);
       }
     }
+  } else if (SW == 8) {
+    softmax_rows16<KD, G, PMODE, SPLIT>(p, sQ, &s_full[0][0], &p_ready[0][0], u_done, acc_done, tmem, warp, lane, rb0,
+                                        n_active, b, split, t_begin, t_end);
   } else {
     // ------------------------------------------------------------ softmax groups: thread = latent row
     const int g = warp >> 2;
@@ -353,9 +565,7 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       auto tile = [&](const int i, auto buf_c, const uint32_t ph) {
         constexpr int buf = decltype(buf_c)::value;
         const uint32_t tS = tL + buf * 64;
-        if ((warp & 3) == 0) HN_TR(g, i, 0);
         if (!ready) mbar_wait(&s_full[g][buf], ph);
-        if ((warp & 3) == 0) HN_TR(g, i, 1);
         fence_after_sync();
         ready = false;
 
@@ -370,7 +580,6 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             uint32_t s[32];
             tmem_ld32(tS + c * 32, s);
             tmem_wait_ld();
-            if ((warp & 3) == 0 && c == 0) HN_TR(g, i, 5);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float x0 = __uint_as_float(s[2 * j]), x1 = __uint_as_float(s[2 * j + 1]);
@@ -471,15 +680,12 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           // the tile S(i+2) that will land in this buffer carries the current reference
           if (buf) m_in1 = m_cur; else m_in0 = m_cur;
         }
-        if ((warp & 3) == 0) HN_TR(g, i, 2);
         tmem_st32(tS, pk);  // P(i) over S columns 0..31 (this thread has read all 64 of them)
         tmem_wait_st();
-        if ((warp & 3) == 0) HN_TR(g, i, 3);
         fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_ready[g][buf]);
         __syncwarp();
-        if ((warp & 3) == 0) HN_TR(g, i, 4);
       };
       {
         int i = 0;
@@ -521,7 +727,7 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 }
 
 
-template <int KD, int G, int PMODE, bool SPLIT>
+template <int KD, int G, int PMODE, bool SPLIT, int SW>
 int launch_small_t(const AttnArgs& a, cudaStream_t stream) {
   CUtensorMap tmQ, tmZ;
   const CUtensorMapSwizzle swz = KD == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -554,21 +760,10 @@ int launch_small_t(const AttnArgs& a, cudaStream_t stream) {
   const long grid = static_cast<long>(p.ctas_per_stream) * a.batch * a.nsplit;
   HN_REQUIRE(grid > 0 && grid < 2147483647L, "attention: grid too large");
   p.mask_words = p.tiles_total;
-  p.trace = nullptr;
-#ifdef HN_DEBUG
-  p.trace = g_trace_buf;
-  if (g_trace_buf != nullptr && (PMODE == 6 || PMODE == 9)) {
-    HN_CHECK_CUDA(cudaFuncSetAttribute(attn_small_kernel<KD, G, PMODE, SPLIT, true>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    HN_CHECK_CUDA(launch_k(attn_small_kernel<KD, G, PMODE, SPLIT, true>, dim3(static_cast<unsigned>(grid)),
-                           dim3((5 * G + 1) * 32), SMEM, stream, tmQ, tmZ, p));
-    return 0;
-  }
-#endif
-  HN_CHECK_CUDA(cudaFuncSetAttribute(attn_small_kernel<KD, G, PMODE, SPLIT, false>,
+  HN_CHECK_CUDA(cudaFuncSetAttribute(attn_small_kernel<KD, G, PMODE, SPLIT, SW>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-  HN_CHECK_CUDA(launch_k(attn_small_kernel<KD, G, PMODE, SPLIT, false>, dim3(static_cast<unsigned>(grid)),
-                         dim3((5 * G + 1) * 32), SMEM, stream, tmQ, tmZ, p));
+  HN_CHECK_CUDA(launch_k(attn_small_kernel<KD, G, PMODE, SPLIT, SW>, dim3(static_cast<unsigned>(grid)),
+                         dim3(((SW + 1) * G + 1) * 32), SMEM, stream, tmQ, tmZ, p));
   HN_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -615,14 +810,42 @@ int small_attention_pick_nsplit(int batch, int L, int H, long N, int kd) {
   return static_cast<int>(best);
 }
 
+// Softmax warps per row block. The product runs 4 (thread = latent row). The 8-warp layout (16 rows per warp, built on
+// the .16x256b / .16x128b TMEM fragments) doubles the warps per scheduler but was measured SLOWER on the B200 (cfg 1
+// volume, batch 4: 2.45 ms vs 2.36 ms; poly-share sweep in profiles/r2_attn_small_experiments.md): the kernel is bound
+// by instruction issue (4.8 instructions per element at thread-per-row, 5.6 at 16 rows per warp), not by latency.
+// It stays in DEBUG builds (HN_SMALL_SW=8) as the record of that experiment.
+static int softmax_warps() {
+#ifdef HN_DEBUG
+  static int sw = 0;
+  if (sw == 0) {
+    const char* e = getenv("HN_SMALL_SW");
+    sw = (e != nullptr && e[0] == '8') ? 8 : 4;
+  }
+  return sw;
+#else
+  return 4;
+#endif
+}
+
 template <int PMODE>
 static int launch_small_variant(const AttnArgs& a, cudaStream_t stream) {
-  if (a.precise) {
-    if (a.kd == 64) return launch_small_t<64, 2, PMODE, true>(a, stream);
-    return launch_small_t<32, 3, PMODE, true>(a, stream);
+#ifdef HN_DEBUG
+  if (softmax_warps() == 8) {
+    if (a.precise) {
+      if (a.kd == 64) return launch_small_t<64, 2, PMODE, true, 8>(a, stream);
+      return launch_small_t<32, 3, PMODE, true, 8>(a, stream);
+    }
+    if (a.kd == 64) return launch_small_t<64, 2, PMODE, false, 8>(a, stream);
+    return launch_small_t<32, 3, PMODE, false, 8>(a, stream);
   }
-  if (a.kd == 64) return launch_small_t<64, 2, PMODE, false>(a, stream);
-  return launch_small_t<32, 3, PMODE, false>(a, stream);
+#endif
+  if (a.precise) {
+    if (a.kd == 64) return launch_small_t<64, 2, PMODE, true, 4>(a, stream);
+    return launch_small_t<32, 3, PMODE, true, 4>(a, stream);
+  }
+  if (a.kd == 64) return launch_small_t<64, 2, PMODE, false, 4>(a, stream);
+  return launch_small_t<32, 3, PMODE, false, 4>(a, stream);
 }
 
 int launch_small_attention(const AttnArgs& a, cudaStream_t stream) {
@@ -638,7 +861,7 @@ int launch_small_attention(const AttnArgs& a, cudaStream_t stream) {
     case 0: return launch_small_variant<0>(a, stream);
     case 5: return launch_small_variant<5>(a, stream);
     case 7: return launch_small_variant<7>(a, stream);
-    case 9: return launch_small_variant<9>(a, stream);
+    case 8: return launch_small_variant<8>(a, stream);
 #endif
     default: return launch_small_variant<6>(a, stream);
   }
@@ -646,9 +869,3 @@ int launch_small_attention(const AttnArgs& a, cudaStream_t stream) {
 
 }  // namespace hn
 
-#ifdef HN_DEBUG
-// debug builds only (make EXTRA=-DHN_DEBUG): timeline buffer for tools/trace_attn.py, 2*MAXG*TR_NT*TR_NP int64
-extern "C" __attribute__((visibility("default"))) void hn_debug_set_trace(void* dev_buf) {
-  hn::g_trace_buf = static_cast<long long*>(dev_buf);
-}
-#endif
