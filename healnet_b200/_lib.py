@@ -74,6 +74,7 @@ SIGNATURES = {
     "hn_set_grads": (c_int, [c_void_p, c_int, c_int, POINTER(c_void_p), c_int]),
     "hn_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p, c_size_t,
                             c_void_p]),
+    "hn_set_io_dtype": (c_int, [c_void_p, c_int]),
     "hn_last_launch_count": (c_int, [c_void_p]),
     "hn_set_attention_export": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "hn_profile_enable": (c_int, [c_void_p, c_int]),

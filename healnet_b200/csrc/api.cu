@@ -496,6 +496,12 @@ int hn_set_attention_export(hn_handle* h, int layer, int module, float* dev_out)
   return 0;
 }
 
+int hn_set_io_dtype(hn_handle* h, int dtype) {
+  HN_REQUIRE(h != nullptr && dtype >= 0 && dtype <= 2, "hn_set_io_dtype: dtype must be 0 (fp32), 1 (bf16) or 2 (fp16)");
+  h->io_dtype = dtype;
+  return 0;
+}
+
 int hn_profile_enable(hn_handle* h, int on) {
   HN_REQUIRE(h != nullptr, "hn_profile_enable: null handle");
   h->profile = on != 0;
@@ -709,7 +715,7 @@ int hn::forward_impl(hn_handle* h, int batch, const void* const* modality_ptrs, 
   bool mask_packed = false;
   auto build_context = [&](int m) -> int {
     ModPlan& mp = ws.mod[m];
-    const float* raw = static_cast<const float*>(modality_ptrs[m]);
+    const void* raw = modality_ptrs[m];
     if (modality_ready_events != nullptr && modality_ready_events[m] != nullptr)
       HN_CHECK_CUDA(cudaStreamWaitEvent(st, static_cast<cudaEvent_t>(modality_ready_events[m]), 0));
     int prc = profile_begin_raw(h, 2, m, 0.0, 0.0, 0.0, st);
@@ -718,10 +724,10 @@ int hn::forward_impl(hn_handle* h, int batch, const void* const* modality_ptrs, 
       HN_TRY(launch_axis_tables(mp.tab, mp.axes, mp.n_axes, d.num_freq_bands, d.max_freq, st));
     if (mp.small)
       HN_TRY(launch_build_z_small(raw, mp.z, mp.zw, batch, mp.Nl, mp.c_raw, mp.n_axes, mp.axes, d.num_freq_bands,
-                                  mp.tab, d.fourier_encode_data, st, mp.tok0, 1));
+                                  mp.tab, d.fourier_encode_data, st, mp.tok0, 1, h->io_dtype));
     else
       HN_TRY(launch_build_z_large(raw, mp.z, mp.ldz, mp.precise ? mp.segC : 0, batch, mp.Nl, mp.c_raw, mp.n_axes,
-                                  mp.axes, d.num_freq_bands, mp.tab, d.fourier_encode_data, st, mp.tok0));
+                                  mp.axes, d.num_freq_bands, mp.tab, d.fourier_encode_data, st, mp.tok0, h->io_dtype));
     profile_end(h, st);
     if (mp.masked && !mask_packed) {
       HN_TRY(launch_pack_mask(mask, ws.mask_bits, batch, mp.Nl, st));

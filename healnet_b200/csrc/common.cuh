@@ -153,13 +153,14 @@ int launch_axis_tables(float* tab, const int* axis_sizes, int n_axes, int n_band
 // standardised context rows, small-C layout: z[b][N][zw] fp16 = [(v-mean)*rstd (C values), 1, 0...], zw = 32 | 64;
 // split != 0: z[b][N][2 zw] = [hi (zw) | lo (zw)]
 // (tok0: index of the first token of this buffer on the modality's full token axis; N = tokens in the buffer)
-int launch_build_z_small(const float* raw, __half* z, int zw, int batch, long N, int c_raw, int n_axes,
+// in_dtype: element type of the caller's raw modality buffer: 0 fp32, 1 bf16, 2 fp16
+int launch_build_z_small(const void* raw, __half* z, int zw, int batch, long N, int c_raw, int n_axes,
                          const int* axis_sizes /*host*/, int n_bands, const float* tab, int fourier,
-                         cudaStream_t stream, long tok0 = 0, int split = 0);
+                         cudaStream_t stream, long tok0 = 0, int split = 0, int in_dtype = 0);
 // standardised context rows, generic layout: z[b*N][ldz] fp16 (pad cols zero); lo_seg > 0: split [hi | lo]
-int launch_build_z_large(const float* raw, __half* z, int ldz, int lo_seg, int batch, long N, int c_raw, int n_axes,
+int launch_build_z_large(const void* raw, __half* z, int ldz, int lo_seg, int batch, long N, int c_raw, int n_axes,
                          const int* axis_sizes /*host*/, int n_bands, const float* tab, int fourier,
-                         cudaStream_t stream, long tok0 = 0);
+                         cudaStream_t stream, long tok0 = 0, int in_dtype = 0);
 // pooled head: logits[b][o] = LN(mean_L x[b]) . W[o] + bias[o]
 // (pooled: batch * D floats of scratch)
 int launch_head(const float* x, int batch, int L, int D, const float* ln_w, const float* ln_b, const float* W,

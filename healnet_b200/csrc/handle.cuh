@@ -98,6 +98,7 @@ struct hn_handle {
   std::vector<hn::AttnPacked> attn;   // [layer][M + 1] (index M = latent self-attention)
   std::vector<hn::FFPacked> ff;       // [layer][M + 1]
   int launches = 0;
+  int io_dtype = 0;               // element type of the modality input buffers: 0 fp32, 1 bf16, 2 fp16 (hn_set_io_dtype)
   // optional per-launch timing of the cross-attention kernels (bench.py roofline): CUDA event pairs on the
   // forward's own stream, one pair per (layer, modality), read back after the caller synchronises
   // opt-in attention-weight export buffers, index layer * (M + 1) + module (M = latent self-attention); null = off

@@ -8,6 +8,8 @@
 // into the projection weights at pack time (pack.cu).
 #include <cstdlib>
 
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace hn {
@@ -152,6 +154,20 @@ __global__ void axis_tables_kernel(float* __restrict__ tab, AxisInfo ax, int B, 
   }
 }
 
+// raw modality elements as the caller holds them: fp32, bf16 or fp16 (hn_set_io_dtype) -> float
+template <typename T>
+__device__ __forceinline__ float in_f(const T* p) {
+  return static_cast<float>(__ldg(p));
+}
+template <>
+__device__ __forceinline__ float in_f<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __bfloat162float(*p);
+}
+template <>
+__device__ __forceinline__ float in_f<__half>(const __half* p) {
+  return __half2float(*p);
+}
+
 // eight consecutive values -> one 16-byte store of their fp16 hi parts and (lo_dst != null) one of the lo parts
 __device__ __forceinline__ void store_hi_lo8(uint4* hi_dst, uint4* lo_dst, const float* o) {
   uint4 w, wl;
@@ -172,8 +188,8 @@ __device__ __forceinline__ void store_hi_lo8(uint4* hi_dst, uint4* lo_dst, const
 // ------------------------------------------------------------------ z rows, small-C layout (C <= ZW-1)
 // one thread per token: raw channels + table features -> standardise -> ZW fp16 = one 64/128-byte row
 // split != 0: rows are [hi (ZW) | lo (ZW)], lo = fp16(value - hi) (the streaming kernel's three-term score product)
-template <int ZW>
-__global__ void __launch_bounds__(256) build_z_small_kernel(const float* __restrict__ raw, __half* __restrict__ z,
+template <int ZW, typename T>
+__global__ void __launch_bounds__(256) build_z_small_kernel(const T* __restrict__ raw, __half* __restrict__ z,
                                                             long tokens_total, long N, int c_raw, AxisInfo ax,
                                                             int F, const float* __restrict__ tab, long tok0, int split) {
   HN_PDL_LAUNCH();
@@ -182,9 +198,9 @@ __global__ void __launch_bounds__(256) build_z_small_kernel(const float* __restr
   if (t >= tokens_total) return;
   const long n = t % N + tok0;
   float v[ZW];
-  const float* r = raw + t * c_raw;
+  const T* r = raw + t * c_raw;
 #pragma unroll
-  for (int i = 0; i < ZW; ++i) v[i] = i < c_raw ? r[i] : 0.f;
+  for (int i = 0; i < ZW; ++i) v[i] = i < c_raw ? in_f(r + i) : 0.f;
   int C = c_raw;
   // row-major token index -> per-axis coordinates
   long rem = n;
@@ -233,8 +249,8 @@ __global__ void __launch_bounds__(256) build_z_small_kernel(const float* __restr
 // Specialisation for the shapes the path is run on (image / volume: 1-4 raw channels, 1-3 axes, the default 2
 // frequency bands -> F = 5): every feature lands in a compile-time register slot, so the row costs ~150 instructions
 // instead of the ~1000 of the generic kernel above (whose runtime column positions need a compare per slot).
-template <int CRAW, int NAX>
-__global__ void __launch_bounds__(256) build_z_small32_fast_kernel(const float* __restrict__ raw, __half* __restrict__ z,
+template <int CRAW, int NAX, typename T>
+__global__ void __launch_bounds__(256) build_z_small32_fast_kernel(const T* __restrict__ raw, __half* __restrict__ z,
                                                                    long tokens_total, long N, AxisInfo ax,
                                                                    const float* __restrict__ tab, long tok0, int split) {
   HN_PDL_LAUNCH();
@@ -247,9 +263,9 @@ __global__ void __launch_bounds__(256) build_z_small32_fast_kernel(const float* 
                      ? static_cast<unsigned>(t) % static_cast<unsigned>(N) + static_cast<unsigned>(tok0)
                      : static_cast<unsigned>(t % N + tok0);
   float v[C];
-  const float* r = raw + t * CRAW;
+  const T* r = raw + t * CRAW;
 #pragma unroll
-  for (int i = 0; i < CRAW; ++i) v[i] = __ldg(r + i);
+  for (int i = 0; i < CRAW; ++i) v[i] = in_f(r + i);
 #pragma unroll
   for (int a = NAX - 1; a >= 0; --a) {
     const unsigned sz = static_cast<unsigned>(ax.size[a]);
@@ -285,7 +301,8 @@ __global__ void __launch_bounds__(256) build_z_small32_fast_kernel(const float* 
 
 // ------------------------------------------------------------------ z rows, generic layout (any C)
 // one warp per token row
-__global__ void __launch_bounds__(256) build_z_large_kernel(const float* __restrict__ raw, __half* __restrict__ z,
+template <typename T>
+__global__ void __launch_bounds__(256) build_z_large_kernel(const T* __restrict__ raw, __half* __restrict__ z,
                                                             int ldz, int seg, int lo_seg, long tokens_total, long N,
                                                             int c_raw, AxisInfo ax, int F,
                                                             const float* __restrict__ tab, long tok0) {
@@ -295,7 +312,7 @@ __global__ void __launch_bounds__(256) build_z_large_kernel(const float* __restr
   const long t = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= tokens_total) return;
   const long n = t % N + tok0;
-  const float* r = raw + t * c_raw;
+  const T* r = raw + t * c_raw;
   const int n_feat = F * ax.n_axes;
   const int C = c_raw + n_feat;
   long rem = n;
@@ -305,7 +322,7 @@ __global__ void __launch_bounds__(256) build_z_large_kernel(const float* __restr
     rem /= ax.size[a];
   }
   auto feat = [&](int c) -> float {
-    if (c < c_raw) return r[c];
+    if (c < c_raw) return in_f(r + c);
     const int k = c - c_raw;
     const int a = k / F;
     return __ldg(tab + static_cast<long>(ax.off[a] + coord[a]) * F + (k - a * F));
@@ -826,9 +843,10 @@ int launch_axis_tables(float* tab, const int* axis_sizes, int n_axes, int n_band
   return 0;
 }
 
-int launch_build_z_small(const float* raw, __half* z, int zw, int batch, long N, int c_raw, int n_axes,
-                         const int* axis_sizes, int n_bands, const float* tab, int fourier, cudaStream_t stream,
-                         long tok0, int split) {
+namespace {
+template <typename T>
+int build_z_small_t(const T* raw, __half* z, int zw, int batch, long N, int c_raw, int n_axes, const int* axis_sizes,
+                    int n_bands, const float* tab, int fourier, cudaStream_t stream, long tok0, int split) {
   const int F = fourier ? 2 * n_bands + 1 : 0;
   const int C = c_raw + F * n_axes;
   HN_REQUIRE(zw == 32 || zw == 64, "small-C context rows are 32 or 64 wide");
@@ -837,29 +855,44 @@ int launch_build_z_small(const float* raw, __half* z, int zw, int batch, long N,
   const long total = static_cast<long>(batch) * N;
   const unsigned grid = static_cast<unsigned>((total + 255) / 256);
   if (zw == 32 && F == 5 && c_raw >= 1 && c_raw <= 4 && n_axes >= 1 && n_axes <= 3) {
-#define HN_FAST(CR, NA)                                                                                      \
-  if (c_raw == CR && n_axes == NA) {                                                                         \
-    HN_CHECK_CUDA(launch_k(build_z_small32_fast_kernel<CR, NA>, dim3(grid), dim3(256), 0, stream, raw, z, total, N, ax, \
-                           tab, tok0, split));                                                               \
-    return 0;                                                                                                \
+#define HN_FAST(CR, NA)                                                                                         \
+  if (c_raw == CR && n_axes == NA) {                                                                            \
+    HN_CHECK_CUDA(launch_k(build_z_small32_fast_kernel<CR, NA, T>, dim3(grid), dim3(256), 0, stream, raw, z, total, N, \
+                           ax, tab, tok0, split));                                                              \
+    return 0;                                                                                                   \
   }
     HN_FAST(1, 1) HN_FAST(1, 2) HN_FAST(1, 3) HN_FAST(2, 1) HN_FAST(2, 2) HN_FAST(2, 3)
     HN_FAST(3, 1) HN_FAST(3, 2) HN_FAST(3, 3) HN_FAST(4, 1) HN_FAST(4, 2) HN_FAST(4, 3)
 #undef HN_FAST
   }
   if (zw == 32)
-    HN_CHECK_CUDA(launch_k(build_z_small_kernel<32>, dim3(grid), dim3(256), 0, stream, raw, z, total, N, c_raw, ax, F, tab,
-                           tok0, split));
+    HN_CHECK_CUDA(launch_k(build_z_small_kernel<32, T>, dim3(grid), dim3(256), 0, stream, raw, z, total, N, c_raw, ax, F,
+                           tab, tok0, split));
   else
-    HN_CHECK_CUDA(launch_k(build_z_small_kernel<64>, dim3(grid), dim3(256), 0, stream, raw, z, total, N, c_raw, ax, F, tab,
-                           tok0, split));
+    HN_CHECK_CUDA(launch_k(build_z_small_kernel<64, T>, dim3(grid), dim3(256), 0, stream, raw, z, total, N, c_raw, ax, F,
+                           tab, tok0, split));
   HN_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+}  // namespace
 
-int launch_build_z_large(const float* raw, __half* z, int ldz, int lo_seg, int batch, long N, int c_raw, int n_axes,
+// in_dtype: element type of `raw` — 0 fp32, 1 bf16, 2 fp16 (hn_set_io_dtype)
+int launch_build_z_small(const void* raw, __half* z, int zw, int batch, long N, int c_raw, int n_axes,
                          const int* axis_sizes, int n_bands, const float* tab, int fourier, cudaStream_t stream,
-                         long tok0) {
+                         long tok0, int split, int in_dtype) {
+  if (in_dtype == 1)
+    return build_z_small_t(static_cast<const __nv_bfloat16*>(raw), z, zw, batch, N, c_raw, n_axes, axis_sizes, n_bands, tab,
+                           fourier, stream, tok0, split);
+  if (in_dtype == 2)
+    return build_z_small_t(static_cast<const __half*>(raw), z, zw, batch, N, c_raw, n_axes, axis_sizes, n_bands, tab,
+                           fourier, stream, tok0, split);
+  return build_z_small_t(static_cast<const float*>(raw), z, zw, batch, N, c_raw, n_axes, axis_sizes, n_bands, tab, fourier,
+                         stream, tok0, split);
+}
+
+int launch_build_z_large(const void* raw_v, __half* z, int ldz, int lo_seg, int batch, long N, int c_raw, int n_axes,
+                         const int* axis_sizes, int n_bands, const float* tab, int fourier, cudaStream_t stream,
+                         long tok0, int in_dtype) {
   const int F = fourier ? 2 * n_bands + 1 : 0;
   const int seg = lo_seg > 0 ? lo_seg : ldz;
   HN_REQUIRE(seg >= c_raw + F * n_axes && ldz >= lo_seg + seg, "build_z_large: bad output layout");
@@ -867,6 +900,19 @@ int launch_build_z_large(const float* raw, __half* z, int ldz, int lo_seg, int b
   const long total = static_cast<long>(batch) * N;
   const unsigned grid = static_cast<unsigned>((total + 7) / 8);
   const int n_feat = F * n_axes;
+  if (in_dtype == 1) {
+    HN_CHECK_CUDA(launch_k(build_z_large_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, stream,
+                           static_cast<const __nv_bfloat16*>(raw_v), z, ldz, seg, lo_seg, total, N, c_raw, ax, F, tab, tok0));
+    HN_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
+  if (in_dtype == 2) {
+    HN_CHECK_CUDA(launch_k(build_z_large_kernel<__half>, dim3(grid), dim3(256), 0, stream,
+                           static_cast<const __half*>(raw_v), z, ldz, seg, lo_seg, total, N, c_raw, ax, F, tab, tok0));
+    HN_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
+  const float* raw = static_cast<const float*>(raw_v);
   const bool fast = c_raw % 4 == 0 && c_raw >= 4 && c_raw <= 1024 && n_feat <= 32 && N < (1L << 31) &&
                     (reinterpret_cast<uintptr_t>(raw) & 15) == 0 && ldz % 4 == 0 && lo_seg % 4 == 0 &&
                     (reinterpret_cast<uintptr_t>(z) & 7) == 0;
@@ -880,7 +926,7 @@ int launch_build_z_large(const float* raw, __half* z, int ldz, int lo_seg, int b
     HN_CHECK_CUDA(launch_k(build_z_large_fast_kernel<8>, dim3(grid), dim3(256), 0, stream, raw, z, ldz, seg, lo_seg, total,
                            N, c_raw, ax, F, tab, tok0));
   else
-    HN_CHECK_CUDA(launch_k(build_z_large_kernel, dim3(grid), dim3(256), 0, stream, raw, z, ldz, seg, lo_seg, total, N,
+    HN_CHECK_CUDA(launch_k(build_z_large_kernel<float>, dim3(grid), dim3(256), 0, stream, raw, z, ldz, seg, lo_seg, total, N,
                            c_raw, ax, F, tab, tok0));
   HN_CHECK_CUDA(cudaGetLastError());
   return 0;

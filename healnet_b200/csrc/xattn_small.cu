@@ -815,18 +815,16 @@ int small_attention_pick_nsplit(int batch, int L, int H, long N, int kd) {
 // volume, batch 4: 2.45 ms vs 2.36 ms; poly-share sweep in profiles/r2_attn_small_experiments.md): the kernel is bound
 // by instruction issue (4.8 instructions per element at thread-per-row, 5.6 at 16 rows per warp), not by latency.
 // It stays in DEBUG builds (HN_SMALL_SW=8) as the record of that experiment.
-static int softmax_warps() {
 #ifdef HN_DEBUG
+static int softmax_warps() {
   static int sw = 0;
   if (sw == 0) {
     const char* e = getenv("HN_SMALL_SW");
     sw = (e != nullptr && e[0] == '8') ? 8 : 4;
   }
   return sw;
-#else
-  return 4;
-#endif
 }
+#endif
 
 template <int PMODE>
 static int launch_small_variant(const AttnArgs& a, cudaStream_t stream) {

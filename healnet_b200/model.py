@@ -447,6 +447,11 @@ class HealNet(nn.Module):
         tok_begin = tok_count = None
         if self._token_shard is not None:
             tok_begin, tok_count = [0] * M, [0] * M
+        # inputs that all arrive in one 16-bit floating type are consumed as they are (hn_set_io_dtype): no widened
+        # copy, half the host-to-device bytes; anything else is staged as fp32 (the reference's dtype follows its
+        # inputs, healnet.py:212)
+        given = {t.dtype for t in tensors[:M] if t is not None}
+        io_dtype = given.pop() if len(given) == 1 and next(iter(given)) in (torch.bfloat16, torch.float16) else torch.float32
         for i in range(min(n_given, M)):
             data = tensors[i]
             if data is None:
@@ -474,7 +479,7 @@ class HealNet(nn.Module):
                 lo, hi = token_shard_bounds(axis_tokens[i], world, rank)
                 tok_begin[i], tok_count[i] = lo, hi - lo
                 data = data.reshape(b, axis_tokens[i], c)[:, lo:hi]
-            staged[i], ready[i] = self._stage_input(data, dev)
+            staged[i], ready[i] = self._stage_input(data, dev, io_dtype)
         if batch is None:
             # reference: `b` is unbound -> UnboundLocalError at :225
             raise UnboundLocalError("cannot infer the batch size: every modality is missing")
@@ -524,6 +529,8 @@ class HealNet(nn.Module):
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             self._sync_native(dev, stream)
+            check(lib.hn_set_io_dtype(self._handle, {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}[io_dtype]),
+                  "hn_set_io_dtype")
             params = [p for p in self.parameters()]
             differentiable = torch.is_grad_enabled() and any(p.requires_grad for p in params)
             if differentiable:
@@ -555,19 +562,19 @@ class HealNet(nn.Module):
             return out.to(dtype=ret_dtype)
         return out.to(device=ret_dev, dtype=ret_dtype)
 
-    def _stage_input(self, data: torch.Tensor, dev: torch.device):
-        """-> (fp32 contiguous device tensor, event or None). Pinned host tensors are copied on a side stream and
+    def _stage_input(self, data: torch.Tensor, dev: torch.device, dtype: torch.dtype = torch.float32):
+        """-> (contiguous device tensor of `dtype`, event or None). Pinned host tensors are copied on a side stream and
         the forward waits for each modality's copy only where it first reads it (hn_forward_ex), so the transfer
         of a large late modality overlaps the work on the earlier ones."""
         if data.device == dev:
-            return data.to(dtype=torch.float32).contiguous(), None
+            return data.to(dtype=dtype).contiguous(), None
         # (a token-sharded slice of a pinned tensor is contiguous per sample: copied sample by sample, still async)
         per_sample = data.dim() == 3 and not data.is_contiguous() and all(data[i].is_contiguous() for i in range(data.shape[0]))
-        if data.device.type == "cpu" and data.is_pinned() and data.dtype == torch.float32 and (data.is_contiguous() or per_sample):
+        if data.device.type == "cpu" and data.is_pinned() and data.dtype == dtype and (data.is_contiguous() or per_sample):
             if self._copy_stream is None or self._copy_stream.device != dev:
                 self._copy_stream = torch.cuda.Stream(device=dev)
             cur = torch.cuda.current_stream(dev)
-            out = torch.empty(data.shape, dtype=torch.float32, device=dev)   # allocated on the compute stream
+            out = torch.empty(data.shape, dtype=dtype, device=dev)   # allocated on the compute stream
             self._copy_stream.wait_stream(cur)                              # ...whose earlier users must be done
             with torch.cuda.stream(self._copy_stream):
                 if per_sample:
@@ -579,7 +586,7 @@ class HealNet(nn.Module):
                 ev = torch.cuda.Event()
                 ev.record(self._copy_stream)
             return out, ev
-        return data.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous(), None
+        return data.to(device=dev, dtype=dtype, non_blocking=True).contiguous(), None
 
     def _launch(self, lib, staged, ready, axis_sizes, skip_self, mask_dev, mask_tokens, batch, want_latents, dev,
                 stream, tok_begin=None, tok_count=None):

@@ -84,7 +84,8 @@ HN_API int hn_pack_weights(hn_handle* h, void* cuda_stream);
 HN_API size_t hn_workspace_bytes(const hn_handle* h, int batch, const int* axis_sizes);
 
 /* Replaces HealNet.forward (healnet.py:190-250), default verbose=False semantics.
- *   modality_ptrs[m] : fp32 (batch, *axes_m, channel_dims[m]) row-major channel-last, or NULL when the
+ *   modality_ptrs[m] : (batch, *axes_m, channel_dims[m]) row-major channel-last, fp32 unless hn_set_io_dtype says
+ *                      otherwise, or NULL when the
  *                      modality is missing (its cross-attention + cross-FF are skipped, the latent
  *                      self-attention block still runs — healnet.py:229-245).
  *   skip_latent_block: optional n_modalities flags; nonzero also skips the latent self-attention + FF that
@@ -97,6 +98,12 @@ HN_API size_t hn_workspace_bytes(const hn_handle* h, int batch, const int* axis_
 HN_API int hn_forward(hn_handle* h, int batch, const void* const* modality_ptrs, const int* axis_sizes,
                       const int* skip_latent_block, const uint8_t* mask, long mask_tokens, float* latents_out,
                       float* logits_out, void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* Element type of the modality input buffers handed to hn_forward* from now on: 0 = fp32 (default), 1 = bf16,
+ * 2 = fp16 — the reference's dtype follows its inputs (healnet.py:212; BASELINE config 3 runs in bf16). The rows are
+ * widened on the fly while they are standardised (no fp32 copy of the inputs exists anywhere); parameters are
+ * registered in fp32, outputs are fp32. */
+HN_API int hn_set_io_dtype(hn_handle* h, int dtype);
 
 /* hn_forward with per-modality "input ready" events: modality_ready_events[m] (a cudaEvent_t, or NULL) is waited on
  * by the forward's stream right before modality m's buffer is first read (just ahead of its layer-0 cross-attention),

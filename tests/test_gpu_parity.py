@@ -218,6 +218,28 @@ def test_bf16_module_and_inputs():
     torch.testing.assert_close(got.float().cpu(), want, rtol=1e-2, atol=2e-2)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_native_16bit_inputs_equal_widened_inputs(dtype):
+    """Inputs that all arrive in bf16 / fp16 are read as they are (hn_set_io_dtype: widened while the context rows are
+    standardised). Widening is exact, so the result must be bit-identical to the forward of the same values passed
+    as fp32 — on the small-context streaming path, the generic path and the tabular row."""
+    kw, shapes = ORACLE_CASES["readme_reduced"]
+    torch.manual_seed(13)
+    model = HealNet(**kw).eval().cuda()
+    xs = [torch.rand(s).to(dtype).cuda() for s in shapes]
+    with torch.no_grad():
+        a = model(list(xs))
+        b = model([t.float() for t in xs])
+        assert a.dtype == dtype and torch.equal(a.float(), b.to(dtype).float())
+        a_lat = model(list(xs), return_embeddings=True)
+        b_lat = model([t.float() for t in xs], return_embeddings=True)
+        assert torch.equal(a_lat.float(), b_lat.to(dtype).float())
+        kw2, shapes2 = ORACLE_CASES["omic_wsi"]
+        m2 = HealNet(**kw2).eval().cuda()
+        ys = [torch.rand(s).to(dtype).cuda() for s in shapes2]
+        assert torch.equal(m2(list(ys)).float(), m2([t.float() for t in ys]).to(dtype).float())
+
+
 def test_pinned_host_inputs_overlap_path():
     """Pinned host tensors take the side-stream copy + per-modality ready-event path (hn_forward_ex); the result must
     be bit-identical to the device-resident call, call after call."""
