@@ -44,7 +44,7 @@ if os.path.exists(rep):
     tob = lambda k: float(d[k][0].replace(",", "")) * scale[d[k][1]]
     out["dram_bytes_per_launch"] = tob("dram__bytes_read.sum") + tob("dram__bytes_write.sum")
     out["kernel"] = d["Kernel Name"][0]
-    out["command"] = ("ncu --set full --clock-control none --import-source on -k regex:attn_small_kernel -s 7 -c 1 "
+    out["command"] = ("ncu --set full --clock-control none --import-source on -k regex:attn_small_kernel -s 15 -c 1 "
                       "python bench.py --steps 1 --warmup 3 --no-cpu")
     json.dump(out, open(os.path.join(P, f"{tag}_attn_small_kernel_summary.json"), "w"), indent=1)
     print({k: out[k]["value"] for k in keys[:8] if k in out})
@@ -69,7 +69,7 @@ if os.path.exists(lst):
     a, b = idx[-2] + 1, idx[-1] + 1
     with open(os.path.join(P, f"{tag}_launches_summary.md"), "w") as f:
         f.write(f"# {tag} — launch list of `python bench.py --steps 2 --warmup 3 --no-cpu` under ncu\n\n")
-        f.write("Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file "
+        f.write("Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file "
                 f"gpurun_out/launches_{tag}.csv python bench.py --steps 2 --warmup 3 --no-cpu`\n")
         f.write(f"Raw per-launch list: `profiles/{tag}_launches.csv` ({len(seq)} launches = one weight-packing pass + 9 "
                 "forwards). Per-launch times under ncu are cold-cache and serialised (programmatic dependent launch "
