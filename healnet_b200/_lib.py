@@ -72,6 +72,7 @@ SIGNATURES = {
     "hn_forward_train": (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int), POINTER(c_int),
                                  c_void_p, c_long, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
     "hn_set_grads": (c_int, [c_void_p, c_int, c_int, POINTER(c_void_p), c_int]),
+    "hn_set_backward_variant": (c_int, [c_void_p, c_int]),
     "hn_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p, c_size_t,
                             c_void_p]),
     "hn_set_io_dtype": (c_int, [c_void_p, c_int]),

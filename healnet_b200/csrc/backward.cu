@@ -138,6 +138,8 @@ struct BwdScratch {
   float *dO, *dq, *ofull, *qf;
   float *S, *dP, *dKV, *dWp, *sv;
   float *u32, *cnu, *g, *du, *w, *rl, *dr, *dw, *delta, *dr_part;
+  __half *rq, *duq;            // tensor-core streaming backward: split operand rows
+  float *row_a, *row_d, *row_s;
   float* dpooled;
   size_t bytes;
 };
@@ -152,14 +154,19 @@ void plan_scratch(const hn_handle* h, int batch, const Workspace& ws, char* base
   const size_t Imax = static_cast<size_t>(I > lI ? I : lI);
   const size_t Hmax = static_cast<size_t>(d.x_heads > d.l_heads ? d.x_heads : d.l_heads);
   size_t n_gen = d.self_per_cross_attn ? L : 0, c_gen = d.self_per_cross_attn ? D : 0, c_small = 0;
-  size_t sp_part = 0;
+  size_t sp_part = 0, zw_max = 0;
   for (int m = 0; m < M; ++m) {
     const ModPlan& mp = ws.mod[m];
     if (!mp.present) continue;
     if (mp.small) {
       c_small = static_cast<size_t>(mp.C) > c_small ? mp.C : c_small;
-      const size_t part = static_cast<size_t>(small_attn_bwd_nsplit(batch, d.x_heads, L, mp.Nl)) * rows * d.x_heads * mp.C;
+      size_t part = static_cast<size_t>(small_attn_bwd_nsplit(batch, d.x_heads, L, mp.Nl)) * rows * d.x_heads * mp.C;
+      // tensor-core variant: one [128-row block][zw] partial per (sample, split, head, latent tile)
+      const size_t part_tc = static_cast<size_t>(batch) * small_attention_pick_nsplit(batch, L, d.x_heads, mp.Nl, mp.zw) *
+                             d.x_heads * ((L + 127) / 128) * 128 * mp.zw;
+      part = part_tc > part ? part_tc : part;
       sp_part = part > sp_part ? part : sp_part;
+      zw_max = static_cast<size_t>(mp.zw) > zw_max ? mp.zw : zw_max;
     } else {
       n_gen = static_cast<size_t>(mp.Nl) > n_gen ? mp.Nl : n_gen;
       c_gen = static_cast<size_t>(mp.C) > c_gen ? mp.C : c_gen;
@@ -195,6 +202,11 @@ void plan_scratch(const hn_handle* h, int batch, const Workspace& ws, char* base
   s.dw = ar.take<float>(rc);
   s.delta = ar.take<float>(rows * d.x_heads);
   s.dr_part = ar.take<float>(sp_part);
+  s.rq = ar.take<__half>(rows * 2 * d.x_heads * zw_max);
+  s.duq = ar.take<__half>(rows * 2 * d.x_heads * zw_max);
+  s.row_a = ar.take<float>(rows * d.x_heads);
+  s.row_d = ar.take<float>(rows * d.x_heads);
+  s.row_s = ar.take<float>(rows * d.x_heads);
   s.dpooled = ar.take<float>(static_cast<size_t>(batch) * D);
   s.bytes = ar.off + 256;
 }
@@ -314,6 +326,12 @@ size_t hn_backward_scratch_bytes(const hn_handle* h, int batch, const int* axis_
   BwdScratch s;
   plan_scratch(h, batch, ws, nullptr, s);
   return s.bytes;
+}
+
+int hn_set_backward_variant(hn_handle* h, int variant) {
+  HN_REQUIRE(h != nullptr && (variant == 0 || variant == 1), "hn_set_backward_variant: 0 (tensor cores) or 1 (fp32 checker)");
+  h->bwd_variant = variant;
+  return 0;
 }
 
 int hn_forward_train(hn_handle* h, int batch, const void* const* modality_ptrs, void* const* modality_ready_events,
@@ -441,24 +459,50 @@ int hn_backward(hn_handle* h, const float* grad_latents, const float* grad_logit
       BW(sg(st, R, C, dh, F32(s.qf, I, 1, dh), F32(Wkv, C, 1, static_cast<long>(dh) * C), s.w, static_cast<long>(H) * C, 1.f,
             0, H, C));
       BW(launch_scale_cols(s.w, gamma, c_nat * LOG2E, C, RH * C, s.rl, st));
-      SmallBwdArgs sa;
-      sa.r = s.rl;
-      sa.du = s.du;
-      sa.delta = s.delta;
-      sa.stats = stats;
-      sa.z = mp.z;
-      sa.z_ld = 2 * zw;
-      sa.z_lo = zw;
-      sa.mask_bits = mp.masked ? ws.mask_bits : nullptr;
-      sa.dr_part = s.dr_part;
-      sa.batch = batch;
-      sa.H = H;
-      sa.L = L;
-      sa.C = C;
-      sa.nsplit = small_attn_bwd_nsplit(batch, H, L, mp.Nl);
-      sa.N = mp.Nl;
-      sa.R_total = RH;
-      BW(launch_small_attn_bwd(sa, s.dr, st));
+      if (h->bwd_variant == 0) {
+        // tensor-core streaming pass (xattn_small.cu: attn_small_bwd_kernel)
+        const int ld = 2 * H * zw;
+        BW(launch_small_bwd_prep(s.rl, s.du, s.delta, stats, batch, H, L, C, zw, s.rq, s.duq, ld, H * zw, s.row_a, s.row_d,
+                                 s.row_s, st));
+        SmallBwdTcArgs ta;
+        ta.rq = s.rq;
+        ta.duq = s.duq;
+        ta.rq_ld = ld;
+        ta.lo_off = H * zw;
+        ta.z = mp.z;
+        ta.kd = zw;
+        ta.row_a = s.row_a;
+        ta.row_d = s.row_d;
+        ta.mask_bits = mp.masked ? ws.mask_bits : nullptr;
+        ta.part = s.dr_part;
+        ta.batch = batch;
+        ta.H = H;
+        ta.L = L;
+        ta.nsplit = small_attention_pick_nsplit(batch, L, H, mp.Nl, zw);
+        ta.N = mp.Nl;
+        BW(launch_small_attention_bwd(ta, st));
+        BW(launch_small_bwd_finish(s.dr_part, s.row_s, batch, ta.nsplit, H, L, C, zw, s.dr, st));
+      } else {
+        // exact fp32 SIMT pass (bwdops.cu), kept as the checker of the tensor-core kernel
+        SmallBwdArgs sa;
+        sa.r = s.rl;
+        sa.du = s.du;
+        sa.delta = s.delta;
+        sa.stats = stats;
+        sa.z = mp.z;
+        sa.z_ld = 2 * zw;
+        sa.z_lo = zw;
+        sa.mask_bits = mp.masked ? ws.mask_bits : nullptr;
+        sa.dr_part = s.dr_part;
+        sa.batch = batch;
+        sa.H = H;
+        sa.L = L;
+        sa.C = C;
+        sa.nsplit = small_attn_bwd_nsplit(batch, H, L, mp.Nl);
+        sa.N = mp.Nl;
+        sa.R_total = RH;
+        BW(launch_small_attn_bwd(sa, s.dr, st));
+      }
       BW(launch_colsum(1, s.w, C, s.dr, C, nullptr, RH, C, c_nat, ga[2], 1, s.colpart, st));    // dgamma += c sum w * dr
       BW(launch_scale_cols(s.dr, gamma, c_nat, C, RH * C, s.dw, st));                            // dw = c gamma * dr
       BW(sg(st, R, dh, C, F32(s.dw, static_cast<long>(H) * C, 1, C), F32(Wkv, 1, C, static_cast<long>(dh) * C), s.dq, I, 1.f, 0,

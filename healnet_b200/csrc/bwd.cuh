@@ -48,6 +48,32 @@ struct SmallBwdArgs {
   long N, R_total;
 };
 int small_attn_bwd_nsplit(int batch, int H, int L, long N);
+
+// tensor-core version of the same pass (xattn_small.cu: attn_small_bwd_kernel). R / DU: split fp16 rows
+// [b][L][rq_ld], head h at columns h*kd (hi) and lo_off + h*kd (lo); R carries P_SHIFT - M in column C of its hi part;
+// DU rows scaled by a per-row power of two; part: [b][nsplit][H][L][kd] fp32 partial accumulators of dR.
+struct SmallBwdTcArgs {
+  const __half* rq;
+  const __half* duq;
+  int rq_ld, lo_off;
+  const __half* z;      // [b][N][2 kd] = [hi | lo]
+  int kd;
+  const float* row_a;   // [(b*L + l)*H + h]
+  const float* row_d;
+  const uint64_t* mask_bits;
+  float* part;
+  int batch, H, L, nsplit;
+  long N;
+};
+int launch_small_attention_bwd(const SmallBwdTcArgs& a, cudaStream_t stream);
+// r / du / delta / stats -> the kernel's operands (R, DU split rows, per-row factors); scale[R] = the power of two DU was
+// multiplied with. Buffers rq / duq must hold rows * rq_ld halves.
+int launch_small_bwd_prep(const float* r, const float* du, const float* delta, const float* stats, int batch, int H,
+                          int L, int C, int kd, __half* rq, __half* duq, int rq_ld, int lo_off, float* row_a,
+                          float* row_d, float* scale, cudaStream_t st);
+// dr[R][C] = (sum over splits of part) / scale
+int launch_small_bwd_finish(const float* part, const float* scale, int batch, int nsplit, int H, int L, int C, int kd,
+                            float* dr, cudaStream_t st);
 int launch_small_attn_bwd(const SmallBwdArgs& a, float* dr, cudaStream_t st);
 
 }  // namespace hn

@@ -511,6 +511,69 @@ __global__ void sum_splits_kernel(const float* __restrict__ part, int nsplit, lo
   }
 }
 
+// operands of the tensor-core streaming backward (xattn_small.cu): one warp per (row, head)
+__global__ void __launch_bounds__(256) small_bwd_prep_kernel(const float* __restrict__ r, const float* __restrict__ du,
+                                                             const float* __restrict__ delta,
+                                                             const float* __restrict__ stats, int batch, int H, int L,
+                                                             int C, int kd, __half* __restrict__ rq,
+                                                             __half* __restrict__ duq, int rq_ld, int lo_off,
+                                                             float* __restrict__ row_a, float* __restrict__ row_d,
+                                                             float* __restrict__ scale) {
+  HN_PDL_LAUNCH();
+  HN_PDL_WAIT();
+  const int lane = threadIdx.x & 31;
+  const long R = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);   // (b*L + l)*H + h
+  if (R >= static_cast<long>(batch) * L * H) return;
+  const int h = static_cast<int>(R % H);
+  const long bl = R / H;
+  const int l = static_cast<int>(bl % L), b = static_cast<int>(bl / L);
+  float mx = 0.f;
+  for (int c = lane; c < C; c += 32) mx = fmaxf(mx, fabsf(du[R * C + c]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  const float s = (mx > 0.f && mx < INFINITY) ? exp2f(-static_cast<float>(ilogbf(mx))) : 1.f;
+  const long st = (static_cast<long>(b) * H + h) * L + l;
+  const float M = stats[2 * st], den = stats[2 * st + 1];
+  const bool dead = !(den > 0.f) || M == -INFINITY;   // fully masked row
+  __half* rr = rq + bl * rq_ld + h * kd;
+  __half* dr = duq + bl * rq_ld + h * kd;
+  for (int c = lane; c < kd; c += 32) {
+    float rv = 0.f, dv = 0.f;
+    if (c < C) {
+      rv = r[R * C + c];
+      dv = du[R * C + c] * s;
+    } else if (c == C) {
+      rv = dead ? 0.f : 10.f - M;   // P_SHIFT - M: exactly the fp16 value the forward folded into Q'
+    }
+    const __half rh = __float2half_rn(rv), dh = __float2half_rn(dv);
+    rr[c] = rh;
+    rr[lo_off + c] = __float2half_rn(rv - __half2float(rh));
+    dr[c] = dh;
+    dr[lo_off + c] = __float2half_rn(dv - __half2float(dh));
+  }
+  if (lane == 0) {
+    row_a[R] = dead ? 0.f : 0.0009765625f / den;
+    row_d[R] = delta[R] * s;
+    scale[R] = s;
+  }
+}
+__global__ void small_bwd_finish_kernel(const float* __restrict__ part, const float* __restrict__ scale, int batch,
+                                        int nsplit, int H, int L, int C, int kd, float* __restrict__ dr) {
+  HN_PDL_LAUNCH();
+  HN_PDL_WAIT();
+  const long n = static_cast<long>(batch) * L * H * C;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const long R = i / C;
+    const int h = static_cast<int>(R % H);
+    const long bl = R / H;
+    const int l = static_cast<int>(bl % L), b = static_cast<int>(bl / L);
+    float s = 0.f;
+    for (int k = 0; k < nsplit; ++k) s += part[((((static_cast<long>(b) * nsplit + k) * H + h) * L) + l) * kd + c];
+    dr[i] = s / scale[R];
+  }
+}
+
 inline unsigned ew_grid(long n) {
   const long g = (n + 255) / 256;
   return static_cast<unsigned>(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
@@ -614,6 +677,22 @@ int launch_kv_fold_bwd(const float* dWp, const float* W, const float* gamma, con
                        int rows2I, int I, int C, float* gW, float* ggamma, float* gbeta, cudaStream_t st) {
   HN_CHECK_CUDA(launch_k(kv_fold_bwd_kernel, dim3((C + 31) / 32), dim3(256), 0, st, dWp, W, gamma, beta, sv, rows2I, I, C, gW,
                          ggamma, gbeta));
+  HN_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_small_bwd_prep(const float* r, const float* du, const float* delta, const float* stats, int batch, int H,
+                          int L, int C, int kd, __half* rq, __half* duq, int rq_ld, int lo_off, float* row_a,
+                          float* row_d, float* scale, cudaStream_t st) {
+  const long R = static_cast<long>(batch) * L * H;
+  HN_CHECK_CUDA(launch_k(small_bwd_prep_kernel, dim3(static_cast<unsigned>((R + 7) / 8)), dim3(256), 0, st, r, du, delta, stats,
+                         batch, H, L, C, kd, rq, duq, rq_ld, lo_off, row_a, row_d, scale));
+  HN_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_small_bwd_finish(const float* part, const float* scale, int batch, int nsplit, int H, int L, int C, int kd,
+                            float* dr, cudaStream_t st) {
+  const long n = static_cast<long>(batch) * L * H * C;
+  HN_CHECK_CUDA(launch_k(small_bwd_finish_kernel, dim3(ew_grid(n)), dim3(256), 0, st, part, scale, batch, nsplit, H, L, C, kd, dr));
   HN_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -120,6 +120,7 @@ struct hn_handle {
   std::vector<std::vector<float*>> g;
   hn::TrainState train;
   char* tape = nullptr;   // non-null only while a training-mode forward is recording
+  int bwd_variant = 0;    // 0: tensor-core kernels for the heavy backward contractions; 1: exact fp32 SIMT checkers
 };
 
 

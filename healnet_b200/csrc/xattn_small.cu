@@ -42,6 +42,7 @@
 #include <cstdlib>
 #include <type_traits>
 
+#include "bwd.cuh"
 #include "common.cuh"
 #include "tc05.cuh"
 
@@ -727,6 +728,285 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 }
 
 
+// =====================================================================================================================
+// Streaming BACKWARD of the small-context cross-attention on the same machinery (training step).
+// No gradient flows into the context rows z, so the backward of the whole streaming pass is, per (sample, head, row l),
+//     dr_l = sum_t dt_lt z_t ,   dt_lt = p_lt (du_l . z_t - delta_l) ,   p_lt = 2^(r_l . z_t - M_l) / den_l
+// (r = log2-unit score vector of the row, du = gradient w.r.t. u_l = sum_t p_lt z_t, delta_l = du_l . u_l; M, den saved
+// by the forward). One more pass over the token axis with the forward's tile pipeline:
+//     S'(i) = R . z_i^T   (SS, three fp16 terms; R carries P_SHIFT - M in the column where z holds its 1.0)
+//     G (i) = DU . z_i^T  (SS, DU split hi + lo: two terms)
+//     softmax warps: dt = 2^S' * a_l * (G - delta_l), a_l = 2^-P_SHIFT / den_l  -> fp16 over the first half of S'
+//     dR += dt . z_i      (TS, dt from TMEM) — accumulator [128 x KD] fp32 per row block
+// DU rows arrive scaled by a per-row power of two (so that fp16 dt keeps its precision whatever the size of the
+// incoming gradient); the caller undoes the scale. There is no running max here (M is known), hence no exact path:
+// every tile is the steady state. S' and G are single-buffered (TMEM: 64 + 64 + KD columns per row block, three row
+// blocks per CTA as in the forward): a row block's tensor and softmax phases alternate, the other two fill the gaps.
+// Out-of-range tokens of a ragged last tile have z = 0 (TMA zero fill) and drop out of dt . z by themselves; masked
+// tokens are zeroed in dt.
+struct SmallBwdDev {
+  int L, H, batch, nsplit, n_ltiles, n_rb, ctas_per_stream, tiles_total;
+  int lo_off;           // column offset of the lo parts inside R / DU rows
+  long N;
+  const uint64_t* mask_bits;
+  const float* row_a;   // [(b*L + l)*H + h]  2^-P_SHIFT / den
+  const float* row_d;   // [(b*L + l)*H + h]  delta (scaled like DU)
+  float* part;          // [b][nsplit][H][L][KD] fp32
+};
+
+template <int KD, int G>
+__global__ void __launch_bounds__((5 * G + 1) * 32, 1)
+attn_small_bwd_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmDU,
+                      const __grid_constant__ CUtensorMap tmZ, SmallBwdDev p) {
+  constexpr int NSB = KD == 64 ? 4 : NST;  // z ring depth (the four operand tiles per row block take the room)
+  constexpr int Q_TILE = BM * KD * 2;     // one [128][KD] fp16 tile
+  constexpr int Q_GROUP = 4 * Q_TILE;     // per row block: [R_hi | R_lo | DU_hi | DU_lo]
+  constexpr int Z_BYTES = BT * KD * 2;
+  constexpr int Z_STAGE = 2 * Z_BYTES;    // [z_hi | z_lo]
+  constexpr uint32_t LAYOUT = (KD == 64) ? SWZ_128B : SWZ_64B;
+  constexpr uint32_t SBO = 8 * KD * 2;
+  constexpr uint32_t V_KADV = 16 * KD * 2;
+  constexpr int GCOLS = 2 * 64 + KD;      // S' | G | dR
+  static_assert(G * GCOLS <= 512, "TMEM budget");
+  constexpr uint32_t idesc_s = idesc_f16(BM, BT, false, false);
+  constexpr uint32_t idesc_u = idesc_f16(BM, KD, false, true);
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sZ = smem + G * Q_GROUP;
+  __shared__ uint64_t q_full, z_full[NST], z_empty[NST];
+  __shared__ uint64_t sg_full[MAXG], p_ready[MAXG], acc_done[MAXG];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int idx = blockIdx.x;
+  const int cta_rb = idx % p.ctas_per_stream;
+  idx /= p.ctas_per_stream;
+  const int b = idx % p.batch;
+  const int split = idx / p.batch;
+  const int rb0 = cta_rb * G;
+  const int n_active = (p.n_rb - rb0) < G ? (p.n_rb - rb0) : G;
+  const int t_begin = static_cast<int>(static_cast<long>(p.tiles_total) * split / p.nsplit);
+  const int t_end = static_cast<int>(static_cast<long>(p.tiles_total) * (split + 1) / p.nsplit);
+  const int n = t_end - t_begin;
+
+  if (n <= 0) {  // more splits than tiles: empty partial
+    HN_PDL_WAIT();
+    for (int g = 0; g < n_active; ++g) {
+      const int rb = rb0 + g, h = rb / p.n_ltiles, lt = rb % p.n_ltiles;
+      const long row0 = ((static_cast<long>(b) * p.nsplit + split) * p.H + h) * p.L + lt * BM;
+      for (int r = threadIdx.x; r < BM; r += blockDim.x)
+        if (lt * BM + r < p.L)
+          for (int c = 0; c < KD; ++c) p.part[(row0 + r) * KD + c] = 0.f;
+    }
+    return;
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(&q_full, 1);
+    for (int s = 0; s < NSB; ++s) {
+      mbar_init(&z_full[s], 1);
+      mbar_init(&z_empty[s], n_active);
+    }
+    for (int g = 0; g < MAXG; ++g) {
+      mbar_init(&sg_full[g], 1);
+      mbar_init(&p_ready[g], 4);
+      mbar_init(&acc_done[g], 1);
+    }
+    fence_mbar_init();
+  }
+  constexpr int PRODUCER_WARP = 5 * G;
+  if (warp == PRODUCER_WARP) tmem_alloc<512>(&tmem_base_s);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  HN_PDL_LAUNCH();
+  HN_PDL_WAIT();
+
+  if (warp == PRODUCER_WARP) {
+    if (elect_one()) {
+      tma_prefetch_desc(&tmR);
+      tma_prefetch_desc(&tmDU);
+      tma_prefetch_desc(&tmZ);
+      mbar_arrive_expect_tx(&q_full, n_active * Q_GROUP);
+      for (int g = 0; g < n_active; ++g) {
+        const int rb = rb0 + g, h = rb / p.n_ltiles, lt = rb % p.n_ltiles;
+        uint8_t* q = sQ + g * Q_GROUP;
+        tma_load_3d(q, &tmR, &q_full, h * KD, lt * BM, b);
+        tma_load_3d(q + Q_TILE, &tmR, &q_full, p.lo_off + h * KD, lt * BM, b);
+        tma_load_3d(q + 2 * Q_TILE, &tmDU, &q_full, h * KD, lt * BM, b);
+        tma_load_3d(q + 3 * Q_TILE, &tmDU, &q_full, p.lo_off + h * KD, lt * BM, b);
+      }
+      for (int i = 0; i < n; ++i) {
+        const int s = i % NSB;
+        mbar_wait_sleepy(&z_empty[s], ((i / NSB) & 1) ^ 1, 20000);
+        mbar_arrive_expect_tx(&z_full[s], Z_STAGE);
+        tma_load_3d(sZ + s * Z_STAGE, &tmZ, &z_full[s], 0, (t_begin + i) * BT, b);
+        tma_load_3d(sZ + s * Z_STAGE + Z_BYTES, &tmZ, &z_full[s], KD, (t_begin + i) * BT, b);
+      }
+    }
+  } else if (warp >= 4 * G) {
+    const int g = warp - 4 * G;
+    if (g < n_active && elect_one()) {
+      const uint32_t tG = tmem + g * GCOLS;
+      const uint32_t q0 = smem_u32(sQ + g * Q_GROUP);
+      mbar_wait(&q_full, 0);
+      for (int i = 0; i < n; ++i) {
+        const int s = i % NSB;
+        mbar_wait(&z_full[s], (i / NSB) & 1);
+        fence_after_sync();
+        const uint32_t z0 = smem_u32(sZ + s * Z_STAGE);
+        // S' = R_hi.z_hi + R_lo.z_hi + R_hi.z_lo ; G = DU_hi.z_hi + DU_lo.z_hi   (tensor pipe executes in issue order:
+        // the previous tile's dt . z has consumed S' columns 0..31 before these overwrite them)
+#pragma unroll
+        for (int k = 0; k < KD / 16; ++k)
+          umma_ss(tG, smem_desc(q0 + k * 32, 16, SBO, LAYOUT), smem_desc(z0 + k * 32, 16, SBO, LAYOUT), idesc_s, k != 0);
+#pragma unroll
+        for (int k = 0; k < KD / 16; ++k)
+          umma_ss(tG, smem_desc(q0 + Q_TILE + k * 32, 16, SBO, LAYOUT), smem_desc(z0 + k * 32, 16, SBO, LAYOUT), idesc_s, true);
+#pragma unroll
+        for (int k = 0; k < KD / 16; ++k)
+          umma_ss(tG, smem_desc(q0 + k * 32, 16, SBO, LAYOUT), smem_desc(z0 + Z_BYTES + k * 32, 16, SBO, LAYOUT), idesc_s, true);
+#pragma unroll
+        for (int k = 0; k < KD / 16; ++k)
+          umma_ss(tG + 64, smem_desc(q0 + 2 * Q_TILE + k * 32, 16, SBO, LAYOUT), smem_desc(z0 + k * 32, 16, SBO, LAYOUT),
+                  idesc_s, k != 0);
+#pragma unroll
+        for (int k = 0; k < KD / 16; ++k)
+          umma_ss(tG + 64, smem_desc(q0 + 3 * Q_TILE + k * 32, 16, SBO, LAYOUT), smem_desc(z0 + k * 32, 16, SBO, LAYOUT),
+                  idesc_s, true);
+        umma_commit(&sg_full[g]);
+        mbar_wait_sleepy(&p_ready[g], i & 1, 20000);
+        fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < BT / 16; ++k)
+          umma_ts(tG + 128, tG + k * 8, smem_desc(z0 + k * V_KADV, 16, SBO, LAYOUT), idesc_u, (i | k) != 0);
+        umma_commit(&z_empty[s]);
+        if (i + 1 == n) umma_commit(&acc_done[g]);
+      }
+    }
+  } else {
+    const int g = warp >> 2;
+    if (g < n_active) {
+      const int rb = rb0 + g, h = rb / p.n_ltiles, lt = rb % p.n_ltiles;
+      const uint32_t lane_base = (warp & 3) * 32;
+      const int trow = lane_base + lane;
+      const int row = lt * BM + trow;
+      const uint32_t tL = tmem_addr(tmem + g * GCOLS, lane_base, 0);
+      const bool has_mask = p.mask_bits != nullptr;
+      float a_l = 0.f, d_l = 0.f;
+      if (row < p.L) {
+        const long R = (static_cast<long>(b) * p.L + row) * p.H + h;
+        a_l = p.row_a[R];
+        d_l = p.row_d[R];
+      }
+      const float ad = -a_l * d_l;
+      for (int i = 0; i < n; ++i) {
+        mbar_wait(&sg_full[g], i & 1);
+        fence_after_sync();
+        uint64_t bits = ~0ull;
+        if (has_mask) bits = p.mask_bits[static_cast<long>(b) * p.tiles_total + t_begin + i];
+        uint32_t pk[32];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t s[32], gq[32];
+          tmem_ld32(tL + c * 32, s);
+          tmem_ld32(tL + 64 + c * 32, gq);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float x0 = __uint_as_float(s[2 * j]), x1 = __uint_as_float(s[2 * j + 1]);
+            // w = a (G - delta)
+            const float w0 = fmaf(__uint_as_float(gq[2 * j]), a_l, ad), w1 = fmaf(__uint_as_float(gq[2 * j + 1]), a_l, ad);
+            if (j & 1) {  // half2 polynomial exponentials, product in half2
+              const uint32_t e = ex2_pair_h2(x0, x1);
+              const __half2 wh = __floats2half2_rn(w0, w1);
+              const __half2 r = __hmul2(*reinterpret_cast<const __half2*>(&e), wh);
+              pk[c * 16 + j] = *reinterpret_cast<const uint32_t*>(&r);
+            } else {
+              pk[c * 16 + j] = pack_half2(ex2_mufu(x0) * w0, ex2_mufu(x1) * w1);
+            }
+          }
+          if (has_mask) {
+            const uint32_t mb = static_cast<uint32_t>(bits >> (32 * c));
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const uint32_t keep = (((mb >> (2 * j)) & 1u) ? 0x0000FFFFu : 0u) | (((mb >> (2 * j + 1)) & 1u) ? 0xFFFF0000u : 0u);
+              pk[c * 16 + j] &= keep;
+            }
+          }
+        }
+        tmem_st32(tL, pk);  // dt(i) over S' columns 0..31 (all 64 columns of S' and G have been read)
+        tmem_wait_st();
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_ready[g]);
+        __syncwarp();
+      }
+      const long part_row = ((static_cast<long>(b) * p.nsplit + split) * p.H + h) * p.L + row;
+      mbar_wait(&acc_done[g], 0);
+      fence_after_sync();
+#pragma unroll
+      for (int c = 0; c < KD; c += 32) {
+        uint32_t u[32];
+        tmem_ld32(tL + 128 + c, u);
+        tmem_wait_ld();
+        if (row < p.L) {
+          float4* dst = reinterpret_cast<float4*>(p.part + part_row * KD + c);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            dst[j] = make_float4(__uint_as_float(u[4 * j]), __uint_as_float(u[4 * j + 1]), __uint_as_float(u[4 * j + 2]),
+                                 __uint_as_float(u[4 * j + 3]));
+        }
+        __syncwarp();
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == PRODUCER_WARP) tmem_dealloc<512>(tmem);
+}
+
+template <int KD, int G>
+int launch_small_bwd_t(const SmallBwdTcArgs& a, cudaStream_t stream) {
+  CUtensorMap tmR, tmDU, tmZ;
+  const CUtensorMapSwizzle swz = KD == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  const uint64_t ld = a.rq_ld;
+  if (!make_tmap_3d_f16(&tmR, a.rq, a.batch, a.L, ld, ld * 2, static_cast<uint64_t>(a.L) * ld * 2, BM, KD, swz) ||
+      !make_tmap_3d_f16(&tmDU, a.duq, a.batch, a.L, ld, ld * 2, static_cast<uint64_t>(a.L) * ld * 2, BM, KD, swz) ||
+      !make_tmap_3d_f16(&tmZ, a.z, a.batch, a.N, 2 * KD, static_cast<uint64_t>(2 * KD) * 2,
+                        static_cast<uint64_t>(a.N) * 2 * KD * 2, BT, KD, swz)) {
+    set_error("attention backward: cuTensorMapEncodeTiled failed");
+    return -2;
+  }
+  SmallBwdDev p;
+  p.L = a.L;
+  p.H = a.H;
+  p.batch = a.batch;
+  p.nsplit = a.nsplit;
+  p.n_ltiles = (a.L + BM - 1) / BM;
+  p.n_rb = p.n_ltiles * a.H;
+  p.ctas_per_stream = (p.n_rb + G - 1) / G;
+  p.tiles_total = static_cast<int>((a.N + BT - 1) / BT);
+  p.lo_off = a.lo_off;
+  p.N = a.N;
+  p.mask_bits = a.mask_bits;
+  p.row_a = a.row_a;
+  p.row_d = a.row_d;
+  p.part = a.part;
+  constexpr int SMEM_NEED = G * 4 * BM * KD * 2 + (KD == 64 ? 4 : NST) * 2 * BT * KD * 2 + 1024;
+  constexpr int SMEM = SMEM_NEED > 120 * 1024 ? SMEM_NEED : 120 * 1024;
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
+  const long grid = static_cast<long>(p.ctas_per_stream) * a.batch * a.nsplit;
+  HN_REQUIRE(grid > 0 && grid < 2147483647L, "attention backward: grid too large");
+  HN_CHECK_CUDA(cudaFuncSetAttribute(attn_small_bwd_kernel<KD, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+  HN_CHECK_CUDA(launch_k(attn_small_bwd_kernel<KD, G>, dim3(static_cast<unsigned>(grid)), dim3((5 * G + 1) * 32), SMEM, stream,
+                         tmR, tmDU, tmZ, p));
+  HN_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 template <int KD, int G, int PMODE, bool SPLIT, int SW>
 int launch_small_t(const AttnArgs& a, cudaStream_t stream) {
   CUtensorMap tmQ, tmZ;
@@ -783,6 +1063,14 @@ static int poly_mode() {
 }
 
 int small_attention_groups(int kd) { return kd == 32 ? 3 : 2; }
+
+int launch_small_attention_bwd(const SmallBwdTcArgs& a, cudaStream_t stream) {
+  HN_REQUIRE(a.batch > 0 && a.L > 0 && a.H > 0 && a.N > 0 && a.nsplit > 0, "attention backward: empty problem");
+  HN_REQUIRE(a.kd == 32 || a.kd == 64, "attention backward: context rows must be 32 or 64 wide");
+  HN_REQUIRE(a.rq_ld % 8 == 0 && a.lo_off >= a.H * a.kd && a.rq_ld >= a.lo_off + a.H * a.kd, "attention backward: bad row layout");
+  if (a.kd == 64) return launch_small_bwd_t<64, 2>(a, stream);
+  return launch_small_bwd_t<32, 3>(a, stream);
+}
 
 // Split the token axis so that the grid is a whole number of waves of one CTA per SM while each CTA still
 // streams enough tiles to amortise its prologue / epilogue.

@@ -303,6 +303,9 @@ class HealNet(nn.Module):
         self.last_launch_count = 0
         self._warned = set()
         self._train_seq = 0      # training-mode forwards so far: only the latest one can be back-propagated
+        # "tensor": heavy backward contractions on tensor cores (default); "fp32": the exact SIMT kernels they are
+        # checked against (hn_set_backward_variant)
+        self.backward_variant = "tensor"
 
     # ------------------------------------------------------------------------------------------------ native
     _NATIVE_DEFAULTS = dict(_handle=None, _handle_dev=None, _weights_sig=None, _staged=(), _workspace=None,
@@ -702,6 +705,8 @@ class HealNet(nn.Module):
             for layer, slot, ps in self._slot_params():
                 arr = (ctypes.c_void_p * len(ps))(*[grads[id(p)].data_ptr() for p in ps])
                 check(lib.hn_set_grads(self._handle, layer, slot, arr, len(ps)), "hn_set_grads")
+            check(lib.hn_set_backward_variant(self._handle, 1 if self.backward_variant == "fp32" else 0),
+                  "hn_set_backward_variant")
             need = lib.hn_backward_scratch_bytes(self._handle, batch, state["sizes"])
             if need == 0:
                 raise _lib.HealNetLibraryError(f"hn_backward_scratch_bytes failed: {_lib.last_error()}")

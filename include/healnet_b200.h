@@ -171,6 +171,10 @@ HN_API int hn_forward_train(hn_handle* h, int batch, const void* const* modality
                             float* latents_out, float* logits_out, void* workspace, size_t workspace_bytes, void* tape,
                             size_t tape_bytes, void* cuda_stream);
 HN_API int hn_set_grads(hn_handle* h, int layer, int slot, void* const* dev_ptrs, int n);
+/* 0 (default): the heavy contractions of hn_backward run on tensor cores (streaming small-context pass on tcgen05 with
+ * fp16 hi/lo operands, large regular GEMMs with bf16 hi/lo operands); 1: the exact fp32 SIMT kernels they are checked
+ * against (tests/test_gpu_backward.py compares both with the reference's gradients). */
+HN_API int hn_set_backward_variant(hn_handle* h, int variant);
 HN_API int hn_backward(hn_handle* h, const float* grad_latents, const float* grad_logits, void* workspace,
                        size_t workspace_bytes, const void* tape, size_t tape_bytes, void* scratch, size_t scratch_bytes,
                        void* cuda_stream);
