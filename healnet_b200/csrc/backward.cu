@@ -138,6 +138,8 @@ struct BwdScratch {
   float *dO, *dq, *ofull, *qf;
   float *S, *dP, *dKV, *dWp, *sv;
   float *u32, *cnu, *g, *du, *w, *rl, *dr, *dw, *delta, *dr_part;
+  void *pA, *pB;               // bf16 hi/lo operand rows of the tensor-core GEMMs
+  float* dh2;                  // [rows][8D] gate gradients (tensor-core feed-forward path)
   __half *rq, *duq;            // tensor-core streaming backward: split operand rows
   float *row_a, *row_d, *row_s;
   float* dpooled;
@@ -202,6 +204,17 @@ void plan_scratch(const hn_handle* h, int batch, const Workspace& ws, char* base
   s.dw = ar.take<float>(rc);
   s.delta = ar.take<float>(rows * d.x_heads);
   s.dr_part = ar.take<float>(sp_part);
+  {
+    const size_t sR = round_up_l(static_cast<long>(rows), 64), sDd = h->segD, s8 = round_up(8 * D, 64), F = 4 * static_cast<size_t>(D);
+    size_t a = 2 * F * 2 * sR;                       // (dh)^T
+    a = rows * 2 * s8 > a ? rows * 2 * s8 : a;       // dh
+    size_t bb = F * 2 * sR;                          // hid^T
+    bb = static_cast<size_t>(D) * 2 * s8 > bb ? static_cast<size_t>(D) * 2 * s8 : bb;   // W1^T
+    bb = F * 2 * sDd > bb ? F * 2 * sDd : bb;        // W2^T
+    s.pA = ar.take<__half>(a);
+    s.pB = ar.take<__half>(bb);
+    s.dh2 = ar.take<float>(rows * 8 * D);
+  }
   s.rq = ar.take<__half>(rows * 2 * d.x_heads * zw_max);
   s.duq = ar.take<__half>(rows * 2 * d.x_heads * zw_max);
   s.row_a = ar.take<float>(rows * d.x_heads);
@@ -224,6 +237,50 @@ int ln_backward(const float* x_in, const float* dxn, const float* gamma, float* 
   BW(launch_colsum(2, dxn, D, x_in, D, s.lnstats, rows, D, 1.f, g_gamma, 1, s.colpart, st));
   BW(launch_colsum(0, dxn, D, nullptr, 0, nullptr, rows, D, 1.f, g_beta, 1, s.colpart, st));
   return 0;
+}
+
+// C[M][N] (+)= A[M][K] B[N][K]^T on tcgen05 from bf16 hi/lo rows packed by launch_pack_bf16 (three-term product)
+int tc_gemm(cudaStream_t st, const void* A, int segA, const void* B, int segB, int M, int N, int K, float* out, int ldo,
+            bool accumulate) {
+  GemmArgs g{static_cast<const __half*>(A), static_cast<const __half*>(B), M, N, K, 2 * segA, 2 * segB,
+             accumulate ? EPI_RES : EPI_F32, 0, nullptr, out, ldo, 3, segA, segB, 0};
+  g.bf16 = 1;
+  return launch_gemm(g, st);
+}
+
+// Feed-forward backward with every contraction on tensor cores: gradient operands as bf16 hi/lo pairs (16 significant
+// bits, fp32 range; three-term products), the recomputed pre-activations through the forward's own fp16-split GEMM.
+int ff_backward_tc(hn_handle* h, const BlockRec& rec, const std::vector<const float*>& wf, const std::vector<float*>& gf,
+                   const FFPacked& fp, const char* tape, long rows, BwdScratch& s, cudaStream_t st) {
+  const hn_desc& d = h->d;
+  const int D = d.l_d, F = 4 * D, sD = h->segD, s4 = h->seg4D;
+  const int R = static_cast<int>(rows), sR = static_cast<int>(round_up_l(rows, 64)), s8 = round_up(2 * F, 64);
+  const float* x_in = reinterpret_cast<const float*>(tape + rec.x_in);
+  const __half* xn = reinterpret_cast<const __half*>(tape + rec.xn);
+  const __half* hid = reinterpret_cast<const __half*>(tape + rec.o);
+  BW(launch_colsum(0, s.dx, D, nullptr, 0, nullptr, rows, D, 1.f, gf[5], 1, s.colpart, st));
+  // dW2 += dx^T hid
+  BW(launch_pack_bf16(s.dx, 0, D, 0, rows, D, s.pA, sR, 1, st));
+  BW(launch_pack_bf16(hid, 1, 2 * s4, s4, rows, F, s.pB, sR, 1, st));
+  BW(tc_gemm(st, s.pA, sR, s.pB, sR, D, F, R, gf[4], F, true));
+  // dhid = dx W2
+  BW(launch_pack_bf16(s.dx, 0, D, 0, rows, D, s.pA, sD, 0, st));
+  BW(launch_pack_bf16(wf[4], 0, F, 0, D, F, s.pB, sD, 1, st));
+  BW(tc_gemm(st, s.pA, sD, s.pB, sD, R, F, D, s.dhid, F, false));
+  // [a | g] (interleaved, bias included) = LN(x) W1^T + b1 through the forward's GEMM
+  GemmArgs g1{xn, fp.W1, R, 2 * F, D, 2 * sD, 2 * sD, EPI_F32, 0, fp.b1, s.hbuf, 2 * F, 3, sD, sD, 0};
+  BW(launch_gemm(g1, st));
+  BW(launch_gate_bwd_il(s.hbuf, s.dhid, s.dh2, rows, F, d.snn, st));
+  BW(launch_colsum(0, s.dh2, 2 * F, nullptr, 0, nullptr, rows, 2 * F, 1.f, gf[3], 1, s.colpart, st));
+  // dW1 += dh^T xn
+  BW(launch_pack_bf16(s.dh2, 0, 2 * F, 0, rows, 2 * F, s.pA, sR, 1, st));
+  BW(launch_pack_bf16(xn, 1, 2 * sD, sD, rows, D, s.pB, sR, 1, st));
+  BW(tc_gemm(st, s.pA, sR, s.pB, sR, 2 * F, D, R, gf[2], D, true));
+  // dxn = dh W1
+  BW(launch_pack_bf16(s.dh2, 0, 2 * F, 0, rows, 2 * F, s.pA, s8, 0, st));
+  BW(launch_pack_bf16(wf[2], 0, D, 0, 2 * F, D, s.pB, s8, 1, st));
+  BW(tc_gemm(st, s.pA, s8, s.pB, s8, R, D, 2 * F, s.dxn, D, false));
+  return ln_backward(x_in, s.dxn, wf[0], gf[0], gf[1], rows, D, s, st);
 }
 
 // x_out = x_in + W2 (a * act(g)) + b2, [a | g] = W1 LN(x_in) + b1   (healnet.py:339-351, 237/245)
@@ -415,7 +472,11 @@ int hn_backward(hn_handle* h, const float* grad_latents, const float* grad_logit
                              ? reinterpret_cast<const float*>(tape + t.blocks[bi + 1].x_in)
                              : x_final;
     if (rec.kind == 3) {
-      BW(ff_backward(h, rec, weights(rec.layer, 2 * rec.m + 1), grads(rec.layer, 2 * rec.m + 1), tape, rows, s, st));
+      if (h->bwd_variant == 0)
+        BW(ff_backward_tc(h, rec, weights(rec.layer, 2 * rec.m + 1), grads(rec.layer, 2 * rec.m + 1),
+                          h->ff[rec.layer * (M + 1) + rec.m], tape, rows, s, st));
+      else
+        BW(ff_backward(h, rec, weights(rec.layer, 2 * rec.m + 1), grads(rec.layer, 2 * rec.m + 1), tape, rows, s, st));
       continue;
     }
     const std::vector<const float*>& wa = weights(rec.layer, 2 * rec.m);

@@ -34,6 +34,13 @@ int launch_scale_cols(const float* in, const float* gamma, float scale, int C, l
 int launch_kv_fold_bwd(const float* dWp, const float* W, const float* gamma, const float* beta, const float* sv,
                        int rows2I, int I, int C, float* gW, float* ggamma, float* gbeta, cudaStream_t st);
 
+// bf16 hi/lo operand rows for the tensor-core GEMMs of the backward: dst [rows][2 seg] (transpose: [C][2 seg], seg >= R),
+// src fp32 (src_half = 0) or split fp16 (src_half = 1, lo at + lo_off)
+int launch_pack_bf16(const void* src, int src_half, long ld_src, int lo_off, long R, int C, void* dst, int seg,
+                     int transpose, cudaStream_t st);
+// gate backward on interleaved (a_j, g_j) pre-activations (bias included) -> dh = [d a | d g]
+int launch_gate_bwd_il(const float* h_il, const float* dhid, float* dh, long rows, int F, int snn, cudaStream_t st);
+
 // streaming backward of the small-context cross-attention
 struct SmallBwdArgs {
   const float* r;       // [R][C]  log2-unit score vectors: s_lt = r_l . z_t

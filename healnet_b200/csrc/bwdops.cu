@@ -5,6 +5,8 @@
 //
 // Conventions: "rows" = batch * l_c latent rows; R = rows * heads for per-head arrays [R][C]; gradients of parameters
 // are ACCUMULATED (+=) into caller-zeroed buffers so that tied layers and repeated modules sum up naturally.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "bwd.cuh"
 
@@ -511,6 +513,81 @@ __global__ void sum_splits_kernel(const float* __restrict__ part, int nsplit, lo
   }
 }
 
+// ------------------------------------------------------------------ bf16 hi/lo operand packing for the backward GEMMs
+// dst rows = [hi (seg cols) | lo (seg cols)], hi = bf16(v), lo = bf16(v - hi) (16 significant bits, fp32 range), pad
+// columns zero. src: fp32 (lo_off == 0) or the forward's split fp16 rows (value = hi + lo at + lo_off).
+// TRANSPOSE: dst[c][r] = src[r][c] (the weight-gradient products contract over the row axis).
+__device__ __forceinline__ float ld_src(const void* src, int src_half, long idx, int lo_off) {
+  if (!src_half) return static_cast<const float*>(src)[idx];
+  const __half* hp = static_cast<const __half*>(src);
+  return __half2float(hp[idx]) + __half2float(hp[idx + lo_off]);
+}
+__device__ __forceinline__ void st_bf16_split(__nv_bfloat16* dst, long idx, int seg, float v) {
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  dst[idx] = hi;
+  dst[idx + seg] = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+__global__ void pack_bf16_kernel(const void* __restrict__ src, int src_half, long ld_src_, int lo_off, long R, int C,
+                                 __nv_bfloat16* __restrict__ dst, int seg) {
+  HN_PDL_LAUNCH();
+  HN_PDL_WAIT();
+  const long n = R * seg;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long r = i / seg;
+    const int c = static_cast<int>(i - r * seg);
+    st_bf16_split(dst, r * 2 * seg + c, seg, c < C ? ld_src(src, src_half, r * ld_src_ + c, lo_off) : 0.f);
+  }
+}
+// 32 x 32 tiles through shared memory: coalesced reads along c, coalesced writes along r
+__global__ void __launch_bounds__(256) pack_bf16_t_kernel(const void* __restrict__ src, int src_half, long ld_src_,
+                                                          int lo_off, long R, int C, __nv_bfloat16* __restrict__ dst,
+                                                          int seg /* >= R */) {
+  HN_PDL_LAUNCH();
+  HN_PDL_WAIT();
+  __shared__ float tile[32][33];
+  const long r0 = static_cast<long>(blockIdx.x) * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 32; j += 8) {
+    const long r = r0 + j;
+    const int c = c0 + tx;
+    tile[j][tx] = (r < R && c < C) ? ld_src(src, src_half, r * ld_src_ + c, lo_off) : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j;
+    const long r = r0 + tx;
+    if (c < C && r < seg) st_bf16_split(dst, static_cast<long>(c) * 2 * seg + r, seg, tile[tx][j]);
+  }
+}
+// FeedForward gate backward on the recomputed pre-activations in the forward GEMM's interleaved layout:
+// h_il[r][2j] = a_j, h_il[r][2j + 1] = g_j (bias included) -> dh[r][j] = d a_j, dh[r][F + j] = d g_j
+__global__ void gate_bwd_il_kernel(const float* __restrict__ h_il, const float* __restrict__ dhid,
+                                   float* __restrict__ dh, long rows, int F, int snn) {
+  HN_PDL_LAUNCH();
+  HN_PDL_WAIT();
+  const long n = rows * F;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long r = i / F;
+    const int j = static_cast<int>(i - r * F);
+    const float2 ag = *reinterpret_cast<const float2*>(h_il + r * 2 * F + 2 * j);
+    const float a = ag.x, g = ag.y, d = dhid[i];
+    float act, dact;
+    if (snn) {
+      const float alpha = 1.6732632423543772848170429916717f, scale = 1.0507009873554804934193349852946f;
+      const float e = expf(g);
+      act = scale * (g > 0.f ? g : alpha * (e - 1.f));
+      dact = scale * (g > 0.f ? 1.f : alpha * e);
+    } else {
+      const float cdf = 0.5f * (1.f + erff(g * 0.70710678118654752440f));
+      act = g * cdf;
+      dact = cdf + g * 0.3989422804014327f * expf(-0.5f * g * g);
+    }
+    dh[r * 2 * F + j] = d * act;
+    dh[r * 2 * F + F + j] = d * a * dact;
+  }
+}
+
 // operands of the tensor-core streaming backward (xattn_small.cu): one warp per (row, head)
 __global__ void __launch_bounds__(256) small_bwd_prep_kernel(const float* __restrict__ r, const float* __restrict__ du,
                                                              const float* __restrict__ delta,
@@ -677,6 +754,26 @@ int launch_kv_fold_bwd(const float* dWp, const float* W, const float* gamma, con
                        int rows2I, int I, int C, float* gW, float* ggamma, float* gbeta, cudaStream_t st) {
   HN_CHECK_CUDA(launch_k(kv_fold_bwd_kernel, dim3((C + 31) / 32), dim3(256), 0, st, dWp, W, gamma, beta, sv, rows2I, I, C, gW,
                          ggamma, gbeta));
+  HN_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_pack_bf16(const void* src, int src_half, long ld_src, int lo_off, long R, int C, void* dst, int seg,
+                     int transpose, cudaStream_t st) {
+  __nv_bfloat16* d = static_cast<__nv_bfloat16*>(dst);
+  if (!transpose) {
+    HN_REQUIRE(seg >= C, "pack_bf16: segment narrower than the row");
+    HN_CHECK_CUDA(launch_k(pack_bf16_kernel, dim3(ew_grid(R * seg)), dim3(256), 0, st, src, src_half, ld_src, lo_off, R, C, d, seg));
+  } else {
+    HN_REQUIRE(seg >= R, "pack_bf16: segment shorter than the column");
+    // the pad columns [R, seg) of every output row must be zero: the tile loop writes them (r < seg) from zeros
+    const dim3 grid(static_cast<unsigned>((seg + 31) / 32), static_cast<unsigned>((C + 31) / 32));
+    HN_CHECK_CUDA(launch_k(pack_bf16_t_kernel, grid, dim3(256), 0, st, src, src_half, ld_src, lo_off, R, C, d, seg));
+  }
+  HN_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_gate_bwd_il(const float* h_il, const float* dhid, float* dh, long rows, int F, int snn, cudaStream_t st) {
+  HN_CHECK_CUDA(launch_k(gate_bwd_il_kernel, dim3(ew_grid(rows * F)), dim3(256), 0, st, h_il, dhid, dh, rows, F, snn));
   HN_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -116,6 +116,9 @@ struct GemmArgs {
   int ln_ld = 0, ln_seg = 0;
   unsigned* ln_counters = nullptr;  // ceil(M / 128) words, zero at the start of the forward
   int ln_epoch = 0;                 // 1-based index of this launch among the forward's fused launches
+  // operands are bf16 instead of fp16 (same split layout): the backward pass, whose gradient operands need fp32's
+  // exponent range; fp32-output epilogues only
+  int bf16 = 0;
 };
 int launch_gemm(const GemmArgs& a, cudaStream_t stream);
 // can this residual GEMM also emit the next LayerNorm (GemmArgs::ln_*)? (shape / alignment rules, HN_GEMM_LN switch)

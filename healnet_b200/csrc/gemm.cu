@@ -61,6 +61,7 @@ struct GemmDev {
   unsigned* ln_counters;
   int ln_epoch;  // fused launches so far in this forward, this one included
   int tiles_m, tiles_n;  // output tiles; with clusters: super-tiles of CN tiles along N (SHARE_A) or M (!SHARE_A)
+  int bf16;              // operands are bf16 (kind::f16 with a_format = b_format = bf16)
 };
 
 __device__ __forceinline__ void split_half(float v, __half& hi, __half& lo) {
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__((2 + EPI_WARPS) * 32, 1) gemm_kernel(const __g
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      constexpr uint32_t idesc = idesc_f16(BM, BN, false, false);
+      const uint32_t idesc = idesc_f16(BM, BN, false, false) | (p.bf16 ? ((1u << 7) | (1u << 10)) : 0u);
       int it = 0, j = 0;
       for (int tile = first; tile < n_tiles; tile += stride, ++j) {
         const int acc = j & 1;
@@ -417,7 +418,7 @@ int launch_t(const GemmArgs& a, cudaStream_t stream) {
   GemmDev p{a.M, a.N, a.K, a.epi, a.act, a.bias, a.out, a.ldo, vec_ok, a.terms, a.a_seg, a.b_seg,
             half_out ? a.out_seg : 0, stages,
             (a.bias != nullptr && (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0) ? 1 : 0,
-            a.ln_gamma, a.ln_beta, a.ln_out, a.ln_ld, a.ln_seg, a.ln_counters, a.ln_epoch, tiles_m, tiles_n};
+            a.ln_gamma, a.ln_beta, a.ln_out, a.ln_ld, a.ln_seg, a.ln_counters, a.ln_epoch, tiles_m, tiles_n, a.bf16};
   const int smem = stages * stage_bytes + 1024;
   int dev = 0, sms = 0;
   HN_CHECK_CUDA(cudaGetDevice(&dev));
@@ -460,6 +461,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
              "gemm: operands must be 16-byte aligned");
   if (a.epi == EPI_GATE_F16) HN_REQUIRE(a.N % 2 == 0, "gemm: gated epilogue needs even N");
   HN_REQUIRE(a.terms >= 1 && a.terms <= 3, "gemm: terms must be 1, 2 or 3");
+  HN_REQUIRE(!a.bf16 || a.epi == EPI_RES || a.epi == EPI_F32, "gemm: bf16 operands go with fp32 epilogues");
   if (a.ln_out != nullptr) {
     const bool resid = a.epi == EPI_RES || a.epi == EPI_RES_LEAKY;
     const bool aligned = (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.ln_out) & 7) == 0 &&

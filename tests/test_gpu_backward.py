@@ -81,8 +81,9 @@ def _check_grads(model, want_grads, rtol=2e-3, sens=None):
     return checked
 
 
+@pytest.mark.parametrize("variant", ["tensor", "fp32"])
 @pytest.mark.parametrize("name", ["tri_small", "omic_wsi_tied", "wide_heads"])
-def test_gradients_match_reference_autograd(golden, name):
+def test_gradients_match_reference_autograd(golden, name, variant):
     """Generic / precise attention paths, odd head sizes, GELU gate, tied layers (gradients of shared parameters are
     the sum over their uses)."""
     meta, sd, ins, outs, _ = golden(name)
@@ -90,6 +91,7 @@ def test_gradients_match_reference_autograd(golden, name):
     model = HealNet(**meta["kwargs"])
     model.load_state_dict(sd)
     model = model.cuda().train()
+    model.backward_variant = variant   # tensor-core contractions / their exact fp32 checkers
     xs = [ins[str(i)].cuda() for i in range(meta["kwargs"]["n_modalities"])]
     logits = model(xs)
     assert logits.requires_grad
