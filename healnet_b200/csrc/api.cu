@@ -816,6 +816,12 @@ int hn::forward_impl(hn_handle* h, int batch, const void* const* modality_ptrs, 
           aa.kd = mp.zw;
           aa.c_ones = mp.C;
           aa.precise = 1;
+#ifdef HN_DEBUG
+          {  // timing experiment only: single-term scores (shows what the two extra score products cost)
+            static const bool nosplit = getenv("HN_SMALL_NOSPLIT") != nullptr;
+            if (nosplit) aa.precise = 0;
+          }
+#endif
           aa.q_lo_off = qw;
           rc = profile_begin(h, m, aa, mp.C, st);
           if (rc != 0) return rc;

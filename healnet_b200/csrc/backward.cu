@@ -139,6 +139,7 @@ struct BwdScratch {
   float *S, *dP, *dKV, *dWp, *sv;
   float *u32, *cnu, *g, *du, *w, *rl, *dr, *dw, *delta, *dr_part;
   void *pA, *pB;               // bf16 hi/lo operand rows of the tensor-core GEMMs
+  size_t capA, capB;           // their capacities in elements
   float* dh2;                  // [rows][8D] gate gradients (tensor-core feed-forward path)
   __half *rq, *duq;            // tensor-core streaming backward: split operand rows
   float *row_a, *row_d, *row_s;
@@ -211,6 +212,25 @@ void plan_scratch(const hn_handle* h, int batch, const Workspace& ws, char* base
     size_t bb = F * 2 * sR;                          // hid^T
     bb = static_cast<size_t>(D) * 2 * s8 > bb ? static_cast<size_t>(D) * 2 * s8 : bb;   // W1^T
     bb = F * 2 * sDd > bb ? F * 2 * sDd : bb;        // W2^T
+    // attention blocks (mm() below): the latent-side products and the per-head products of the materialised core.
+    // Operand rows are [hi | lo] of round_up(K, 64) columns each.
+    auto seg2 = [](size_t k) { return 2 * static_cast<size_t>(round_up_l(static_cast<long>(k), 64)); };
+    auto up = [](size_t& x, size_t v) { if (v > x) x = v; };
+    const size_t I2 = 2 * Imax;
+    up(a, rows * seg2(D));  up(bb, Imax * seg2(D));            // dO = dy Wo, q = xn Wq^T
+    up(a, D * seg2(rows));  up(bb, Imax * seg2(rows));         // dWo += dy^T o
+    up(a, I2 * seg2(rows)); up(bb, D * seg2(rows));            // dWq / dWkv
+    up(a, rows * seg2(I2)); up(bb, D * seg2(I2));              // dxn = dq Wq, dKV Wkv
+    if (n_gen > 0) {
+      // core of the generic / latent attention with n_gen tokens per sample, capped: larger token axes keep the fp32 path
+      const size_t nz = static_cast<size_t>(batch) * Hmax, cap = static_cast<size_t>(96) << 20;
+      size_t ca = nz * (n_gen > static_cast<size_t>(L) ? n_gen : L) * seg2(n_gen > static_cast<size_t>(L) ? n_gen : L);
+      size_t cb = nz * n_gen * seg2(L > 128 ? L : 128);
+      up(a, ca < cap ? ca : cap);
+      up(bb, cb < cap ? cb : cap);
+    }
+    s.capA = a;
+    s.capB = bb;
     s.pA = ar.take<__half>(a);
     s.pB = ar.take<__half>(bb);
     s.dh2 = ar.take<float>(rows * 8 * D);
@@ -245,6 +265,36 @@ int tc_gemm(cudaStream_t st, const void* A, int segA, const void* B, int segB, i
   GemmArgs g{static_cast<const __half*>(A), static_cast<const __half*>(B), M, N, K, 2 * segA, 2 * segB,
              accumulate ? EPI_RES : EPI_F32, 0, nullptr, out, ldo, 3, segA, segB, 0};
   g.bf16 = 1;
+  return launch_gemm(g, st);
+}
+
+// C[b1][b2][m][n] (+)= alpha * sum_k A(m, k) B(k, n) — the contraction of sg() above — on tcgen05: both operands are
+// packed to bf16 hi/lo rows with the contraction index contiguous (three-term products: 16 significant bits, fp32
+// range), batches stacked along the rows, one batched GEMM launch. Small products, operands that do not fit the
+// packing buffers, and the fp32 checker variant (hn_set_backward_variant(1)) keep the exact fp32 SIMT kernel.
+int mm(const hn_handle* h, BwdScratch& s, cudaStream_t st, int M, int N, int K, const SgOperand& A, const SgOperand& B,
+       float* C, long c_row, float alpha = 1.f, int accumulate = 0, int nb1 = 1, long c_b1 = 0, int nb2 = 1,
+       long c_b2 = 0) {
+  const long nz = static_cast<long>(nb1) * nb2;
+  const size_t segK = static_cast<size_t>(round_up_l(K, 64));
+  const size_t needA = static_cast<size_t>(nz) * M * 2 * segK, needB = static_cast<size_t>(nz) * N * 2 * segK;
+  const bool small = static_cast<double>(M) * N * K * nz < 4.0e6 || K < 16 || M < 16 || N < 8;
+  if (h->bwd_variant != 0 || small || needA > s.capA || needB > s.capB || c_row >= 2147483647L || nz > 65535 ||
+      static_cast<long>(M) * nz >= 2147483647L || static_cast<long>(N) * nz >= 2147483647L)
+    return sg(st, M, N, K, A, B, C, c_row, alpha, accumulate, nb1, c_b1, nb2, c_b2);
+  const int seg = static_cast<int>(segK);
+  BW(launch_pack_bf16_strided(A.p, A.type, A.lo_off, A.s_row, A.s_col, A.s_b1, A.s_b2, nb1, nb2, M, K, s.pA, seg, st));
+  BW(launch_pack_bf16_strided(B.p, B.type, B.lo_off, B.s_col, B.s_row, B.s_b1, B.s_b2, nb1, nb2, N, K, s.pB, seg, st));
+  GemmArgs g{static_cast<const __half*>(s.pA), static_cast<const __half*>(s.pB), M, N, K, 2 * seg, 2 * seg,
+             accumulate ? EPI_RES : EPI_F32, 0, nullptr, C, static_cast<int>(c_row), 3, seg, seg, 0};
+  g.bf16 = 1;
+  g.nbatch = static_cast<int>(nz);
+  g.nb2 = nb2;
+  g.a_brows = M;
+  g.b_brows = N;
+  g.out_b1 = c_b1;
+  g.out_b2 = c_b2;
+  g.alpha = alpha;
   return launch_gemm(g, st);
 }
 
@@ -306,27 +356,27 @@ int ff_backward(hn_handle* h, const BlockRec& rec, const std::vector<const float
 // The materialised attention core shared by the generic cross-attention and the latent self-attention:
 // in: dO [rows][I], Q (split, log2-scaled, head pitch hp) and K / V (split, head pitch hp) of b samples of N
 // tokens; out: dq [rows][I] (w.r.t. the unscaled q), dKV [b*N][2I] (K gradient in columns [0, I), V in [I, 2I)).
-int attention_core_backward(int batch, int H, int L, long N, int dh, int hp, float c_nat, const __half* Q, int q_ld,
+int attention_core_backward(const hn_handle* h, int batch, int H, int L, long N, int dh, int hp, float c_nat, const __half* Q, int q_ld,
                             int q_lo, const __half* KV, long kv_ld, int kv_lo, int k_col0, int v_col0,
                             const float* stats, const uint64_t* mask_bits, BwdScratch& s, cudaStream_t st) {
   const int I = H * dh;
   const long LN_ = static_cast<long>(L) * N, HLN = static_cast<long>(H) * LN_;
   const int n = static_cast<int>(N);
   // S = Q K^T (log2 units)
-  BW(sg(st, L, n, hp, H16(Q, q_lo, q_ld, 1, static_cast<long>(L) * q_ld, hp),
+  BW(mm(h, s, st, L, n, hp, H16(Q, q_lo, q_ld, 1, static_cast<long>(L) * q_ld, hp),
         H16(KV + k_col0, kv_lo, 1, kv_ld, N * kv_ld, hp), s.S, N, 1.f, 0, batch, HLN, H, LN_));
   BW(launch_softmax_recompute(s.S, stats, H, L, N, mask_bits, static_cast<long>(batch) * H * L, st));
   // dV[n][h, d] = sum_l P[l][n] dO[l][h, d]
-  BW(sg(st, n, dh, L, F32(s.S, 1, N, HLN, LN_), F32(s.dO, I, 1, static_cast<long>(L) * I, dh), s.dKV + I, 2 * I, 1.f, 0,
+  BW(mm(h, s, st, n, dh, L, F32(s.S, 1, N, HLN, LN_), F32(s.dO, I, 1, static_cast<long>(L) * I, dh), s.dKV + I, 2 * I, 1.f, 0,
         batch, N * 2 * I, H, dh));
   // dP[l][n] = dO[l] . V[n]
-  BW(sg(st, L, n, dh, F32(s.dO, I, 1, static_cast<long>(L) * I, dh), H16(KV + v_col0, kv_lo, 1, kv_ld, N * kv_ld, hp), s.dP,
+  BW(mm(h, s, st, L, n, dh, F32(s.dO, I, 1, static_cast<long>(L) * I, dh), H16(KV + v_col0, kv_lo, 1, kv_ld, N * kv_ld, hp), s.dP,
         N, 1.f, 0, batch, HLN, H, LN_));
   BW(launch_softmax_bwd(s.dP, s.S, N, static_cast<long>(batch) * H * L, st));  // dt = P (dP - sum P dP), natural-log units
   // dq = c dt K ;  dK = c dt^T q = ln2 dt^T Q  (Q carries c log2(e))
-  BW(sg(st, L, dh, n, F32(s.dP, N, 1, HLN, LN_), H16(KV + k_col0, kv_lo, kv_ld, 1, N * kv_ld, hp), s.dq, I, c_nat, 0, batch,
+  BW(mm(h, s, st, L, dh, n, F32(s.dP, N, 1, HLN, LN_), H16(KV + k_col0, kv_lo, kv_ld, 1, N * kv_ld, hp), s.dq, I, c_nat, 0, batch,
         static_cast<long>(L) * I, H, dh));
-  BW(sg(st, n, dh, L, F32(s.dP, 1, N, HLN, LN_), H16(Q, q_lo, q_ld, 1, static_cast<long>(L) * q_ld, hp), s.dKV, 2 * I,
+  BW(mm(h, s, st, n, dh, L, F32(s.dP, 1, N, HLN, LN_), H16(Q, q_lo, q_ld, 1, static_cast<long>(L) * q_ld, hp), s.dKV, 2 * I,
         0.69314718055994530942f, 0, batch, N * 2 * I, H, dh));
   return 0;
 }
@@ -492,7 +542,7 @@ int hn_backward(hn_handle* h, const float* grad_latents, const float* grad_logit
     const int H = self ? d.l_heads : d.x_heads, dh = self ? d.latent_dim_head : d.cross_dim_head;
     const int hp = self ? h->hpl : h->hpx, I = H * dh;
     const float c_nat = 2.f / std::sqrt(static_cast<float>(dh));
-    BW(sg(st, R, I, D, F32(s.dy, D, 1), F32(wa[iWo], I, 1), s.dO, I));  // dO = dy Wo  (unpadded head layout)
+    BW(mm(h, s, st, R, I, D, F32(s.dy, D, 1), F32(wa[iWo], I, 1), s.dO, I));  // dO = dy Wo  (unpadded head layout)
 
     if (rec.kind == 0) {
       // ---------------------------------------------------------------- small-context cross-attention
@@ -504,20 +554,20 @@ int hn_backward(hn_handle* h, const float* grad_latents, const float* grad_logit
       const float* Wkv = wa[5];
       BW(launch_small_pre(o, 2 * sHZ, sHZ, zw, H, C, rows, gamma, beta, s.u32, s.cnu, st));
       // o_h = Wv_h (gamma * u + beta): rebuilt for the out-projection weight gradient
-      BW(sg(st, R, dh, C, F32(s.cnu, static_cast<long>(H) * C, 1, C), F32(Wkv + static_cast<long>(I) * C, 1, C, static_cast<long>(dh) * C),
+      BW(mm(h, s, st, R, dh, C, F32(s.cnu, static_cast<long>(H) * C, 1, C), F32(Wkv + static_cast<long>(I) * C, 1, C, static_cast<long>(dh) * C),
             s.ofull, I, 1.f, 0, H, dh));
-      BW(sg(st, D, I, R, F32(s.dy, 1, D), F32(s.ofull, I, 1), ga[iWo], I, 1.f, 1));              // dWo += dy^T o
+      BW(mm(h, s, st, D, I, R, F32(s.dy, 1, D), F32(s.ofull, I, 1), ga[iWo], I, 1.f, 1));              // dWo += dy^T o
       // g = Wv_h^T dO_h ; dWv_h += dO_h^T (gamma * u + beta)
-      BW(sg(st, R, C, dh, F32(s.dO, I, 1, dh), F32(Wkv + static_cast<long>(I) * C, C, 1, static_cast<long>(dh) * C), s.g,
+      BW(mm(h, s, st, R, C, dh, F32(s.dO, I, 1, dh), F32(Wkv + static_cast<long>(I) * C, C, 1, static_cast<long>(dh) * C), s.g,
             static_cast<long>(H) * C, 1.f, 0, H, C));
-      BW(sg(st, dh, C, R, F32(s.dO, 1, I, dh), F32(s.cnu, static_cast<long>(H) * C, 1, C), ga[5] + static_cast<long>(I) * C, C,
+      BW(mm(h, s, st, dh, C, R, F32(s.dO, 1, I, dh), F32(s.cnu, static_cast<long>(H) * C, 1, C), ga[5] + static_cast<long>(I) * C, C,
             1.f, 1, H, static_cast<long>(dh) * C));
       BW(launch_colsum(1, s.g, C, s.u32, C, nullptr, RH, C, 1.f, ga[2], 1, s.colpart, st));     // dgamma += sum g * u
       BW(launch_colsum(0, s.g, C, nullptr, 0, nullptr, RH, C, 1.f, ga[3], 1, s.colpart, st));   // dbeta  += sum g
       BW(launch_small_du(s.g, s.u32, gamma, C, RH, s.du, s.delta, st));
       // scores: s_lt = r_l . z_t with r = c gamma * (Wk_h^T q_l)
-      BW(sg(st, R, I, D, H16(xn, sD, 2 * sD, 1), F32(wa[iWq], 1, D), s.qf, I));                  // q = xn Wq^T
-      BW(sg(st, R, C, dh, F32(s.qf, I, 1, dh), F32(Wkv, C, 1, static_cast<long>(dh) * C), s.w, static_cast<long>(H) * C, 1.f,
+      BW(mm(h, s, st, R, I, D, H16(xn, sD, 2 * sD, 1), F32(wa[iWq], 1, D), s.qf, I));                  // q = xn Wq^T
+      BW(mm(h, s, st, R, C, dh, F32(s.qf, I, 1, dh), F32(Wkv, C, 1, static_cast<long>(dh) * C), s.w, static_cast<long>(H) * C, 1.f,
             0, H, C));
       BW(launch_scale_cols(s.w, gamma, c_nat * LOG2E, C, RH * C, s.rl, st));
       if (h->bwd_variant == 0) {
@@ -566,23 +616,23 @@ int hn_backward(hn_handle* h, const float* grad_latents, const float* grad_logit
       }
       BW(launch_colsum(1, s.w, C, s.dr, C, nullptr, RH, C, c_nat, ga[2], 1, s.colpart, st));    // dgamma += c sum w * dr
       BW(launch_scale_cols(s.dr, gamma, c_nat, C, RH * C, s.dw, st));                            // dw = c gamma * dr
-      BW(sg(st, R, dh, C, F32(s.dw, static_cast<long>(H) * C, 1, C), F32(Wkv, 1, C, static_cast<long>(dh) * C), s.dq, I, 1.f, 0,
+      BW(mm(h, s, st, R, dh, C, F32(s.dw, static_cast<long>(H) * C, 1, C), F32(Wkv, 1, C, static_cast<long>(dh) * C), s.dq, I, 1.f, 0,
             H, dh));                                                                              // dq_h = Wk_h dw
-      BW(sg(st, dh, C, R, F32(s.qf, 1, I, dh), F32(s.dw, static_cast<long>(H) * C, 1, C), ga[5], C, 1.f, 1, H,
+      BW(mm(h, s, st, dh, C, R, F32(s.qf, 1, I, dh), F32(s.dw, static_cast<long>(H) * C, 1, C), ga[5], C, 1.f, 1, H,
             static_cast<long>(dh) * C));                                                          // dWk_h += q_h^T dw
     } else {
       // ---------------------------------------------------------------- generic cross-attention / latent self-attention
       const int ow = H * hp;
-      BW(sg(st, D, dh, R, F32(s.dy, 1, D), H16(o, ow, 2 * ow, 1, hp), ga[iWo], I, 1.f, 1, H, dh));  // dWo += dy^T o
+      BW(mm(h, s, st, D, dh, R, F32(s.dy, 1, D), H16(o, ow, 2 * ow, 1, hp), ga[iWo], I, 1.f, 1, H, dh));  // dWo += dy^T o
       const AttnPacked& ap = h->attn[rec.layer * (M + 1) + rec.m];
       if (self) {
         const int qw = 3 * ow;
         GemmArgs gq{xn, ap.Wq, R, qw, D, 2 * sD, 2 * sD, EPI_F16, 0, nullptr, ws.q, 2 * qw, 3, sD, sD, qw};
         BW(launch_gemm(gq, st));                                                                  // [Q | K | V] as in the forward
-        BW(attention_core_backward(batch, H, L, L, dh, hp, c_nat, ws.q, 2 * qw, qw, ws.q, 2 * qw, qw, ow, 2 * ow, stats,
+        BW(attention_core_backward(h, batch, H, L, L, dh, hp, c_nat, ws.q, 2 * qw, qw, ws.q, 2 * qw, qw, ow, 2 * ow, stats,
                                    nullptr, s, st));
-        BW(sg(st, 2 * I, D, R, F32(s.dKV, 1, 2 * I), H16(xn, sD, 2 * sD, 1), ga[iWkv], D, 1.f, 1));  // dWkv += dKV^T xn
-        BW(sg(st, R, D, 2 * I, F32(s.dKV, 2 * I, 1), F32(wa[iWkv], D, 1), s.dxn, D));               // dxn  = dKV Wkv
+        BW(mm(h, s, st, 2 * I, D, R, F32(s.dKV, 1, 2 * I), H16(xn, sD, 2 * sD, 1), ga[iWkv], D, 1.f, 1));  // dWkv += dKV^T xn
+        BW(mm(h, s, st, R, D, 2 * I, F32(s.dKV, 2 * I, 1), F32(wa[iWkv], D, 1), s.dxn, D));               // dxn  = dKV Wkv
       } else {
         const ModPlan& mp = ws.mod[rec.m];
         const int C = mp.C, qw = ow, kvw = 2 * ow;
@@ -592,17 +642,17 @@ int hn_backward(hn_handle* h, const float* grad_latents, const float* grad_logit
         GemmArgs gkv{mp.z, ap.Wkv, static_cast<int>(tok), kvw, C, mp.ldz, 2 * mp.segC, EPI_F16, 0, ap.bkv, ws.kv, 2 * kvw, 3,
                      mp.segC, mp.segC, kvw};
         BW(launch_gemm(gkv, st));
-        BW(attention_core_backward(batch, H, L, mp.Nl, dh, hp, c_nat, ws.q, 2 * qw, qw, ws.kv, 2 * kvw, kvw, 0, ow, stats,
+        BW(attention_core_backward(h, batch, H, L, mp.Nl, dh, hp, c_nat, ws.q, 2 * qw, qw, ws.kv, 2 * kvw, kvw, 0, ow, stats,
                                    mp.masked ? ws.mask_bits : nullptr, s, st));
         // K = Wk (gamma * z) (+ const), V = Wv (gamma * z + beta): weight gradients through the folded context LayerNorm
-        BW(sg(st, 2 * I, C, static_cast<int>(tok), F32(s.dKV, 1, 2 * I), H16(mp.z, mp.segC, mp.ldz, 1), s.dWp, C));
+        BW(mm(h, s, st, 2 * I, C, static_cast<int>(tok), F32(s.dKV, 1, 2 * I), H16(mp.z, mp.segC, mp.ldz, 1), s.dWp, C));
         BW(launch_colsum(0, s.dKV, 2 * I, nullptr, 0, nullptr, tok, 2 * I, 1.f, s.sv, 0, s.colpart, st));
         BW(launch_kv_fold_bwd(s.dWp, wa[5], wa[2], wa[3], s.sv, 2 * I, I, C, ga[5], ga[2], ga[3], st));
       }
     }
     // q = Wq LN(x): dWq += dq^T xn ; dxn (+)= dq Wq
-    BW(sg(st, I, D, R, F32(s.dq, 1, I), H16(xn, sD, 2 * sD, 1), ga[iWq], D, 1.f, 1));
-    BW(sg(st, R, D, I, F32(s.dq, I, 1), F32(wa[iWq], D, 1), s.dxn, D, 1.f, self ? 1 : 0));
+    BW(mm(h, s, st, I, D, R, F32(s.dq, 1, I), H16(xn, sD, 2 * sD, 1), ga[iWq], D, 1.f, 1));
+    BW(mm(h, s, st, R, D, I, F32(s.dq, I, 1), F32(wa[iWq], D, 1), s.dxn, D, 1.f, self ? 1 : 0));
     BW(ln_backward(x_in, s.dxn, wa[0], ga[0], ga[1], rows, D, s, st));
   }
   // x0 = repeat(latents, 'n d -> b n d')   (healnet.py:225)

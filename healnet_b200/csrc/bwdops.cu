@@ -560,6 +560,40 @@ __global__ void __launch_bounds__(256) pack_bf16_t_kernel(const void* __restrict
     if (c < C && r < seg) st_bf16_split(dst, static_cast<long>(c) * 2 * seg + r, seg, tile[tx][j]);
   }
 }
+// General form for the strided, batched products of the attention blocks: dst[(z R + r) 2 seg + c] = hi, [+ seg] = lo
+// of src(z, r, c) = p[b1 s_b1 + b2 s_b2 + r s_r + c s_c], z = b1 nb2 + b2; columns [C, seg) zero. 32 x 32 tiles:
+// read along whichever of (r, c) is contiguous in the source, always write along c.
+struct PackSrc {
+  const void* p;
+  int type, lo_off;
+  long s_r, s_c, s_b1, s_b2;
+};
+__global__ void __launch_bounds__(256) pack_bf16_strided_kernel(PackSrc s, int nb2, long R, int C,
+                                                                __nv_bfloat16* __restrict__ dst, int seg) {
+  HN_PDL_LAUNCH();
+  HN_PDL_WAIT();
+  __shared__ float tile[32][33];
+  const int z = blockIdx.z;
+  const long base = static_cast<long>(z / nb2) * s.s_b1 + static_cast<long>(z % nb2) * s.s_b2;
+  const long r0 = static_cast<long>(blockIdx.y) * 32;
+  const int c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const bool r_fast = s.s_r == 1 && s.s_c != 1;
+  for (int j = ty; j < 32; j += 8) {
+    const long r = r_fast ? r0 + tx : r0 + j;
+    const int c = r_fast ? c0 + j : c0 + tx;
+    float v = 0.f;
+    if (r < R && c < C) v = ld_src(s.p, s.type, base + r * s.s_r + c * s.s_c, s.lo_off);
+    if (r_fast) tile[tx][j] = v; else tile[j][tx] = v;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const long r = r0 + j;
+    const int c = c0 + tx;
+    if (r < R && c < seg) st_bf16_split(dst, (static_cast<long>(z) * R + r) * 2 * seg + c, seg, tile[j][tx]);
+  }
+}
+
 // FeedForward gate backward on the recomputed pre-activations in the forward GEMM's interleaved layout:
 // h_il[r][2j] = a_j, h_il[r][2j + 1] = g_j (bias included) -> dh[r][j] = d a_j, dh[r][F + j] = d g_j
 __global__ void gate_bwd_il_kernel(const float* __restrict__ h_il, const float* __restrict__ dhid,
@@ -769,6 +803,16 @@ int launch_pack_bf16(const void* src, int src_half, long ld_src, int lo_off, lon
     const dim3 grid(static_cast<unsigned>((seg + 31) / 32), static_cast<unsigned>((C + 31) / 32));
     HN_CHECK_CUDA(launch_k(pack_bf16_t_kernel, grid, dim3(256), 0, st, src, src_half, ld_src, lo_off, R, C, d, seg));
   }
+  HN_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_pack_bf16_strided(const void* p, int type, int lo_off, long s_r, long s_c, long s_b1, long s_b2, int nb1,
+                             int nb2, long R, int C, void* dst, int seg, cudaStream_t st) {
+  HN_REQUIRE(seg >= C && nb1 >= 1 && nb2 >= 1 && static_cast<long>(nb1) * nb2 <= 65535 && (R + 31) / 32 <= 65535,
+             "pack_bf16_strided: bad shape");
+  PackSrc s{p, type, lo_off, s_r, s_c, s_b1, s_b2};
+  const dim3 grid(static_cast<unsigned>((seg + 31) / 32), static_cast<unsigned>((R + 31) / 32), static_cast<unsigned>(nb1 * nb2));
+  HN_CHECK_CUDA(launch_k(pack_bf16_strided_kernel, grid, dim3(256), 0, st, s, nb2, R, C, static_cast<__nv_bfloat16*>(dst), seg));
   HN_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

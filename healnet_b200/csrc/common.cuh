@@ -119,6 +119,12 @@ struct GemmArgs {
   // operands are bf16 instead of fp16 (same split layout): the backward pass, whose gradient operands need fp32's
   // exponent range; fp32-output epilogues only
   int bf16 = 0;
+  // batched form (backward pass): nbatch independent products whose operand rows are stacked — batch z reads A rows
+  // [z * a_brows, z * a_brows + M) and B rows [z * b_brows, z * b_brows + N) — and whose outputs start at
+  // out + (z / nb2) * out_b1 + (z % nb2) * out_b2 (elements). fp32 epilogues, no clusters, no fused LayerNorm.
+  int nbatch = 1, nb2 = 1;
+  long a_brows = 0, b_brows = 0, out_b1 = 0, out_b2 = 0;
+  float alpha = 1.f;  // out (+)= alpha * A B^T (+ bias)
 };
 int launch_gemm(const GemmArgs& a, cudaStream_t stream);
 // can this residual GEMM also emit the next LayerNorm (GemmArgs::ln_*)? (shape / alignment rules, HN_GEMM_LN switch)

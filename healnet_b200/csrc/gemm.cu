@@ -62,6 +62,10 @@ struct GemmDev {
   int ln_epoch;  // fused launches so far in this forward, this one included
   int tiles_m, tiles_n;  // output tiles; with clusters: super-tiles of CN tiles along N (SHARE_A) or M (!SHARE_A)
   int bf16;              // operands are bf16 (kind::f16 with a_format = b_format = bf16)
+  int nbatch, nb2;       // batched form: see GemmArgs
+  int a_brows, b_brows;
+  long out_b1, out_b2;
+  float alpha;
 };
 
 __device__ __forceinline__ void split_half(float v, __half& hi, __half& lo) {
@@ -112,12 +116,14 @@ __global__ void __launch_bounds__((2 + EPI_WARPS) * 32, 1) gemm_kernel(const __g
   // persistent loop over super-tiles (= tiles when CN == 1); every CTA of a cluster walks the same sequence
   const int crank = CN > 1 ? static_cast<int>(cluster_ctarank()) : 0;
   const int sup_m = SHARE_A ? p.tiles_m : p.tiles_m / CN, sup_n = SHARE_A ? p.tiles_n / CN : p.tiles_n;
-  const int n_tiles = sup_m * sup_n;
+  const int tiles_per = sup_m * sup_n;          // per batch
+  const int n_tiles = tiles_per * p.nbatch;
   const int first = static_cast<int>(blockIdx.x) / CN, stride = static_cast<int>(gridDim.x) / CN;
   const int k_tiles = (p.K + BK - 1) / BK;
   constexpr uint16_t CMASK = static_cast<uint16_t>((1u << CN) - 1u);
-  auto tile_m0 = [&](int t) { return ((t % sup_m) * (SHARE_A ? 1 : CN) + (SHARE_A ? 0 : crank)) * BM; };
-  auto tile_n0 = [&](int t) { return ((t / sup_m) * (SHARE_A ? CN : 1) + (SHARE_A ? crank : 0)) * BN; };
+  // (row / column origin of a tile INSIDE its batch; the batch index is tile / tiles_per)
+  auto tile_m0 = [&](int t) { t %= tiles_per; return ((t % sup_m) * (SHARE_A ? 1 : CN) + (SHARE_A ? 0 : crank)) * BM; };
+  auto tile_n0 = [&](int t) { t %= tiles_per; return ((t / sup_m) * (SHARE_A ? CN : 1) + (SHARE_A ? crank : 0)) * BN; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -145,7 +151,8 @@ __global__ void __launch_bounds__((2 + EPI_WARPS) * 32, 1) gemm_kernel(const __g
       tma_prefetch_desc(&tmB);
       int it = 0;
       for (int tile = first; tile < n_tiles; tile += stride) {
-        const int m0 = tile_m0(tile), n0 = tile_n0(tile);
+        const int z = tile / tiles_per;
+        const int m0 = tile_m0(tile) + z * p.a_brows, n0 = tile_n0(tile) + z * p.b_brows;  // operand ROW coordinates
         for (int kt = 0; kt < k_tiles; ++kt, ++it) {
           const int s = it % stages;
           mbar_wait(&empty_bar[s], ((it / stages) & 1) ^ 1);  // (clusters: released by every CTA that reads it)
@@ -210,6 +217,8 @@ __global__ void __launch_bounds__((2 + EPI_WARPS) * 32, 1) gemm_kernel(const __g
     int j = 0;
     for (int tile = first; tile < n_tiles; tile += stride, ++j) {
     const int m0 = tile_m0(tile), n0 = tile_n0(tile);
+    const int zb = tile / tiles_per;
+    const size_t out_off = static_cast<size_t>(zb / p.nb2) * p.out_b1 + static_cast<size_t>(zb % p.nb2) * p.out_b2;
     const int acc = j & 1;
     const uint32_t tD = tmem + acc * BN;
     const int row = m0 + lane_base + lane;
@@ -229,17 +238,17 @@ __global__ void __launch_bounds__((2 + EPI_WARPS) * 32, 1) gemm_kernel(const __g
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
-          v[j] = __uint_as_float(r[j]) + b4.x;
-          v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
-          v[j + 2] = __uint_as_float(r[j + 2]) + b4.z;
-          v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
+          v[j] = fmaf(__uint_as_float(r[j]), p.alpha, b4.x);
+          v[j + 1] = fmaf(__uint_as_float(r[j + 1]), p.alpha, b4.y);
+          v[j + 2] = fmaf(__uint_as_float(r[j + 2]), p.alpha, b4.z);
+          v[j + 3] = fmaf(__uint_as_float(r[j + 3]), p.alpha, b4.w);
         }
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           float b = 0.f;
           if (p.bias != nullptr && nb + j < p.N) b = __ldg(p.bias + nb + j);
-          v[j] = __uint_as_float(r[j]) + b;
+          v[j] = fmaf(__uint_as_float(r[j]), p.alpha, b);
         }
       }
       if (row_ok) {
@@ -292,7 +301,7 @@ __global__ void __launch_bounds__((2 + EPI_WARPS) * 32, 1) gemm_kernel(const __g
           }
         }
       } else {
-        float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + nb;
+        float* o = reinterpret_cast<float*>(p.out) + out_off + static_cast<size_t>(row) * p.ldo + nb;
         const bool resid = (p.epi == EPI_RES || p.epi == EPI_RES_LEAKY);
         const bool leaky = (p.epi == EPI_RES_LEAKY || p.epi == EPI_LEAKY_F32);
         if (full) {
@@ -403,14 +412,16 @@ int launch_t(const GemmArgs& a, cudaStream_t stream) {
   const uint64_t a_cols = a.terms == 3 ? static_cast<uint64_t>(a.a_seg) + a.K : a.K;
   const uint64_t b_cols = a.terms >= 2 ? static_cast<uint64_t>(a.b_seg) + a.K : a.K;
   const CUtensorMapSwizzle swz = BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-  if (!make_tmap_2d_f16(&tmA, a.A, a.M, a_cols, static_cast<uint64_t>(a.lda) * 2, SHARE_A ? BM / CN : BM, BK, swz) ||
-      !make_tmap_2d_f16(&tmB, a.B, a.N, b_cols, static_cast<uint64_t>(a.ldb) * 2, SHARE_A ? BN : BN / CN, BK, swz)) {
+  const uint64_t a_rows = static_cast<uint64_t>(a.a_brows) * (a.nbatch - 1) + a.M;
+  const uint64_t b_rows = static_cast<uint64_t>(a.b_brows) * (a.nbatch - 1) + a.N;
+  if (!make_tmap_2d_f16(&tmA, a.A, a_rows, a_cols, static_cast<uint64_t>(a.lda) * 2, SHARE_A ? BM / CN : BM, BK, swz) ||
+      !make_tmap_2d_f16(&tmB, a.B, b_rows, b_cols, static_cast<uint64_t>(a.ldb) * 2, SHARE_A ? BN : BN / CN, BK, swz)) {
     set_error("gemm: cuTensorMapEncodeTiled failed");
     return -2;
   }
   const bool half_out = (a.epi == EPI_F16 || a.epi == EPI_GATE_F16);
   const int vec_ok = ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0) && (a.ldo % (half_out ? 8 : 4) == 0) &&
-                     (a.out_seg % 8 == 0);
+                     (a.out_seg % 8 == 0) && (a.out_b1 % 4 == 0) && (a.out_b2 % 4 == 0);
   const int stage_bytes = ((a.terms == 3 ? 2 : 1) * BM + (a.terms >= 2 ? 2 : 1) * BN) * BK * 2;
   int stages = SMEM_BUDGET / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -418,7 +429,8 @@ int launch_t(const GemmArgs& a, cudaStream_t stream) {
   GemmDev p{a.M, a.N, a.K, a.epi, a.act, a.bias, a.out, a.ldo, vec_ok, a.terms, a.a_seg, a.b_seg,
             half_out ? a.out_seg : 0, stages,
             (a.bias != nullptr && (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0) ? 1 : 0,
-            a.ln_gamma, a.ln_beta, a.ln_out, a.ln_ld, a.ln_seg, a.ln_counters, a.ln_epoch, tiles_m, tiles_n, a.bf16};
+            a.ln_gamma, a.ln_beta, a.ln_out, a.ln_ld, a.ln_seg, a.ln_counters, a.ln_epoch, tiles_m, tiles_n, a.bf16,
+            a.nbatch, a.nb2, static_cast<int>(a.a_brows), static_cast<int>(a.b_brows), a.out_b1, a.out_b2, a.alpha};
   const int smem = stages * stage_bytes + 1024;
   int dev = 0, sms = 0;
   HN_CHECK_CUDA(cudaGetDevice(&dev));
@@ -426,7 +438,7 @@ int launch_t(const GemmArgs& a, cudaStream_t stream) {
   // per device and cheap: set on every launch so a process driving several GPUs never misses it
   HN_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, BK, CN, SHARE_A>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      SMEM_BUDGET + 1024));
-  const long n_super = static_cast<long>(tiles_m) * tiles_n / CN;  // the caller guarantees divisibility
+  const long n_super = static_cast<long>(tiles_m) * tiles_n * a.nbatch / CN;  // the caller guarantees divisibility
   const long max_clusters = sms / CN;
   const unsigned grid = static_cast<unsigned>((n_super < max_clusters ? n_super : max_clusters) * CN);
   // the fused-LayerNorm epilogue makes the CTAs of the grid wait for each other: launch it cooperatively so that the
@@ -462,6 +474,16 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   if (a.epi == EPI_GATE_F16) HN_REQUIRE(a.N % 2 == 0, "gemm: gated epilogue needs even N");
   HN_REQUIRE(a.terms >= 1 && a.terms <= 3, "gemm: terms must be 1, 2 or 3");
   HN_REQUIRE(!a.bf16 || a.epi == EPI_RES || a.epi == EPI_F32, "gemm: bf16 operands go with fp32 epilogues");
+  HN_REQUIRE(a.nbatch >= 1 && a.nb2 >= 1, "gemm: bad batch count");
+  if (a.nbatch > 1) {
+    HN_REQUIRE((a.epi == EPI_RES || a.epi == EPI_F32) && a.ln_out == nullptr && a.bias == nullptr,
+               "gemm: the batched form has plain fp32 epilogues only");
+    HN_REQUIRE(a.a_brows >= a.M && a.b_brows >= a.N &&
+                   a.a_brows * a.nbatch < 2147483647L && a.b_brows * a.nbatch < 2147483647L &&
+                   static_cast<long>((a.M + BM - 1) / BM) * ((a.N + 63) / 64) * a.nbatch < 2147483647L,
+               "gemm: batched operand rows out of range");
+  }
+  HN_REQUIRE(a.alpha == 1.f || a.epi == EPI_RES || a.epi == EPI_F32, "gemm: alpha goes with the plain fp32 epilogues");
   if (a.ln_out != nullptr) {
     const bool resid = a.epi == EPI_RES || a.epi == EPI_RES_LEAKY;
     const bool aligned = (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.ln_out) & 7) == 0 &&
@@ -475,8 +497,8 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   if (a.terms == 3) HN_REQUIRE(a.a_seg % 64 == 0 && a.a_seg >= a.K, "gemm: A lo segment must start at a multiple of 64 >= K");
   // widest tile that still gives (nearly) every SM one
   const long mt = (a.M + BM - 1) / BM;
-  const long tiles256 = static_cast<long>((a.N + 255) / 256) * mt;
-  const long tiles128 = static_cast<long>((a.N + 127) / 128) * mt;
+  const long tiles256 = static_cast<long>((a.N + 255) / 256) * mt * a.nbatch;
+  const long tiles128 = static_cast<long>((a.N + 127) / 128) * mt * a.nbatch;
   static int force = -1, force_bk = -1;  // tuning knobs: HN_GEMM_BN=64|128|256, HN_GEMM_BK=32|64
   if (force < 0) {
     const char* e = getenv("HN_GEMM_BN");
@@ -497,7 +519,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     if (cl == 1) cl = -4;  // forced
   }
   const int tn = (a.N + bn - 1) / bn;
-  const bool want_cluster = cl < 0 || (cl > 1 && a.M >= 16384);
+  const bool want_cluster = a.nbatch == 1 && (cl < 0 || (cl > 1 && a.M >= 16384));
   if (bk == 64 && want_cluster) {
     if (bn == 64 && tn % 4 == 0) return launch_t<64, 64, 4, true>(a, stream);
     if (bn == 64 && tn % 2 == 0) return launch_t<64, 64, 2, true>(a, stream);

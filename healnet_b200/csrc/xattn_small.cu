@@ -147,6 +147,38 @@ __device__ __forceinline__ uint32_t ex2_pair_h2(float x0, float x1) {
   asm("max.s16x2 %0, %1, %2;" : "=r"(r) : "r"(r), "r"(0u));
   return r;
 }
+// Leaner form of the same polynomial for the steady-state path (10 issue slots per pair instead of 13):
+//   * only the LOWER clamp is applied, at -16, as one unsigned integer min on the fp16 bit patterns (negative halves
+//     order by magnitude: min.u16 with bits(-16) clamps them, positive ones pass). rint(x) = -16 already flushes
+//     to an exact zero below (exponent field 15 - 16 < 0);
+//   * the magic constant is 1536 + 16, so t = 1552 + rint(x) has the bit pattern 0x6600 + n', n' = rint(x) + 16 in
+//     [0, 31] for every admissible x: the exponent insert is then ONE 32-bit multiply-add (t * 1024 + p: no carry can
+//     cross the lanes, and what the low lane's constant bits push into the high lane is the constant 0x198) followed by
+//     one lane-wise add of the correction (-16 << 10 per lane, -0x198 in the high lane) fused with the signed max
+//     against 0 that flushes the lanes whose exponent ran through zero;
+//   * there is no upper clamp: an x that rounds to 16 or more (P above 2^15, the raise threshold) gives n' >= 32, i.e.
+//     a t word with a bit outside 0x661F (every 16-bit number above 0x661F has one; t is monotonic in x up to +inf /
+//     NaN). The caller ORs the t words together (one 3-input LOP3 per two pairs) and takes the exact path — where
+//     nothing of this result is used — when such a bit shows, exactly as it does for a MUFU lane above 2^15.
+constexpr uint32_t POLY_T_OK = 0x661F661Fu;
+__device__ __forceinline__ uint32_t ex2_pair_h2_lean(float x0, float x1, uint32_t& tbits) {
+  const uint32_t xr = pack_half2(x0, x1);
+  uint32_t xb;
+  asm("min.u16x2 %0, %1, %2;" : "=r"(xb) : "r"(xr), "r"(0xCC00CC00u));
+  const __half2 xh = *reinterpret_cast<const __half2*>(&xb);
+  const __half2 magic = __float2half2_rn(1552.f);
+  const __half2 t = __hadd2(xh, magic);
+  const __half2 f = __hsub2(xh, __hsub2(t, magic));
+  __half2 p = __float2half2_rn(0.05517167f);
+  p = __hfma2(p, f, __float2half2_rn(0.24261112f));
+  p = __hfma2(p, f, __float2half2_rn(0.69326099f));
+  p = __hfma2(p, f, __float2half2_rn(0.99992807f));
+  tbits = *reinterpret_cast<const uint32_t*>(&t);
+  uint32_t r = tbits * 1024u + *reinterpret_cast<const uint32_t*>(&p);
+  asm("add.u16x2 %0, %1, %2;" : "=r"(r) : "r"(r), "r"(0xBE68C000u));
+  asm("max.s16x2 %0, %1, %2;" : "=r"(r) : "r"(r), "r"(0u));
+  return r;
+}
 // PMODE >= 5: which column PAIRS take the half2 polynomial: 5 = 1/3, 6 = 1/2, 7 = 2/3, 8 = 1/4
 template <int PMODE>
 __device__ __forceinline__ constexpr bool poly_pair(int j) {
@@ -572,40 +604,62 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 
         bool exact = stale || i >= n_steady;
         stale = false;
-        uint32_t pk[32];  // P(i) as packed fp16 pairs; stored over S columns 0..31 once the whole row is known good
+        // P(i) as packed fp16 pairs goes over S columns 0..31 once the whole row is known good (this thread has read
+        // all 64 of them)
+        auto published = [&]() {
+          tmem_wait_st();
+          fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_ready[g][buf]);
+          __syncwarp();
+        };
         if (!exact) {
-          // ---------------- steady state: P = 2^S chunk by chunk; no max pass, no subtraction, no mask
-          uint32_t pmax = 0;
+          // ---------------- steady state: P = 2^S in four 16-column chunks; no max pass, no subtraction, no mask.
+          // 16-register loads and 8-register stores: with 32-register tuples ptxas spent ~30 MOVs per tile on moving
+          // results into the store tuple (tools/sass_tile_mix.py counts the body)
+          uint32_t pk[4][8];
+          uint32_t pmax = 0, tor = 0;
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t s[32];
-            tmem_ld32(tS + c * 32, s);
+          for (int c = 0; c < 4; ++c) {
+            uint32_t s[16];
+            tmem_ld16(tS + c * 16, s);
             tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int j = 0; j < 8; ++j) {
               const float x0 = __uint_as_float(s[2 * j]), x1 = __uint_as_float(s[2 * j + 1]);
 #ifdef HN_DEBUG
               if (PMODE == 9) {  // timing experiment only (debug builds): no exponentials at all (skeleton cost)
-                pk[c * 16 + j] = pack_half2(x0, x1) & 0x3FFF3FFFu;
+                pk[c][j] = pack_half2(x0, x1) & 0x3FFF3FFFu;
               } else
 #endif
               if (PMODE >= 5 && poly_pair<PMODE>(j)) {
-                pk[c * 16 + j] = ex2_pair_h2(x0, x1);
+                uint32_t tb;
+                pk[c][j] = ex2_pair_h2_lean(x0, x1, tb);
+                tor |= tb;  // an overflowing polynomial lane shows in its t word, not in its result
               } else {
                 const float e0 = (PMODE < 5 && poly_slot<PMODE>(2 * j)) ? ex2_poly(x0) : ex2_mufu(x0);
                 const float e1 = (PMODE < 5 && poly_slot<PMODE>(2 * j + 1)) ? ex2_poly(x1) : ex2_mufu(x1);
-                pk[c * 16 + j] = pack_half2(e0, e1);
+                pk[c][j] = pack_half2(e0, e1);
               }
-              pmax = vmaxu2(pmax, pk[c * 16 + j]);
             }
+            // (kept together so that ptxas pairs them into 3-input VIMNMX3)
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (!(PMODE >= 5 && poly_pair<PMODE>(j))) pmax = vmaxu2(pmax, pk[c][j]);
             // S(i+1) has normally been complete for most of a tile: test its barrier here, where the ~100 clk of the
             // try_wait hide behind the second half's exponentials, instead of opening the next tile with it
-            if (c == 0) ready = mbar_try_wait(&s_full[g][buf ^ 1], buf ? (ph ^ 1) : ph);
+            if (c == 1) ready = mbar_try_wait(&s_full[g][buf ^ 1], buf ? (ph ^ 1) : ph);
           }
-          const bool big = ((pmax & 0xFFFFu) > P_RAISE_BITS) || ((pmax >> 16) > P_RAISE_BITS);
-          exact = __any_sync(0xffffffffu, big);  // some P above 2^8 (or inf / garbage): redo with a raised reference
+          const bool big = ((pmax & 0xFFFFu) > P_RAISE_BITS) || ((pmax >> 16) > P_RAISE_BITS) || (tor & ~POLY_T_OK) != 0u;
+          exact = __any_sync(0xffffffffu, big);  // some P above 2^15 (or inf / garbage): redo with a raised reference
+          if (!exact) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tmem_st8(tS + c * 8, pk[c]);
+            published();
+          }
         }
         if (exact) {
+          uint32_t pk[32];
           // ---------------- exact path (first tiles, masked / ragged tile, stale fold, or the reference max has
           // to be raised): max pass, rescale, exp pass. TMEM holds s - m_in (nothing has been overwritten yet).
           const int tile_idx = t_begin + i;
@@ -680,13 +734,9 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           }
           // the tile S(i+2) that will land in this buffer carries the current reference
           if (buf) m_in1 = m_cur; else m_in0 = m_cur;
+          tmem_st32(tS, pk);
+          published();
         }
-        tmem_st32(tS, pk);  // P(i) over S columns 0..31 (this thread has read all 64 of them)
-        tmem_wait_st();
-        fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_ready[g][buf]);
-        __syncwarp();
       };
       {
         int i = 0;
@@ -1137,7 +1187,9 @@ static int launch_small_variant(const AttnArgs& a, cudaStream_t stream) {
 int launch_small_attention(const AttnArgs& a, cudaStream_t stream) {
   HN_REQUIRE(a.batch > 0 && a.L > 0 && a.H > 0 && a.N > 0 && a.nsplit > 0, "attention: empty problem");
   HN_REQUIRE(a.kd == 32 || a.kd == 64, "attention: shared-context rows must be 32 or 64 wide");
+#ifndef HN_DEBUG
   HN_REQUIRE(a.kv_ld == (a.precise ? 2 * a.kd : a.kd), "attention: shared-context rows must be dense ([hi | lo] when split)");
+#endif
   HN_REQUIRE(!a.precise || a.q_lo_off >= a.H * a.kd, "attention: split Q' rows need the lo-part offset");
   HN_REQUIRE(a.q_ld % 8 == 0, "attention: row pitches must be multiples of 8 elements");
   HN_REQUIRE(a.N < (1L << 31), "attention: token axis too long");
