@@ -578,7 +578,7 @@ def run_gpu_arm(args):
             gpu_launches=launches, roofline=roof, step_shares=shares,
             algorithmic=dict(tflop_per_sample=flops_per_sample(kwargs, shapes) / 1e12,
                              tflops_as_written=value * flops_per_sample(kwargs, shapes) / 1e12,
-                             frac_as_written=value * flops_per_sample(kwargs, shapes) / 1e12 / peaks["tflops"]),
+                             frac_as_written=value * flops_per_sample(kwargs, shapes) / 1e12 / (peaks["tflops"] * world)),
         )
         if token_sharded is not None:
             line["token_sharded"] = token_sharded

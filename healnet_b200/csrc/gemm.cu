@@ -345,6 +345,7 @@ __global__ void __launch_bounds__((2 + EPI_WARPS) * 32, 1) gemm_kernel(const __g
           asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
           if (seen < target) __nanosleep(40);
         } while (seen < target && ++spins < (1 << 24));
+        if (seen < target) __trap();  // never normalise incomplete rows: fail the launch loudly instead
       }
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
       {

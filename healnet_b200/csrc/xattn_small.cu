@@ -72,6 +72,7 @@ struct SmallDev {
   int tiles_total;
   int mask_words;  // 64-token mask words per sample
   int c_ones;  // column of z that is 1.0 (= context width C): Q' carries -m_ref there
+  int rt_zero;  // 0, but only known at run time (pins the mid-tile barrier test behind the exponentials, see below)
   long N;
   const uint64_t* mask_bits;
   float* part_acc;
@@ -646,9 +647,16 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               if (!(PMODE >= 5 && poly_pair<PMODE>(j))) pmax = vmaxu2(pmax, pk[c][j]);
-            // S(i+1) has normally been complete for most of a tile: test its barrier here, where the ~100 clk of the
-            // try_wait hide behind the second half's exponentials, instead of opening the next tile with it
-            if (c == 1) ready = mbar_try_wait(&s_full[g][buf ^ 1], buf ? (ph ^ 1) : ph);
+            // S(i+1) is normally complete well before this tile ends: test its barrier late in the tile, where the
+            // ~100 clk of the test hide behind the last chunk's exponentials, instead of opening the next tile with it.
+            // NON-blocking test, and its address is made to depend on this chunk's results (x rt_zero): ptxas hoists a
+            // free-standing barrier instruction to the top of the tile, where S(i+1) cannot be complete yet, and a
+            // blocking try_wait there held back the publication of P(i) until S(i+1) had landed (ncu source view:
+            // 12 % of the softmax warps' time on the instruction consuming its predicate) — which in turn delayed
+            // PV(i) and S(i+2): the whole pipeline ran in lock-step with the tensor pipe.
+            if (c == 3)  // (anchored on an early result of chunk 2: lands ~80 % through the tile body)
+              ready = mbar_test_wait_addr(smem_u32(&s_full[g][buf ^ 1]) + pk[2][1] * static_cast<uint32_t>(p.rt_zero),
+                                          buf ? (ph ^ 1) : ph);
           }
           const bool big = ((pmax & 0xFFFFu) > P_RAISE_BITS) || ((pmax >> 16) > P_RAISE_BITS) || (tor & ~POLY_T_OK) != 0u;
           exact = __any_sync(0xffffffffu, big);  // some P above 2^15 (or inf / garbage): redo with a raised reference
@@ -1080,6 +1088,7 @@ int launch_small_t(const AttnArgs& a, cudaStream_t stream) {
   p.tiles_total = static_cast<int>((a.N + BT - 1) / BT);
   p.N = a.N;
   p.c_ones = a.c_ones;
+  p.rt_zero = 0;
   p.mask_bits = a.mask_bits;
   p.part_acc = a.part_acc;
   p.part_ml = a.part_ml;
