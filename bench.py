@@ -458,23 +458,27 @@ def run_gpu_arm(args):
     # step i+1 is enqueued (its H2D copies included) before step i's logits are waited for, so the GPU never idles on
     # the host; every step's result still lands in pinned host memory and is read there.
     out_shape = (batch, kwargs["out_dims"])
-    host_out = [torch.empty(out_shape, dtype=io_dtype).pin_memory() for _ in range(2)]
-    out_ready = [torch.cuda.Event() for _ in range(2)]
+    DEPTH = 3   # steps in flight: step i is enqueued before step i-2's logits are read (the module stages the inputs
+                # of up to `host_staging_depth` = 3 calls in separate device buffers)
+    host_out = [torch.empty(out_shape, dtype=io_dtype).pin_memory() for _ in range(DEPTH)]
+    out_ready = [torch.cuda.Event() for _ in range(DEPTH)]
 
     def run_e2e(steps):
         model.keep_output_on_device = True
         checksum = 0.0
         for i in range(steps):
-            out = model(list(host))                      # H2D of this step's inputs + forward, asynchronous
-            host_out[i % 2].copy_(out, non_blocking=True)  # D2H of this step's logits
-            out_ready[i % 2].record()
-            if i >= 1:                                   # read the previous step's logits on the host
-                out_ready[(i - 1) % 2].synchronize()
-                checksum += float(host_out[(i - 1) % 2].float().sum())
-        out_ready[(steps - 1) % 2].synchronize()
-        checksum += float(host_out[(steps - 1) % 2].float().sum())
+            out = model(list(host))                          # H2D of this step's inputs + forward, asynchronous
+            host_out[i % DEPTH].copy_(out, non_blocking=True)  # D2H of this step's logits
+            out_ready[i % DEPTH].record()
+            j = i - (DEPTH - 1)
+            if j >= 0:                                       # read an earlier step's logits on the host
+                out_ready[j % DEPTH].synchronize()
+                checksum += float(host_out[j % DEPTH].float().sum())
+        for j in range(max(steps - (DEPTH - 1), 0), steps):
+            out_ready[j % DEPTH].synchronize()
+            checksum += float(host_out[j % DEPTH].float().sum())
         model.keep_output_on_device = False
-        return host_out[(steps - 1) % 2], checksum
+        return host_out[(steps - 1) % DEPTH], checksum
 
     def barrier():
         if world > 1:
@@ -506,17 +510,23 @@ def run_gpu_arm(args):
         kts = {(k, m): model.read_kernel_timing(m, k) for m in range(len(shapes)) for k in (0, 1, 2)}
     model.enable_kernel_timing(False)
     launches = model.last_launch_count * args.steps
-    run_e2e(2)
-    # wall clock here on purpose: the timed region ends when the last step's logits have been read on the host
-    barrier()
-    t0 = time.perf_counter()
-    out_h, _ = run_e2e(args.steps)
-    torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    run_e2e(DEPTH + 1)
+    # wall clock here on purpose: the timed region ends when the last step's logits have been read on the host.
+    # Three repetitions of the K-step region, the median is reported (all three are in the line): the region is ~0.1 s
+    # of wall clock on a shared host, where a single descheduling of this process is worth tens of per cent.
+    e2e_runs = []
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        out_h, _ = run_e2e(args.steps)
+        torch.cuda.synchronize(dev)
+        e2e_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e2e_s], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        e2e_runs.append(e2e_s)
+    e2e_s = sorted(e2e_runs)[1]
 
     # token-sharded forward of rank 0's batch on every multi-GPU run: checked against the unsharded result
     token_sharded = None
@@ -574,7 +584,11 @@ def run_gpu_arm(args):
             e2e=dict(value=global_batch * args.steps / e2e_s, unit="samples/s",
                      h2d_bytes_per_step=sum(t.numel() * t.element_size() for t in host),
                      d2h_bytes_per_step=out_h.numel() * out_h.element_size(),
-                     pipeline="depth 2: step i+1 is enqueued before step i's logits are read on the host"),
+                     pipeline="depth 3: step i is enqueued before step i-2's logits are read on the host; inputs "
+                              "staged round-robin in 3 device buffer sets, each copy waiting only for the forward "
+                              "that last read its set",
+                     runs_samples_per_s=[round(global_batch * args.steps / t, 1) for t in e2e_runs],
+                     statistic="median of 3 repetitions of the K-step region"),
             gpu_launches=launches, roofline=roof, step_shares=shares,
             algorithmic=dict(tflop_per_sample=flops_per_sample(kwargs, shapes) / 1e12,
                              tflops_as_written=value * flops_per_sample(kwargs, shapes) / 1e12,

@@ -286,6 +286,13 @@ class HealNet(nn.Module):
         self._staged = []       # keeps staged fp32 device copies alive while the handle borrows them
         self._workspace = None
         self._copy_stream = None
+        # inference calls with pinned host inputs: persistent device staging sets used round-robin. The copies of call
+        # i wait only for the forward that last READ set i % depth (an event per set), not for all earlier compute, so
+        # step i+1's host-to-device transfer runs under step i's kernels whatever the PCIe rate of the day is.
+        self.host_staging_depth = 3
+        self._stage_ring = None     # [depth] dicts: modality index -> device tensor
+        self._stage_done = None     # [depth] events: the forward that consumed the set has been enqueued / finished
+        self._stage_k = 0
         self._export_registered = False
         # token-axis sharding across GPUs (enable_token_sharding): (rank, world, min_tokens) or None
         self._token_shard = None
@@ -310,7 +317,7 @@ class HealNet(nn.Module):
     # ------------------------------------------------------------------------------------------------ native
     _NATIVE_DEFAULTS = dict(_handle=None, _handle_dev=None, _weights_sig=None, _staged=(), _workspace=None,
                             _copy_stream=None, _export_registered=False, _exchange=None, _token_shard=None,
-                            _exchange_group=None, _xerr=None)
+                            _exchange_group=None, _xerr=None, _stage_ring=None, _stage_done=None, _stage_k=0)
 
     def __getstate__(self):
         """copy.deepcopy / pickle / torch.save(model): the native handle, staged weights and workspace are
@@ -453,6 +460,16 @@ class HealNet(nn.Module):
         # inputs that all arrive in one 16-bit floating type are consumed as they are (hn_set_io_dtype): no widened
         # copy, half the host-to-device bytes; anything else is staged as fp32 (the reference's dtype follows its
         # inputs, healnet.py:212)
+        # (training-mode calls keep freshly allocated copies: the backward pass may still need them)
+        ring_k = None
+        if not torch.is_grad_enabled() and self.host_staging_depth >= 2:
+            if self._stage_ring is None or len(self._stage_ring) != self.host_staging_depth:
+                self._stage_ring = [dict() for _ in range(self.host_staging_depth)]
+                self._stage_done = [None] * self.host_staging_depth
+                self._stage_k = 0
+            ring_k = self._stage_k
+            self._stage_k = (ring_k + 1) % self.host_staging_depth
+            self._stage_waited = False
         given = {t.dtype for t in tensors[:M] if t is not None}
         io_dtype = given.pop() if len(given) == 1 and next(iter(given)) in (torch.bfloat16, torch.float16) else torch.float32
         for i in range(min(n_given, M)):
@@ -482,7 +499,7 @@ class HealNet(nn.Module):
                 lo, hi = token_shard_bounds(axis_tokens[i], world, rank)
                 tok_begin[i], tok_count[i] = lo, hi - lo
                 data = data.reshape(b, axis_tokens[i], c)[:, lo:hi]
-            staged[i], ready[i] = self._stage_input(data, dev, io_dtype)
+            staged[i], ready[i] = self._stage_input(data, dev, io_dtype, None if ring_k is None else (ring_k, i))
         if batch is None:
             # reference: `b` is unbound -> UnboundLocalError at :225
             raise UnboundLocalError("cannot infer the batch size: every modality is missing")
@@ -557,6 +574,10 @@ class HealNet(nn.Module):
             else:
                 out = self._launch(lib, staged, ready, axis_sizes, skip_self, mask_dev, mask_tokens, batch,
                                    want_latents, dev, stream, tok_begin, tok_count)
+            if ring_k is not None and any(e is not None for e in ready):
+                done = torch.cuda.Event()
+                done.record(torch.cuda.current_stream(dev))
+                self._stage_done[ring_k] = done
             if nan_rows is not None and any(t is not None for t in staged):
                 out = torch.where(nan_rows.view(-1, *([1] * (out.dim() - 1))), torch.full_like(out, float("nan")), out)
         if ret_dtype is not None and not ret_dtype.is_floating_point:
@@ -565,10 +586,11 @@ class HealNet(nn.Module):
             return out.to(dtype=ret_dtype)
         return out.to(device=ret_dev, dtype=ret_dtype)
 
-    def _stage_input(self, data: torch.Tensor, dev: torch.device, dtype: torch.dtype = torch.float32):
+    def _stage_input(self, data: torch.Tensor, dev: torch.device, dtype: torch.dtype = torch.float32, slot=None):
         """-> (contiguous device tensor of `dtype`, event or None). Pinned host tensors are copied on a side stream and
         the forward waits for each modality's copy only where it first reads it (hn_forward_ex), so the transfer
-        of a large late modality overlaps the work on the earlier ones."""
+        of a large late modality overlaps the work on the earlier ones. `slot` = (staging set, modality): copy into
+        the persistent buffer of that set (see host_staging_depth) instead of a fresh allocation."""
         if data.device == dev:
             return data.to(dtype=dtype).contiguous(), None
         # (a token-sharded slice of a pinned tensor is contiguous per sample: copied sample by sample, still async)
@@ -577,15 +599,28 @@ class HealNet(nn.Module):
             if self._copy_stream is None or self._copy_stream.device != dev:
                 self._copy_stream = torch.cuda.Stream(device=dev)
             cur = torch.cuda.current_stream(dev)
-            out = torch.empty(data.shape, dtype=dtype, device=dev)   # allocated on the compute stream
-            self._copy_stream.wait_stream(cur)                              # ...whose earlier users must be done
+            if slot is not None:
+                k, i = slot
+                out = self._stage_ring[k].get(i)
+                if out is None or out.shape != data.shape or out.dtype != dtype or out.device != dev:
+                    out = torch.empty(data.shape, dtype=dtype, device=dev)
+                    out.record_stream(self._copy_stream)
+                    self._stage_ring[k][i] = out
+                    self._copy_stream.wait_stream(cur)      # new memory: its earlier users on this stream must be done
+                elif not self._stage_waited and self._stage_done[k] is not None:
+                    self._copy_stream.wait_event(self._stage_done[k])   # the forward that last read this set
+                self._stage_waited = True
+            else:
+                out = torch.empty(data.shape, dtype=dtype, device=dev)   # allocated on the compute stream
+                self._copy_stream.wait_stream(cur)                          # ...whose earlier users must be done
             with torch.cuda.stream(self._copy_stream):
                 if per_sample:
                     for i in range(data.shape[0]):
                         out[i].copy_(data[i], non_blocking=True)
                 else:
                     out.copy_(data, non_blocking=True)
-                out.record_stream(self._copy_stream)
+                if slot is None:
+                    out.record_stream(self._copy_stream)
                 ev = torch.cuda.Event()
                 ev.record(self._copy_stream)
             return out, ev
