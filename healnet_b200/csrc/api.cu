@@ -816,6 +816,7 @@ int hn::forward_impl(hn_handle* h, int batch, const void* const* modality_ptrs, 
           aa.kd = mp.zw;
           aa.c_ones = mp.C;
           aa.precise = 1;
+          aa.z_tail_merged = (mp.zw == 32 && mp.C >= 17 && mp.C <= 23) ? 1 : 0;   // as launch_build_z_small wrote them
 #ifdef HN_DEBUG
           {  // timing experiment only: single-term scores (shows what the two extra score products cost)
             static const bool nosplit = getenv("HN_SMALL_NOSPLIT") != nullptr;
@@ -1166,8 +1167,10 @@ int hn_op_attention(const void* Q, int q_ld, const void* KV, long kv_ld, int k_c
                     int c_ones, int head_pitch_cols, int batch, int L, int H, long N, int nsplit, const uint8_t* mask,
                     void* mask_bits_scratch, float* part_acc, float* part_ml, void* cuda_stream) {
   // shared_kv: 0 generic, 1 small-context kernel (xattn_small.cu) on single fp16 operands, 3 the same on split
-  // operands (Q' rows [hi | lo at q_ld / 2], z rows [hi (kd) | lo (kd)], kv_ld = 2 kd) — the mode the forward uses
-  HN_REQUIRE(shared_kv == 0 || shared_kv == 1 || shared_kv == 3, "hn_op_attention: shared_kv must be 0, 1 or 3");
+  // operands (Q' rows [hi | lo at q_ld / 2], z rows [hi (kd) | lo (kd)], kv_ld = 2 kd); 4 = 3 with z rows whose lo half
+  // carries the merged tail written by the context-row builder (kd 32, 17 <= C <= 23) — the mode the forward uses
+  HN_REQUIRE(shared_kv == 0 || shared_kv == 1 || shared_kv == 3 || shared_kv == 4,
+             "hn_op_attention: shared_kv must be 0, 1, 3 or 4");
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   AttnArgs aa{};
   aa.Q = static_cast<const __half*>(Q);
@@ -1179,10 +1182,11 @@ int hn_op_attention(const void* Q, int q_ld, const void* KV, long kv_ld, int k_c
   aa.shared_kv = shared_kv ? 1 : 0;
   aa.c_ones = c_ones;
   aa.hp = head_pitch_cols > 0 ? head_pitch_cols : 64;
-  aa.kd = shared_kv == 3 ? static_cast<int>(kv_ld / 2) : (shared_kv ? static_cast<int>(kv_ld) : 64);
-  if (shared_kv == 3) {
+  aa.kd = shared_kv >= 3 ? static_cast<int>(kv_ld / 2) : (shared_kv ? static_cast<int>(kv_ld) : 64);
+  if (shared_kv >= 3) {
     aa.precise = 1;
     aa.q_lo_off = q_ld / 2;
+    aa.z_tail_merged = shared_kv == 4;  // the z rows carry the merged tail (see hn_op_build_context, split rows)
   }
   aa.batch = batch;
   aa.L = L;

@@ -194,6 +194,10 @@ struct AttnArgs {
   int precise = 0;
   int q_lo_off = 0, kv_lo_off = 0;
   int c_ones = 0;        // shared_kv only: index of the 1.0 column of z (= context width C)
+  // shared_kv + precise, kd 32, 17 <= C <= 23: the lo half of every z row also carries the HI parts of columns 16..C-1
+  // in its columns C+1.. (written by launch_build_z_small): the kernel then folds the second 16-column step of both
+  // lo-order score products into ONE UMMA (five score UMMAs per tile instead of six; xattn_small.cu)
+  int z_tail_merged = 0;
   int shared_kv;  // 1 = small-C path
   int kd;         // operand width per head: 64 generic; 32 or 64 (= z row width) on the small-C path
   int hp = 64;    // generic path: head pitch in Q / K / V columns and accumulator width, 64 or 128 (dim_head > 64)

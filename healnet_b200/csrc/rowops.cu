@@ -244,6 +244,14 @@ __global__ void __launch_bounds__(256) build_z_small_kernel(const T* __restrict_
   uint4* dst = reinterpret_cast<uint4*>(z + t * (split ? 2 * ZW : ZW));
 #pragma unroll
   for (int i = 0; i < ZW / 8; ++i) store_hi_lo8(dst + i, split ? dst + ZW / 8 + i : nullptr, v + 8 * i);
+  if (ZW == 32 && split && C >= 17 && C <= 23) {
+    // merged tail of the streaming kernel's score products (xattn_small.cu): the lo half also carries the hi parts of
+    // columns 16..C-1, right behind its (zero) column C
+    __half* lo = z + t * 2 * ZW + ZW;
+#pragma unroll
+    for (int i = 16; i < 24; ++i)
+      if (i < C) lo[C + 1 + i - 16] = __float2half_rn(v[i]);
+  }
 }
 
 // Specialisation for the shapes the path is run on (image / volume: 1-4 raw channels, 1-3 axes, the default 2
@@ -296,6 +304,11 @@ __global__ void __launch_bounds__(256) build_z_small32_fast_kernel(const T* __re
       o[j] = i < C ? (v[i < C ? i : 0] - mean) * rstd : (i == C ? 1.f : 0.f);
     }
     store_hi_lo8(dst + g, split ? dst + ZW / 8 + g : nullptr, o);
+  }
+  if (split && C >= 17 && C <= 23) {  // merged tail (see build_z_small_kernel)
+    __half* lo = z + t * 2 * ZW + ZW;
+#pragma unroll
+    for (int i = 16; i < C; ++i) lo[C + 1 + i - 16] = __float2half_rn((v[i < C ? i : 0] - mean) * rstd);
   }
 }
 

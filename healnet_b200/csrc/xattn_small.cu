@@ -73,6 +73,11 @@ struct SmallDev {
   int mask_words;  // 64-token mask words per sample
   int c_ones;  // column of z that is 1.0 (= context width C): Q' carries -m_ref there
   int rt_zero;  // 0, but only known at run time (pins the mid-tile barrier test behind the exponentials, see below)
+  // 16-column steps of the score products that hold non-zero columns: kh for Q'h.zh (columns 0..C, the fold / ones
+  // column included), kl for each of Q'l.zh and Q'h.zl (columns 0..C-1); merged: their second step runs as ONE UMMA
+  // on the re-arranged Q'l / zl tails (kl = 1 then). The tensor-core pipe (82-87 % busy, ncu) bounds this kernel once
+  // the softmax side is lean: an S UMMA costs ~48 clk of shared-memory operand reads for 32 clk of math.
+  int kh, kl, merged;
   long N;
   const uint64_t* mask_bits;
   float* part_acc;
@@ -441,7 +446,7 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint8_t* sQ = smem;
   uint8_t* sZ = smem + G * Q_GROUP;
   __shared__ uint64_t q_full, z_full[NST], z_empty[NST];
-  __shared__ uint64_t s_full[MAXG][2], p_ready[MAXG][2], u_done[MAXG], acc_done[MAXG];
+  __shared__ uint64_t s_full[MAXG][2], p_ready[MAXG][2], u_done[MAXG], acc_done[MAXG], q_fixed[MAXG];
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -486,6 +491,7 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       mbar_init(&p_ready[g][1], SW);
       mbar_init(&u_done[g], 1);
       mbar_init(&acc_done[g], 1);
+      mbar_init(&q_fixed[g], SW);
     }
     fence_mbar_init();
   }
@@ -531,23 +537,26 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         mbar_wait(&z_full[s], (i / NST) & 1);
         fence_after_sync();
         const uint32_t z0 = smem_u32(sZ + s * Z_STAGE);
-#pragma unroll
-        for (int k = 0; k < KD / 16; ++k)
+        // (only the 16-column steps that hold non-zero columns: columns above C are zero in Q' and z)
+        for (int k = 0; k < p.kh; ++k)
           umma_ss(tG + (i & 1) * 64, smem_desc(q0 + k * 32, 16, SBO, LAYOUT), smem_desc(z0 + k * 32, 16, SBO, LAYOUT),
                   idesc_s, k != 0);
         if (SPLIT) {
-#pragma unroll
-          for (int k = 0; k < KD / 16; ++k)  // Q'_lo . z_hi
+          for (int k = 0; k < p.kl; ++k)  // Q'_lo . z_hi
             umma_ss(tG + (i & 1) * 64, smem_desc(q0 + Q_TILE + k * 32, 16, SBO, LAYOUT),
                     smem_desc(z0 + k * 32, 16, SBO, LAYOUT), idesc_s, true);
-#pragma unroll
-          for (int k = 0; k < KD / 16; ++k)  // Q'_hi . z_lo
+          for (int k = 0; k < p.kl; ++k)  // Q'_hi . z_lo
             umma_ss(tG + (i & 1) * 64, smem_desc(q0 + k * 32, 16, SBO, LAYOUT),
                     smem_desc(z0 + Z_BYTES + k * 32, 16, SBO, LAYOUT), idesc_s, true);
+          if (p.merged)  // columns 16..C-1 of both lo-order products: [Q'h tail | 0 | Q'l tail] . [zl tail | 0 | zh tail]
+            umma_ss(tG + (i & 1) * 64, smem_desc(q0 + Q_TILE + 32, 16, SBO, LAYOUT),
+                    smem_desc(z0 + Z_BYTES + 32, 16, SBO, LAYOUT), idesc_s, true);
         }
         umma_commit(&s_full[g][i & 1]);
       };
       mbar_wait(&q_full, 0);
+      if (SPLIT && p.merged) mbar_wait(&q_fixed[g], 0);  // the row owners have re-arranged the tail of the Q'l tile
+      fence_after_sync();
       issue_s(0);
       if (n > 1) issue_s(1);
       for (int i = 0; i < n; ++i) {
@@ -584,6 +593,40 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       float m_ref = -INFINITY;  // reference max (log2 units), always exactly representable in fp16
       float m_in0 = 0.f, m_in1 = 0.f;  // offset baked into S buffer 0 / 1 by the fold (0: none; else m_ref - P_SHIFT)
 
+      if (SPLIT && KD == 32 && p.merged) {
+        // Merged tail (17 <= C <= 23): columns 16..C-1 of the two lo-order products Q'l.zh and Q'h.zl go through ONE
+        // UMMA on the second 16-column step of the Q'l and zl tiles. The context rows arrive with zl[16..32) =
+        // [zl_16 .. zl_C-1 | 0 | zh_16 .. zh_C-1 | 0 ..] (rowops.cu); every thread re-arranges ITS row of the Q'l tile
+        // to match, once: [Q'h_16 .. Q'h_C-1 | 0 | Q'l_16 .. Q'l_C-1 | 0 ..].
+        mbar_wait(&q_full, 0);
+        uint8_t* qh_t = sQ + g * Q_GROUP;
+        uint8_t* ql_t = qh_t + Q_TILE;
+        const int e = p.c_ones - 16;
+        __half hi_t[8], lo_t[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          hi_t[j] = __float2half_rn(0.f);
+          lo_t[j] = __float2half_rn(0.f);
+          if (j < e) {
+            hi_t[j] = *reinterpret_cast<const __half*>(qh_t + swizzled_off<KD>(trow, 16 + j));
+            lo_t[j] = *reinterpret_cast<const __half*>(ql_t + swizzled_off<KD>(trow, 16 + j));
+          }
+        }
+#pragma unroll
+        for (int c = 16; c < 32; ++c) {
+          __half v = __float2half_rn(0.f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (j < e && c == 16 + j) v = hi_t[j];
+            if (j < e && c == p.c_ones + 1 + j) v = lo_t[j];
+          }
+          *reinterpret_cast<__half*>(ql_t + swizzled_off<KD>(trow, c)) = v;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&q_fixed[g]);
+        __syncwarp();
+      }
       // tiles [0, n_steady) can take the steady-state path (complete, unmasked 64-token tiles; only the globally last
       // tile of the token axis can be ragged)
       const int n_full = (t_end == p.tiles_total && (p.N % BT) != 0) ? n - 1 : n;
@@ -1089,6 +1132,10 @@ int launch_small_t(const AttnArgs& a, cudaStream_t stream) {
   p.N = a.N;
   p.c_ones = a.c_ones;
   p.rt_zero = 0;
+  p.kh = (a.c_ones + 1 + 15) / 16;
+  p.kl = (a.c_ones + 15) / 16;
+  p.merged = (a.z_tail_merged && SPLIT && KD == 32 && SW == 4 && a.c_ones >= 17 && a.c_ones <= 23) ? 1 : 0;
+  if (p.merged) p.kl = 1;
   p.mask_bits = a.mask_bits;
   p.part_acc = a.part_acc;
   p.part_ml = a.part_ml;

@@ -237,7 +237,9 @@ HN_API int hn_op_attention_nsplit(int batch, int L, int H, long N, int small_kd)
 /* Streaming attention partials + combine. shared_kv == 1: small-C path (Q rows kd = kv_ld = 32 | 64 wide per head,
  * KV = z rows whose column c_ones is 1.0; Q column c_ones must be 0); shared_kv == 3: the same on split operands —
  * Q' rows [hi (H kd) | lo at column q_ld / 2], z rows [hi (kd) | lo (kd)] (kv_ld = 2 kd), scores from three fp16
- * products (the forward's mode); part_acc rows are kd (small-C) or 64 (generic: head_pitch = 64 | 128) floats wide;
+ * products; shared_kv == 4: as 3, on z rows whose lo half carries the merged tail the context-row builder writes for
+ * kd 32 and 17 <= C <= 23 (lo columns C+1 .. 2C-16 = hi columns 16 .. C-1; the forward's mode: five score products per
+ * tile instead of six); part_acc rows are kd (small-C) or 64 (generic: head_pitch = 64 | 128) floats wide;
  * head_pitch is the column pitch of one head in Q / K / V / O. */
 HN_API int hn_op_attention(const void* Q, int q_ld, const void* KV, long kv_ld, int k_col0, int v_col0, int shared_kv,
                            int c_ones, int head_pitch, int batch, int L, int H, long N, int nsplit, const uint8_t* mask,

@@ -119,7 +119,15 @@ def test_build_context_matches_reference_encoding(axes, c):
                                    tab.data_ptr(), st) == 0
     assert torch.equal(zs[..., :zw], z)
     torch.testing.assert_close((zs[..., :C].float() + zs[..., zw:zw + C].float()).cpu(), want, rtol=2e-5, atol=2e-5)
-    assert bool((zs[..., zw + C:] == 0).all())
+    if zw == 32 and 17 <= C <= 23:
+        # merged tail (xattn_small.cu): the lo half also carries the hi parts of columns 16..C-1 right behind its zero
+        # column C; everything else above the context width is zero
+        e = C - 16
+        assert bool((zs[..., zw + C] == 0).all())
+        assert torch.equal(zs[..., zw + C + 1:zw + C + 1 + e], zs[..., 16:C])
+        assert bool((zs[..., zw + C + 1 + e:] == 0).all())
+    else:
+        assert bool((zs[..., zw + C:] == 0).all())
     ldz = (C + 7) // 8 * 8
     z2 = torch.full((b * N, ldz), float("nan"), dtype=torch.float16, device="cuda")
     assert lib.hn_op_build_context(raw.data_ptr(), z2.data_ptr(), ldz, 0, b, c, len(axes), sizes, bands, max_freq, 1,
@@ -176,7 +184,7 @@ def _split_cols(x):
     return torch.cat([hi, (x - hi.float()).half()], dim=-1)
 
 
-@pytest.mark.parametrize("kd,C", [(32, 18), (32, 31), (64, 50)])
+@pytest.mark.parametrize("kd,C", [(32, 18), (32, 31), (64, 50), (32, 13), (32, 16), (32, 23), (64, 40)])
 @pytest.mark.parametrize("b,H,L,N", [(1, 1, 128, 64), (2, 8, 512, 30000), (1, 3, 200, 4100), (2, 2, 130, 777)])
 @pytest.mark.parametrize("masked", [False, True])
 def test_small_context_attention_kernel(kd, C, b, H, L, N, masked):
@@ -196,7 +204,9 @@ def test_small_context_attention_kernel(kd, C, b, H, L, N, masked):
         mask[:, :2] = True
         if N > 200:
             mask[0, 64:192] = False  # whole tiles masked out
-    for variant in (1, 3):
+    # variant 4 (the forward's mode for 17 <= C <= 23): variant 3 on z rows that carry the merged tail, i.e. the hi
+    # parts of columns 16..C-1 copied behind column C of the lo half — five score UMMAs per tile instead of six
+    for variant in (1, 3, 4) if (kd == 32 and 17 <= C <= 23) else (1, 3):
         if variant == 1:
             q = q32.reshape(b, L, H * kd).half()
             z = z32.half()
@@ -206,6 +216,8 @@ def test_small_context_attention_kernel(kd, C, b, H, L, N, masked):
             qs = _split_cols(q32)                                          # (b, L, H, 2kd)
             q = torch.cat([qs[..., :kd].reshape(b, L, H * kd), qs[..., kd:].reshape(b, L, H * kd)], dim=-1).contiguous()
             z = _split_cols(z32).contiguous()
+            if variant == 4:
+                z[..., kd + C + 1:kd + C + 1 + (C - 16)] = z[..., 16:C]
             q_ld, kv_ld = 2 * H * kd, 2 * kd
             q_ref, z_ref = q32, z32
         qh = q_ref.permute(0, 2, 1, 3)
@@ -254,13 +266,15 @@ def test_small_context_split_scores_are_exact_for_peaked_softmax():
     p = torch.softmax(s * math.log(2.0), dim=-1)
     want = (p @ z32.half().float()[:, None].expand(b, H, N, kd).double()).float()
     errs = {}
-    for variant in (1, 3):
+    for variant in (1, 3, 4):
         if variant == 1:
             q, z, q_ld, kv_ld = q32.reshape(b, L, H * kd).half(), z32.half(), H * kd, kd
         else:
             qs = _split_cols(q32)
             q = torch.cat([qs[..., :kd].reshape(b, L, H * kd), qs[..., kd:].reshape(b, L, H * kd)], dim=-1).contiguous()
             z, q_ld, kv_ld = _split_cols(z32).contiguous(), 2 * H * kd, 2 * kd
+            if variant == 4:   # merged tail (the forward's mode at this context width)
+                z[..., kd + C + 1:kd + C + 1 + (C - 16)] = z[..., 16:C]
         nsplit = lib.hn_op_attention_nsplit(b, L, H, N, kd)
         acc = torch.full((b * nsplit * H * 128 * kd,), float("nan"), device="cuda")
         ml = torch.full((b * nsplit * H * 128 * 2,), float("nan"), device="cuda")
@@ -274,9 +288,10 @@ def test_small_context_split_scores_are_exact_for_peaked_softmax():
                                  torch.zeros(H * C, device="cuda").data_ptr(), out.data_ptr(), 2 * H * 64, st) == 0
         got = out[:, :H * 64].float().view(b, L, H, 64).permute(0, 2, 1, 3)[..., :C]
         errs[variant] = float((got - want[..., :C]).abs().max())
-    print("peaked softmax, max abs error of sum p z: single fp16", errs[1], "split", errs[3])
-    assert errs[3] < 2.5e-3            # fp16 P and fp16 output remain
+    print("peaked softmax, max abs error of sum p z: single fp16", errs[1], "split", errs[3], "split, merged tail", errs[4])
+    assert errs[3] < 2.5e-3 and errs[4] < 2.5e-3            # fp16 P and fp16 output remain
     assert errs[3] < 0.5 * errs[1] or errs[1] < 2.5e-3
+    assert errs[4] < 0.5 * errs[1] or errs[1] < 2.5e-3
 
 
 @pytest.mark.parametrize("variant", [1, 3])
