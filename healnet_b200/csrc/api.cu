@@ -821,6 +821,8 @@ int hn::forward_impl(hn_handle* h, int batch, const void* const* modality_ptrs, 
           {  // timing experiment only: single-term scores (shows what the two extra score products cost)
             static const bool nosplit = getenv("HN_SMALL_NOSPLIT") != nullptr;
             if (nosplit) aa.precise = 0;
+            static const bool nomerge = getenv("HN_SMALL_NOMERGE") != nullptr;   // A/B of the merged score tail
+            if (nomerge) aa.z_tail_merged = 0;
           }
 #endif
           aa.q_lo_off = qw;

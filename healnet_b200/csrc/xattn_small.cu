@@ -73,11 +73,11 @@ struct SmallDev {
   int mask_words;  // 64-token mask words per sample
   int c_ones;  // column of z that is 1.0 (= context width C): Q' carries -m_ref there
   int rt_zero;  // 0, but only known at run time (pins the mid-tile barrier test behind the exponentials, see below)
-  // 16-column steps of the score products that hold non-zero columns: kh for Q'h.zh (columns 0..C, the fold / ones
-  // column included), kl for each of Q'l.zh and Q'h.zl (columns 0..C-1); merged: their second step runs as ONE UMMA
-  // on the re-arranged Q'l / zl tails (kl = 1 then). The tensor-core pipe (82-87 % busy, ncu) bounds this kernel once
-  // the softmax side is lean: an S UMMA costs ~48 clk of shared-memory operand reads for 32 clk of math.
-  int kh, kl, merged;
+  // Which 16-column steps of the score products hold non-zero columns (Q'h.zh: columns 0..C, the fold / ones column
+  // included; Q'l.zh and Q'h.zl: columns 0..C-1); merged: the second step of both lo-order products runs as ONE UMMA on
+  // the re-arranged Q'l / zl tails. (ncu: the tensor-core pipe is 82-87 % busy in this kernel.)
+  int mode;    // KD 32, split: 0 = C <= 15 (1 + 1 + 1 UMMAs), 1 = C == 16 (2 + 1 + 1), 2 = merged tail (2 + 1 + 1 + 1), 3 = all
+  int merged;
   long N;
   const uint64_t* mask_bits;
   float* part_acc;
@@ -532,47 +532,85 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     if (g < n_active && elect_one()) {
       const uint32_t tG = tmem + g * GCOLS;
       const uint32_t q0 = smem_u32(sQ + g * Q_GROUP);
-      auto issue_s = [&](int i) {
-        const int s = i % NST;
-        mbar_wait(&z_full[s], (i / NST) & 1);
-        fence_after_sync();
-        const uint32_t z0 = smem_u32(sZ + s * Z_STAGE);
-        // (only the 16-column steps that hold non-zero columns: columns above C are zero in Q' and z)
-        for (int k = 0; k < p.kh; ++k)
-          umma_ss(tG + (i & 1) * 64, smem_desc(q0 + k * 32, 16, SBO, LAYOUT), smem_desc(z0 + k * 32, 16, SBO, LAYOUT),
-                  idesc_s, k != 0);
+      // S(i) = Q'.z_i^T into S buffer i & 1; z0 = shared address of the tile's ring stage (already landed). Only the
+      // 16-column steps that hold non-zero columns are issued (columns above C are zero in Q' and z): KH steps of
+      // Q'h.zh, KL of each lo-order product, compile-time per mode so that the issue sequence stays branch-free.
+      auto issue_s_c = [&](int i, uint32_t z0, auto kh_c, auto kl_c, auto mg_c) {
+        constexpr int KH = decltype(kh_c)::value, KL = decltype(kl_c)::value;
+        constexpr bool MG = decltype(mg_c)::value;
+        const uint32_t tS = tG + (i & 1) * 64;
+#pragma unroll
+        for (int k = 0; k < KH; ++k)
+          umma_ss(tS, smem_desc(q0 + k * 32, 16, SBO, LAYOUT), smem_desc(z0 + k * 32, 16, SBO, LAYOUT), idesc_s, k != 0);
         if (SPLIT) {
-          for (int k = 0; k < p.kl; ++k)  // Q'_lo . z_hi
-            umma_ss(tG + (i & 1) * 64, smem_desc(q0 + Q_TILE + k * 32, 16, SBO, LAYOUT),
-                    smem_desc(z0 + k * 32, 16, SBO, LAYOUT), idesc_s, true);
-          for (int k = 0; k < p.kl; ++k)  // Q'_hi . z_lo
-            umma_ss(tG + (i & 1) * 64, smem_desc(q0 + k * 32, 16, SBO, LAYOUT),
-                    smem_desc(z0 + Z_BYTES + k * 32, 16, SBO, LAYOUT), idesc_s, true);
-          if (p.merged)  // columns 16..C-1 of both lo-order products: [Q'h tail | 0 | Q'l tail] . [zl tail | 0 | zh tail]
-            umma_ss(tG + (i & 1) * 64, smem_desc(q0 + Q_TILE + 32, 16, SBO, LAYOUT),
-                    smem_desc(z0 + Z_BYTES + 32, 16, SBO, LAYOUT), idesc_s, true);
+#pragma unroll
+          for (int k = 0; k < KL; ++k)  // Q'_lo . z_hi
+            umma_ss(tS, smem_desc(q0 + Q_TILE + k * 32, 16, SBO, LAYOUT), smem_desc(z0 + k * 32, 16, SBO, LAYOUT), idesc_s,
+                    true);
+#pragma unroll
+          for (int k = 0; k < KL; ++k)  // Q'_hi . z_lo
+            umma_ss(tS, smem_desc(q0 + k * 32, 16, SBO, LAYOUT), smem_desc(z0 + Z_BYTES + k * 32, 16, SBO, LAYOUT), idesc_s,
+                    true);
+          if (MG)  // columns 16..C-1 of both lo-order products: [Q'h tail | 0 | Q'l tail] . [zl tail | 0 | zh tail]
+            umma_ss(tS, smem_desc(q0 + Q_TILE + 32, 16, SBO, LAYOUT), smem_desc(z0 + Z_BYTES + 32, 16, SBO, LAYOUT), idesc_s,
+                    true);
         }
         umma_commit(&s_full[g][i & 1]);
       };
+      using std::integral_constant;
+      auto issue_s = [&](int i, uint32_t z0) {
+        constexpr int KF = KD / 16;
+        if (KD == 32 && SPLIT) {
+          switch (p.mode) {
+            case 0: issue_s_c(i, z0, integral_constant<int, 1>{}, integral_constant<int, 1>{}, std::false_type{}); return;
+            case 1: issue_s_c(i, z0, integral_constant<int, 2>{}, integral_constant<int, 1>{}, std::false_type{}); return;
+            case 2: issue_s_c(i, z0, integral_constant<int, 2>{}, integral_constant<int, 1>{}, std::true_type{}); return;
+            default: break;
+          }
+        }
+        issue_s_c(i, z0, integral_constant<int, KF>{}, integral_constant<int, KF>{}, std::false_type{});
+      };
+      auto z_stage = [&](int i) {  // wait until tile i's context rows have landed; -> their shared address
+        const int s = i % NST;
+        mbar_wait(&z_full[s], (i / NST) & 1);
+        return smem_u32(sZ + s * Z_STAGE);
+      };
       mbar_wait(&q_full, 0);
       if (SPLIT && p.merged) mbar_wait(&q_fixed[g], 0);  // the row owners have re-arranged the tail of the Q'l tile
-      fence_after_sync();
-      issue_s(0);
-      if (n > 1) issue_s(1);
+      {
+        const uint32_t za = z_stage(0);
+        fence_after_sync();
+        issue_s(0, za);
+      }
+      if (n > 1) {
+        const uint32_t zb = z_stage(1);
+        fence_after_sync();
+        issue_s(1, zb);
+      }
       for (int i = 0; i < n; ++i) {
+        // The softmax warps' wait for S(i+2) starts the moment they publish P(i): everything on this thread between
+        // that arrival and the commit of S(i+2) is on their critical path (ncu: 56 % of the tiles found S not yet
+        // complete). So whatever does not depend on P(i) happens BEFORE the wait: the tile's V descriptors, and the
+        // arrival of the context rows of tile i+2 (landed long ago: the ring is 8 deep).
+        const int s = i % NST;
+        const uint32_t z0 = smem_u32(sZ + s * Z_STAGE);
+        uint64_t dv[BT / 16];
+#pragma unroll
+        for (int k = 0; k < BT / 16; ++k) dv[k] = smem_desc(z0 + k * V_KADV, 16, SBO, LAYOUT);
+        const bool more = i + 2 < n;
+        uint32_t z2 = 0;
+        if (more) z2 = z_stage(i + 2);
+        asm volatile("" ::"l"(dv[0]), "l"(dv[1]), "l"(dv[2]), "l"(dv[3]), "r"(z2) : "memory");
         // all softmax warps of the group: S(i) consumed, P(i) in TMEM, Q' fold up to date. Two alternating barriers: a warp may run
         // one tile ahead of its group but never two, so it cannot arrive twice in one phase of either.
         mbar_wait_sleepy(&p_ready[g][i & 1], (i >> 1) & 1, 20000);
         fence_after_sync();
-        const int s = i % NST;
-        const uint32_t z0 = smem_u32(sZ + s * Z_STAGE);
 #pragma unroll
         for (int k = 0; k < BT / 16; ++k)
-          umma_ts(tG + 128, tG + (i & 1) * 64 + k * 8, smem_desc(z0 + k * V_KADV, 16, SBO, LAYOUT), idesc_u,
-                  (i | k) != 0);
+          umma_ts(tG + 128, tG + (i & 1) * 64 + k * 8, dv[k], idesc_u, (i | k) != 0);
         umma_commit(&z_empty[s]);
         umma_commit(&u_done[g]);
-        if (i + 2 < n) issue_s(i + 2);
+        if (more) issue_s(i + 2, z2);
         if (i + 1 == n) umma_commit(&acc_done[g]);
       }
     }
@@ -1132,10 +1170,8 @@ int launch_small_t(const AttnArgs& a, cudaStream_t stream) {
   p.N = a.N;
   p.c_ones = a.c_ones;
   p.rt_zero = 0;
-  p.kh = (a.c_ones + 1 + 15) / 16;
-  p.kl = (a.c_ones + 15) / 16;
   p.merged = (a.z_tail_merged && SPLIT && KD == 32 && SW == 4 && a.c_ones >= 17 && a.c_ones <= 23) ? 1 : 0;
-  if (p.merged) p.kl = 1;
+  p.mode = a.c_ones <= 15 ? 0 : a.c_ones == 16 ? 1 : p.merged ? 2 : 3;
   p.mask_bits = a.mask_bits;
   p.part_acc = a.part_acc;
   p.part_ml = a.part_ml;
