@@ -448,6 +448,11 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   __shared__ uint64_t q_full, z_full[NST], z_empty[NST];
   __shared__ uint64_t s_full[MAXG][2], p_ready[MAXG][2], u_done[MAXG], acc_done[MAXG], q_fixed[MAXG];
   __shared__ uint32_t tmem_base_s;
+  // UMMA shared-memory descriptors of the context-row ring, one row per stage: [0..3] the V operand of the four
+  // 16-token steps of P.z, [4..7] the K operand steps zh k0, zh k1, zl k0, zl k1 (K-major). Read back with VOLATILE
+  // loads before the issuer's wait for P(i), so that they sit in registers when the wait returns (ptxas otherwise
+  // re-materialises the ~45 instructions of descriptor arithmetic behind the wait, i.e. on the P(i) -> S(i+2) chain).
+  __shared__ __align__(16) uint64_t z_desc[NST][8];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int idx = blockIdx.x;
@@ -495,6 +500,16 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     }
     fence_mbar_init();
   }
+  if (threadIdx.x >= 32 && threadIdx.x < 32 + NST) {
+    const int st = threadIdx.x - 32;
+    const uint32_t z0 = smem_u32(sZ + st * Z_STAGE);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) z_desc[st][k] = smem_desc(z0 + k * V_KADV, 16, SBO, LAYOUT);
+    z_desc[st][4] = smem_desc(z0, 16, SBO, LAYOUT);
+    z_desc[st][5] = smem_desc(z0 + 32, 16, SBO, LAYOUT);
+    z_desc[st][6] = smem_desc(z0 + Z_BYTES, 16, SBO, LAYOUT);
+    z_desc[st][7] = smem_desc(z0 + Z_BYTES + 32, 16, SBO, LAYOUT);
+  }
   constexpr int PRODUCER_WARP = (SW + 1) * G;
   if (warp == PRODUCER_WARP) tmem_alloc<512>(&tmem_base_s);
   fence_before_sync();
@@ -535,40 +550,44 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       // S(i) = Q'.z_i^T into S buffer i & 1; z0 = shared address of the tile's ring stage (already landed). Only the
       // 16-column steps that hold non-zero columns are issued (columns above C are zero in Q' and z): KH steps of
       // Q'h.zh, KL of each lo-order product, compile-time per mode so that the issue sequence stays branch-free.
-      auto issue_s_c = [&](int i, uint32_t z0, auto kh_c, auto kl_c, auto mg_c) {
+      // dz: the K-operand descriptors of the tile's ring stage (KD 32: zh k0, zh k1, zl k0, zl k1 from the table)
+      auto issue_s_c = [&](int i, uint32_t z0, const uint64_t (&dz)[4], auto kh_c, auto kl_c, auto mg_c) {
         constexpr int KH = decltype(kh_c)::value, KL = decltype(kl_c)::value;
         constexpr bool MG = decltype(mg_c)::value;
         const uint32_t tS = tG + (i & 1) * 64;
+        auto zh = [&](int k) { return KD == 32 ? dz[k] : smem_desc(z0 + k * 32, 16, SBO, LAYOUT); };
+        auto zl = [&](int k) { return KD == 32 ? dz[2 + k] : smem_desc(z0 + Z_BYTES + k * 32, 16, SBO, LAYOUT); };
 #pragma unroll
-        for (int k = 0; k < KH; ++k)
-          umma_ss(tS, smem_desc(q0 + k * 32, 16, SBO, LAYOUT), smem_desc(z0 + k * 32, 16, SBO, LAYOUT), idesc_s, k != 0);
+        for (int k = 0; k < KH; ++k) umma_ss(tS, smem_desc(q0 + k * 32, 16, SBO, LAYOUT), zh(k), idesc_s, k != 0);
         if (SPLIT) {
 #pragma unroll
           for (int k = 0; k < KL; ++k)  // Q'_lo . z_hi
-            umma_ss(tS, smem_desc(q0 + Q_TILE + k * 32, 16, SBO, LAYOUT), smem_desc(z0 + k * 32, 16, SBO, LAYOUT), idesc_s,
-                    true);
+            umma_ss(tS, smem_desc(q0 + Q_TILE + k * 32, 16, SBO, LAYOUT), zh(k), idesc_s, true);
 #pragma unroll
           for (int k = 0; k < KL; ++k)  // Q'_hi . z_lo
-            umma_ss(tS, smem_desc(q0 + k * 32, 16, SBO, LAYOUT), smem_desc(z0 + Z_BYTES + k * 32, 16, SBO, LAYOUT), idesc_s,
-                    true);
+            umma_ss(tS, smem_desc(q0 + k * 32, 16, SBO, LAYOUT), zl(k), idesc_s, true);
           if (MG)  // columns 16..C-1 of both lo-order products: [Q'h tail | 0 | Q'l tail] . [zl tail | 0 | zh tail]
-            umma_ss(tS, smem_desc(q0 + Q_TILE + 32, 16, SBO, LAYOUT), smem_desc(z0 + Z_BYTES + 32, 16, SBO, LAYOUT), idesc_s,
-                    true);
+            umma_ss(tS, smem_desc(q0 + Q_TILE + 32, 16, SBO, LAYOUT), zl(1), idesc_s, true);
         }
         umma_commit(&s_full[g][i & 1]);
       };
       using std::integral_constant;
-      auto issue_s = [&](int i, uint32_t z0) {
+      const int mode = p.mode;
+      auto issue_s = [&](int i, uint32_t z0, const uint64_t (&dz)[4]) {
         constexpr int KF = KD / 16;
         if (KD == 32 && SPLIT) {
-          switch (p.mode) {
-            case 0: issue_s_c(i, z0, integral_constant<int, 1>{}, integral_constant<int, 1>{}, std::false_type{}); return;
-            case 1: issue_s_c(i, z0, integral_constant<int, 2>{}, integral_constant<int, 1>{}, std::false_type{}); return;
-            case 2: issue_s_c(i, z0, integral_constant<int, 2>{}, integral_constant<int, 1>{}, std::true_type{}); return;
-            default: break;
-          }
+          // (an if-chain: a switch became an indirect branch through a constant-bank table on the critical path)
+          if (mode == 2) { issue_s_c(i, z0, dz, integral_constant<int, 2>{}, integral_constant<int, 1>{}, std::true_type{}); return; }
+          if (mode == 0) { issue_s_c(i, z0, dz, integral_constant<int, 1>{}, integral_constant<int, 1>{}, std::false_type{}); return; }
+          if (mode == 1) { issue_s_c(i, z0, dz, integral_constant<int, 2>{}, integral_constant<int, 1>{}, std::false_type{}); return; }
         }
-        issue_s_c(i, z0, integral_constant<int, KF>{}, integral_constant<int, KF>{}, std::false_type{});
+        issue_s_c(i, z0, dz, integral_constant<int, KF>{}, integral_constant<int, KF>{}, std::false_type{});
+      };
+      // volatile 16-byte reads of one table row half: [first, first + 4)
+      auto load_desc4 = [&](int stage, int first, uint64_t (&d)[4]) {
+        const uint32_t a = smem_u32(&z_desc[stage][first]);
+        asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];" : "=l"(d[0]), "=l"(d[1]) : "r"(a));
+        asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];" : "=l"(d[2]), "=l"(d[3]) : "r"(a + 16));
       };
       auto z_stage = [&](int i) {  // wait until tile i's context rows have landed; -> their shared address
         const int s = i % NST;
@@ -577,30 +596,33 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       };
       mbar_wait(&q_full, 0);
       if (SPLIT && p.merged) mbar_wait(&q_fixed[g], 0);  // the row owners have re-arranged the tail of the Q'l tile
-      {
-        const uint32_t za = z_stage(0);
+      for (int j = 0; j < 2 && j < n; ++j) {
+        const uint32_t za = z_stage(j);
+        uint64_t dz[4];
+        load_desc4(j % NST, 4, dz);
         fence_after_sync();
-        issue_s(0, za);
-      }
-      if (n > 1) {
-        const uint32_t zb = z_stage(1);
-        fence_after_sync();
-        issue_s(1, zb);
+        issue_s(j, za, dz);
       }
       for (int i = 0; i < n; ++i) {
         // The softmax warps' wait for S(i+2) starts the moment they publish P(i): everything on this thread between
         // that arrival and the commit of S(i+2) is on their critical path (ncu: 56 % of the tiles found S not yet
-        // complete). So whatever does not depend on P(i) happens BEFORE the wait: the tile's V descriptors, and the
-        // arrival of the context rows of tile i+2 (landed long ago: the ring is 8 deep).
+        // complete). So whatever does not depend on P(i) happens BEFORE the wait: the tile's V descriptors, the
+        // arrival of the context rows of tile i+2 (landed long ago: the ring is 8 deep) and their descriptors.
         const int s = i % NST;
-        const uint32_t z0 = smem_u32(sZ + s * Z_STAGE);
-        uint64_t dv[BT / 16];
+        uint64_t dv[4], dz[4] = {0, 0, 0, 0};
+        if (KD == 32) {
+          load_desc4(s, 0, dv);
+        } else {
+          const uint32_t z0 = smem_u32(sZ + s * Z_STAGE);
 #pragma unroll
-        for (int k = 0; k < BT / 16; ++k) dv[k] = smem_desc(z0 + k * V_KADV, 16, SBO, LAYOUT);
+          for (int k = 0; k < 4; ++k) dv[k] = smem_desc(z0 + k * V_KADV, 16, SBO, LAYOUT);
+        }
         const bool more = i + 2 < n;
         uint32_t z2 = 0;
-        if (more) z2 = z_stage(i + 2);
-        asm volatile("" ::"l"(dv[0]), "l"(dv[1]), "l"(dv[2]), "l"(dv[3]), "r"(z2) : "memory");
+        if (more) {
+          z2 = z_stage(i + 2);
+          if (KD == 32) load_desc4((i + 2) % NST, 4, dz);
+        }
         // all softmax warps of the group: S(i) consumed, P(i) in TMEM, Q' fold up to date. Two alternating barriers: a warp may run
         // one tile ahead of its group but never two, so it cannot arrive twice in one phase of either.
         mbar_wait_sleepy(&p_ready[g][i & 1], (i >> 1) & 1, 20000);
@@ -610,7 +632,7 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           umma_ts(tG + 128, tG + (i & 1) * 64 + k * 8, dv[k], idesc_u, (i | k) != 0);
         umma_commit(&z_empty[s]);
         umma_commit(&u_done[g]);
-        if (more) issue_s(i + 2, z2);
+        if (more) issue_s(i + 2, z2, dz);
         if (i + 1 == n) umma_commit(&acc_done[g]);
       }
     }
