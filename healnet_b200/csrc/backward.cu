@@ -283,8 +283,10 @@ int mm(const hn_handle* h, BwdScratch& s, cudaStream_t st, int M, int N, int K, 
       static_cast<long>(M) * nz >= 2147483647L || static_cast<long>(N) * nz >= 2147483647L)
     return sg(st, M, N, K, A, B, C, c_row, alpha, accumulate, nb1, c_b1, nb2, c_b2);
   const int seg = static_cast<int>(segK);
-  BW(launch_pack_bf16_strided(A.p, A.type, A.lo_off, A.s_row, A.s_col, A.s_b1, A.s_b2, nb1, nb2, M, K, s.pA, seg, st));
-  BW(launch_pack_bf16_strided(B.p, B.type, B.lo_off, B.s_col, B.s_row, B.s_b1, B.s_b2, nb1, nb2, N, K, s.pB, seg, st));
+  SgOperand Bt = B;   // B(k, n) viewed as rows n x contraction index k
+  Bt.s_row = B.s_col;
+  Bt.s_col = B.s_row;
+  BW(launch_pack_bf16_pair(A, M, Bt, N, K, nb1, nb2, s.pA, s.pB, seg, st));
   GemmArgs g{static_cast<const __half*>(s.pA), static_cast<const __half*>(s.pB), M, N, K, 2 * seg, 2 * seg,
              accumulate ? EPI_RES : EPI_F32, 0, nullptr, C, static_cast<int>(c_row), 3, seg, seg, 0};
   g.bf16 = 1;

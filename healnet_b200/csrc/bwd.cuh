@@ -38,10 +38,11 @@ int launch_kv_fold_bwd(const float* dWp, const float* W, const float* gamma, con
 // src fp32 (src_half = 0) or split fp16 (src_half = 1, lo at + lo_off)
 int launch_pack_bf16(const void* src, int src_half, long ld_src, int lo_off, long R, int C, void* dst, int seg,
                      int transpose, cudaStream_t st);
-// general strided / batched form: dst[(z R + r) 2 seg + c] = hi | lo of p[b1 s_b1 + b2 s_b2 + r s_r + c s_c]
-// (z = b1 nb2 + b2; type 0 = fp32, 1 = split fp16 with the lo part at + lo_off), pad columns zero
-int launch_pack_bf16_strided(const void* p, int type, int lo_off, long s_r, long s_c, long s_b1, long s_b2, int nb1,
-                             int nb2, long R, int C, void* dst, int seg, cudaStream_t st);
+// general strided / batched form, both operands of one product in ONE launch: dst[(z R + r) 2 seg + c] = hi | lo of
+// p[b1 s_b1 + b2 s_b2 + r s_row + c s_col] (z = b1 nb2 + b2; type 0 = fp32, 1 = split fp16 with the lo part at
+// + lo_off), c < K, pad columns zero. The operands are given as (rows, contraction index) views.
+int launch_pack_bf16_pair(const SgOperand& A, long RA, const SgOperand& B_as_rows, long RB, int K, int nb1, int nb2,
+                          void* dstA, void* dstB, int seg, cudaStream_t st);
 // gate backward on interleaved (a_j, g_j) pre-activations (bias included) -> dh = [d a | d g]
 int launch_gate_bwd_il(const float* h_il, const float* dhid, float* dh, long rows, int F, int snn, cudaStream_t st);
 

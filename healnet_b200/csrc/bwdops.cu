@@ -568,15 +568,32 @@ struct PackSrc {
   int type, lo_off;
   long s_r, s_c, s_b1, s_b2;
 };
-__global__ void __launch_bounds__(256) pack_bf16_strided_kernel(PackSrc s, int nb2, long R, int C,
-                                                                __nv_bfloat16* __restrict__ dst, int seg) {
+// One launch packs BOTH operands of a product: blocks [0, blocks_a) work on operand a, the rest on operand b.
+struct PackJob {
+  PackSrc s;
+  long R;
+  int C, seg;
+  __nv_bfloat16* dst;
+  int tiles_c, tiles_r;   // 32 x 32 tiles per batch entry
+};
+__global__ void __launch_bounds__(256) pack_bf16_strided_kernel(PackJob ja, PackJob jb, long blocks_a, int nb2) {
   HN_PDL_LAUNCH();
   HN_PDL_WAIT();
   __shared__ float tile[32][33];
-  const int z = blockIdx.z;
+  const bool second = static_cast<long>(blockIdx.x) >= blocks_a;
+  const PackJob& j = second ? jb : ja;
+  long blk = static_cast<long>(blockIdx.x) - (second ? blocks_a : 0);
+  const PackSrc& s = j.s;
+  const long R = j.R;
+  const int C = j.C, seg = j.seg;
+  __nv_bfloat16* __restrict__ dst = j.dst;
+  const int tc = static_cast<int>(blk % j.tiles_c);
+  blk /= j.tiles_c;
+  const int tr = static_cast<int>(blk % j.tiles_r);
+  const int z = static_cast<int>(blk / j.tiles_r);
   const long base = static_cast<long>(z / nb2) * s.s_b1 + static_cast<long>(z % nb2) * s.s_b2;
-  const long r0 = static_cast<long>(blockIdx.y) * 32;
-  const int c0 = blockIdx.x * 32;
+  const long r0 = static_cast<long>(tr) * 32;
+  const int c0 = tc * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const bool r_fast = s.s_r == 1 && s.s_c != 1;
   for (int j = ty; j < 32; j += 8) {
@@ -806,13 +823,25 @@ int launch_pack_bf16(const void* src, int src_half, long ld_src, int lo_off, lon
   HN_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
-int launch_pack_bf16_strided(const void* p, int type, int lo_off, long s_r, long s_c, long s_b1, long s_b2, int nb1,
-                             int nb2, long R, int C, void* dst, int seg, cudaStream_t st) {
-  HN_REQUIRE(seg >= C && nb1 >= 1 && nb2 >= 1 && static_cast<long>(nb1) * nb2 <= 65535 && (R + 31) / 32 <= 65535,
-             "pack_bf16_strided: bad shape");
-  PackSrc s{p, type, lo_off, s_r, s_c, s_b1, s_b2};
-  const dim3 grid(static_cast<unsigned>((seg + 31) / 32), static_cast<unsigned>((R + 31) / 32), static_cast<unsigned>(nb1 * nb2));
-  HN_CHECK_CUDA(launch_k(pack_bf16_strided_kernel, grid, dim3(256), 0, st, s, nb2, R, C, static_cast<__nv_bfloat16*>(dst), seg));
+int launch_pack_bf16_pair(const SgOperand& A, long RA, const SgOperand& B_as_rows, long RB, int K, int nb1, int nb2,
+                          void* dstA, void* dstB, int seg, cudaStream_t st) {
+  HN_REQUIRE(seg >= K && nb1 >= 1 && nb2 >= 1, "pack_bf16_pair: bad shape");
+  const long nz = static_cast<long>(nb1) * nb2;
+  auto job = [&](const SgOperand& o, long R, void* dst) {
+    PackJob j;
+    j.s = PackSrc{o.p, o.type, o.lo_off, o.s_row, o.s_col, o.s_b1, o.s_b2};
+    j.R = R;
+    j.C = K;
+    j.seg = seg;
+    j.dst = static_cast<__nv_bfloat16*>(dst);
+    j.tiles_c = (seg + 31) / 32;
+    j.tiles_r = static_cast<int>((R + 31) / 32);
+    return j;
+  };
+  const PackJob ja = job(A, RA, dstA), jb = job(B_as_rows, RB, dstB);
+  const long ba = static_cast<long>(ja.tiles_c) * ja.tiles_r * nz, bb = static_cast<long>(jb.tiles_c) * jb.tiles_r * nz;
+  HN_REQUIRE(ba + bb < 2147483647L, "pack_bf16_pair: grid too large");
+  HN_CHECK_CUDA(launch_k(pack_bf16_strided_kernel, dim3(static_cast<unsigned>(ba + bb)), dim3(256), 0, st, ja, jb, ba, nb2));
   HN_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -433,12 +433,20 @@ int launch_t(const GemmArgs& a, cudaStream_t stream) {
             a.ln_gamma, a.ln_beta, a.ln_out, a.ln_ld, a.ln_seg, a.ln_counters, a.ln_epoch, tiles_m, tiles_n, a.bf16,
             a.nbatch, a.nb2, static_cast<int>(a.a_brows), static_cast<int>(a.b_brows), a.out_b1, a.out_b2, a.alpha};
   const int smem = stages * stage_bytes + 1024;
-  int dev = 0, sms = 0;
+  // per device, once: SM count and the kernel's shared-memory opt-in (the backward pass makes ~1000 GEMM launches per
+  // step: three runtime calls per launch were a visible share of the host's enqueue time)
+  int dev = 0;
   HN_CHECK_CUDA(cudaGetDevice(&dev));
-  HN_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  // per device and cheap: set on every launch so a process driving several GPUs never misses it
-  HN_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, BK, CN, SHARE_A>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     SMEM_BUDGET + 1024));
+  static int sms_of[64] = {0};
+  static bool attr_set[64] = {false};   // (per template instantiation)
+  const int slot = dev & 63;
+  if (sms_of[slot] == 0) HN_CHECK_CUDA(cudaDeviceGetAttribute(&sms_of[slot], cudaDevAttrMultiProcessorCount, dev));
+  const int sms = sms_of[slot];
+  if (!attr_set[slot]) {
+    HN_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, BK, CN, SHARE_A>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       SMEM_BUDGET + 1024));
+    attr_set[slot] = true;
+  }
   const long n_super = static_cast<long>(tiles_m) * tiles_n * a.nbatch / CN;  // the caller guarantees divisibility
   const long max_clusters = sms / CN;
   const unsigned grid = static_cast<unsigned>((n_super < max_clusters ? n_super : max_clusters) * CN);

@@ -734,7 +734,14 @@ class HealNet(nn.Module):
             raise RuntimeError("only the most recent training-mode forward of a HealNet module can be back-propagated "
                                "(one tape per native handle); call backward() before the next forward()")
         dev, batch, params = state["dev"], state["batch"], state["params"]
-        grads = {id(p): torch.zeros(p.shape, device=dev, dtype=torch.float32) for p in params}
+        # one zero-filled buffer for all gradients (one launch instead of one per parameter), 64-byte aligned views
+        offs, total = {}, 0
+        for p in params:
+            if id(p) not in offs:
+                offs[id(p)] = total
+                total += (p.numel() + 15) // 16 * 16
+        flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        grads = {id(p): flat[offs[id(p)]:offs[id(p)] + p.numel()].view(p.shape) for p in params}
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             for layer, slot, ps in self._slot_params():
