@@ -79,7 +79,7 @@ def flops_per_sample(kwargs, shapes) -> float:
 
 def load_traffic():
     """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/), or None."""
-    for name in ("r2_attn_small_kernel_summary.json", "r1_final_attn_small_kernel_summary.json"):
+    for name in ("r2b_attn_small_kernel_summary.json", "r2_attn_small_kernel_summary.json", "r1_final_attn_small_kernel_summary.json"):
         try:
             return float(json.load(open(os.path.join(ROOT, "profiles", name)))["dram_bytes_per_launch"])
         except (OSError, KeyError, ValueError):
