@@ -125,6 +125,10 @@ struct GemmArgs {
   int nbatch = 1, nb2 = 1;
   long a_brows = 0, b_brows = 0, out_b1 = 0, out_b2 = 0;
   float alpha = 1.f;  // out (+)= alpha * A B^T (+ bias)
+  // EPI_F16 with split output: output columns >= hi_only_from (a multiple of the N tile) are formed from the hi parts of
+  // both operands only (one product instead of `terms`) and stored without their lo part — the V half of the K/V
+  // projection of a long token axis, which the attention contracts as fp16 hi anyway (AttnArgs::v_hi_only).
+  int hi_only_from = 0x7fffffff;
 };
 int launch_gemm(const GemmArgs& a, cudaStream_t stream);
 // can this residual GEMM also emit the next LayerNorm (GemmArgs::ln_*)? (shape / alignment rules, HN_GEMM_LN switch)
@@ -193,6 +197,10 @@ struct AttnArgs {
   // softmax does not average away (tests/test_gpu_fullsize.py), so the forward always runs precise.
   int precise = 0;
   int q_lo_off = 0, kv_lo_off = 0;
+  // precise generic path on a LONG token axis: contract P with the hi parts of V only (a convex combination of fp16
+  // values: rounding stays below 2^-11 relative and averages over the tokens — what the small-context path does with
+  // z); short axes (N <= 2048: few tokens, no averaging) keep P.Vh + P.Vl
+  int v_hi_only = 0;
   int c_ones = 0;        // shared_kv only: index of the 1.0 column of z (= context width C)
   // shared_kv + precise, kd 32, 17 <= C <= 23: the lo half of every z row also carries the HI parts of columns 16..C-1
   // in its columns C+1.. (written by launch_build_z_small): the kernel then folds the second 16-column step of both

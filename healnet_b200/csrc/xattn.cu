@@ -44,6 +44,7 @@ struct AttnDev {
   long N;
   int k_col0, v_col0;
   int q_lo_off, kv_lo_off;  // precise mode: column offsets of the lo parts
+  int v_lo;                 // precise mode: also contract P with the lo parts of V (short token axes)
   const uint64_t* mask_bits;
   float* part_acc;
   float* part_ml;
@@ -146,7 +147,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       for (int i = 0; i < n; ++i) {
         const int s = i % NSTAGE;
         mbar_wait(&kv_empty[s], ((i / NSTAGE) & 1) ^ 1);
-        mbar_arrive_expect_tx(&kv_full[s], STAGE_BYTES);
+        mbar_arrive_expect_tx(&kv_full[s], (PREC && !p.v_lo) ? STAGE_BYTES - NA * K_BYTES : STAGE_BYTES);
         const int tok0 = (t_begin + i) * BT;
         uint8_t* st = sKV + s * STAGE_BYTES;
 #pragma unroll
@@ -155,7 +156,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
           if (!SHARED) tma_load_3d(st + (NA + a) * K_BYTES, &tmKV, &kv_full[s], vcol + a * KD, tok0, b);
           if (PREC) {
             tma_load_3d(st + (2 * NA + a) * K_BYTES, &tmKV, &kv_full[s], p.kv_lo_off + kcol + a * KD, tok0, b);
-            tma_load_3d(st + (3 * NA + a) * K_BYTES, &tmKV, &kv_full[s], p.kv_lo_off + vcol + a * KD, tok0, b);
+            if (p.v_lo) tma_load_3d(st + (3 * NA + a) * K_BYTES, &tmKV, &kv_full[s], p.kv_lo_off + vcol + a * KD, tok0, b);
           }
         }
       }
@@ -204,7 +205,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
           for (int k = 0; k < BT / 16; ++k)
             umma_ts(tU + a * KD, tP0 + (i & 1) * 32 + k * 8, smem_desc(v0 + a * K_BYTES + k * V_KADV, 16, SBO, LAYOUT),
                     idesc_u, (i | k) != 0);
-          if (PREC) {
+          if (PREC && p.v_lo) {
 #pragma unroll
             for (int k = 0; k < BT / 16; ++k)  // P . V_lo
               umma_ts(tU + a * KD, tP0 + (i & 1) * 32 + k * 8,
@@ -364,6 +365,7 @@ int launch_t(const AttnArgs& a, cudaStream_t stream) {
   p.v_col0 = a.v_col0;
   p.q_lo_off = a.q_lo_off;
   p.kv_lo_off = a.kv_lo_off;
+  p.v_lo = a.v_hi_only ? 0 : 1;
   p.mask_bits = a.mask_bits;
   p.part_acc = a.part_acc;
   p.part_ml = a.part_ml;
