@@ -323,10 +323,12 @@ def run_reference_arm(args):
     line = dict(metric=METRIC, value=v, unit="samples/s", n_gpus=args.gpus, steps=steps, warmup=1,
                 ms_per_step=total / steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f32", data="synthetic", impl="reference",
-                config=_config(args.workload, kwargs, shapes, per_gpu, per_gpu, "cpu: one sample per counted step"),
+                config=_config(args.workload, kwargs, shapes, per_gpu, per_gpu * max(args.gpus, 1),
+                               "cpu: one sample per counted step"),
                 cpu_baseline=dict(value=v, unit="samples/s", cores=threads, kind=kind, sample=sample),
                 e2e=dict(value=v, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0, samples_per_step=1, step_times_s=[round(t, 3) for t in times])
+    line["config"].update(operands="fp32 (torch CPU ops)", l2="host memory (no GPU involved)")   # same keys as the GPU arm
     if unmodified is not None:
         line["reference_unmodified"] = unmodified
     if note:
