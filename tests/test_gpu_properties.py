@@ -53,3 +53,30 @@ def test_batch_independence_cfg1_full_size():
     assert bool(torch.isfinite(full).all())
     for i in range(2):
         torch.testing.assert_close(m([t[i:i + 1] for t in xs]), full[i:i + 1], rtol=1e-3, atol=1e-4)
+
+
+def test_pinned_host_inputs_in_flight_match_device_inputs():
+    """Serving loop on pinned HOST inputs: several forwards in flight (the module stages each call's inputs in one of
+    `host_staging_depth` persistent device buffer sets, copied on a side stream that waits only for the forward that
+    last read the set). Every call must see ITS inputs: results equal the forwards of the same tensors passed as device
+    tensors, bit for bit, also when the queue is deeper than the ring and when shapes change between calls."""
+    torch.manual_seed(0)
+    kw = dict(n_modalities=3, channel_dims=[200, 3, 3], num_spatial_axes=[1, 2, 3], out_dims=4, l_c=128, l_d=128, depth=2)
+    m = HealNet(**kw).eval().cuda()
+    g = torch.Generator().manual_seed(1)
+
+    def batch(b, vol):
+        return [torch.rand(b, 1, 200, generator=g).pin_memory(), torch.rand(b, 64, 64, 3, generator=g).pin_memory(),
+                torch.rand((b,) + vol + (3,), generator=g).pin_memory()]
+
+    calls = [batch(2, (4, 48, 48)) for _ in range(7)] + [batch(3, (3, 40, 56))] + [batch(2, (4, 48, 48)) for _ in range(3)]
+    with torch.no_grad():
+        want = [m([t.cuda() for t in xs]).clone() for xs in calls]
+        torch.cuda.synchronize()
+        m.keep_output_on_device = True
+        got = [m(list(xs)) for xs in calls]          # all enqueued back to back, nothing read in between
+        torch.cuda.synchronize()
+        m.keep_output_on_device = False
+    for i, (a, b) in enumerate(zip(got, want)):
+        assert torch.equal(a, b), f"call {i}: host-staged forward differs from the device-input forward"
+    assert len(m._stage_ring) == m.host_staging_depth
