@@ -1239,6 +1239,12 @@ int launch_small_attention_bwd(const SmallBwdTcArgs& a, cudaStream_t stream) {
 // Split the token axis so that the grid is a whole number of waves of one CTA per SM while each CTA still
 // streams enough tiles to amortise its prologue / epilogue.
 int small_attention_pick_nsplit(int batch, int L, int H, long N, int kd) {
+#ifdef HN_DEBUG
+  {  // tuning knob of debug builds: force the number of token splits of long axes
+    static const char* e = getenv("HN_SMALL_NSPLIT");
+    if (e != nullptr && atoi(e) > 0 && N > 100000) return atoi(e);
+  }
+#endif
   const int G = small_attention_groups(kd);
   const long n_rb = static_cast<long>((L + BM - 1) / BM) * H;
   const long base = ((n_rb + G - 1) / G) * batch;
