@@ -13,20 +13,25 @@
 //     SAME z tiles: 4 softmax warps per row block -> 12 softmax warps per SM, 3 per scheduler, so that one
 //     group's TMEM / mbarrier latency is covered by the others; the z tile is fetched once per G row blocks;
 //   * S is double-buffered in TMEM (P(i) is written over the first half of S(i), which frees the columns for a
-//     second S buffer): S(i+1) is complete long before the softmax of tile i ends, so no tensor-pipe latency
-//     sits on the critical path;
-//   * softmax threads own one latent row (one TMEM lane) and work in 32-column chunks (S -> P in place of
-//     registers, ~80 regs/thread);
-//   * half of the exponentials are evaluated on the FMA / ALU pipes, two at a time in half2 arithmetic (Cody-Waite
-//     range reduction + degree-3 minimax polynomial + integer exponent insert, 12 instructions per column pair
-//     incl. the fp16 pack) so MUFU only sees the rest (pipe microbenchmark: 23 elem/clk/SM for a 3/8 fp32
-//     mix vs 16 for MUFU alone, tools/microbench/mb_pipes.cu; HN_POLY_MODE sweeps the share; 1/2 measured best once the
-//     per-tile bookkeeping was taken off the serial path, tools/microbench/mb_softmax.cu gives the no-sync bound);
+//     second S buffer), so S(i+1) is computed while the softmax of tile i runs;
+//   * softmax threads own one latent row (one TMEM lane) and work in 16-column chunks (four 16-register TMEM loads,
+//     four 8-register stores per tile);
+//   * half of the exponentials are evaluated on the FMA / ALU pipes, two at a time in half2 arithmetic (range
+//     reduction with the magic-constant trick + degree-3 minimax polynomial + integer exponent insert, ~10 issue slots
+//     per column pair incl. the fp16 pack: ex2_pair_h2_lean) so MUFU only sees the rest (pipe microbenchmark: 23
+//     elem/clk/SM for a 3/8 fp32 mix vs 16 for MUFU alone, tools/microbench/mb_pipes.cu; HN_POLY_MODE sweeps the share in
+//     debug builds; 1/2 measured best, also on the round-2 kernel);
 //   * the running max is a lazily raised reference: the steady state does no max pass at all — it only tracks
-//     the max of the packed fp16 P words (VIMNMX3.U16x2, a quarter of an instruction per element) and falls
-//     back to the exact two-pass path when a P exceeds 2^8 (or on the first / a masked / the ragged last tile);
+//     the max of the packed fp16 P words of the MUFU lanes (VIMNMX3.U16x2) and the OR of the polynomial lanes' t words,
+//     and falls back to the exact two-pass path when a P exceeds 2^15 (or on the first / a masked / the ragged last tile);
 //   * the "- max" of the softmax costs nothing: Q' carries -m_ref (fp16) in the column where z holds its 1.0,
-//     so the S UMMA delivers q.z - m_ref directly; the owning thread rewrites that smem element on the rare raise.
+//     so the S UMMA delivers q.z - m_ref directly; the owning thread rewrites that smem element on the rare raise;
+//   * what bounds it (ncu, profiles/r2b_*): no single pipe (issue 73 %, tensor-core instruction pipe 77 %, XU 56 %) but
+//     the chain  P(i) published -> issuer wakes -> PV(i), S(i+2) on a busy tensor pipe -> softmax wakes.  Everything
+//     that can leave that chain has: the mid-tile barrier test is non-blocking and pinned late (a hoisted blocking
+//     try_wait held P(i) back until S(i+1) had landed), the issuer fetches its descriptors and waits for tile i+2's
+//     context rows BEFORE it waits for P(i), and the score product only issues the 16-column steps that hold context
+//     columns (merged tail for 17 <= C <= 23).
 // Warp roles: warps 0..4G-1 = softmax groups (4 warps each); warps 4G..5G-1 = one UMMA issuer warp per group
 // (S = Q'.z^T (SS) ; U += P.z (TS, P from TMEM)), each blocking on its own group's barrier — a single issuer
 // polling several groups' mbarriers (~150 clk per test) starved the groups, and letting a softmax warp issue
@@ -37,8 +42,9 @@
 // [hi (KD) | lo (KD)] — and S = Q'h.zh + Q'l.zh + Q'h.zl (three K blocks into the same TMEM accumulator). With single
 // fp16 operands the score error grows like |s| * 2^-11 and does not average out once the softmax is peaked (measured at
 // the full cfg 1 volume with to_q scaled x8 / x32: latent error 1e-3 / 9e-3, tests/test_gpu_fullsize.py); the split
-// makes the scores fp32-exact for two extra 32-clk UMMAs per tile on a tensor pipe that was 26 % busy. P.z (the value
-// side) keeps the hi part only: it is a convex combination whose fp16 rounding stays below 2^-11 relative.
+// makes the scores fp32-exact for up to four extra UMMAs per tile (two at the volume's C = 18 with the merged tail, none
+// beyond the three terms' single steps at the image's C = 13). P.z (the value side) keeps the hi part only: it is a
+// convex combination whose fp16 rounding stays below 2^-11 relative.
 #include <cstdlib>
 #include <type_traits>
 
