@@ -162,7 +162,9 @@ __device__ __forceinline__ uint32_t ex2_pair_h2(float x0, float x1) {
 // Leaner form of the same polynomial for the steady-state path (10 issue slots per pair instead of 13):
 //   * only the LOWER clamp is applied, at -16, as one unsigned integer min on the fp16 bit patterns (negative halves
 //     order by magnitude: min.u16 with bits(-16) clamps them, positive ones pass). rint(x) = -16 already flushes
-//     to an exact zero below (exponent field 15 - 16 < 0);
+//     to an exact zero below (exponent field 15 - 16 < 0); for -15.5 < x < -14 the field is 0 and the lane reads as a
+//     subnormal — a weight below 2^-24 of the reference, under-estimated by up to 40 %, never over-estimated
+//     (tests/test_exp2_lane_model.py models the whole sequence on the CPU, exhaustively over the fp16 inputs);
 //   * the magic constant is 1536 + 16, so t = 1552 + rint(x) has the bit pattern 0x6600 + n', n' = rint(x) + 16 in
 //     [0, 31] for every admissible x: the exponent insert is then ONE 32-bit multiply-add (t * 1024 + p: no carry can
 //     cross the lanes, and what the low lane's constant bits push into the high lane is the constant 0x198) followed by
