@@ -265,8 +265,8 @@ __global__ void __launch_bounds__(256) build_z_small32_fast_kernel(const T* __re
   HN_PDL_WAIT();
   constexpr int F = 5, ZW = 32, C = CRAW + NAX * F;
   static_assert(C < ZW, "context row must leave room for the ones column");
-  const long t = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (t >= tokens_total) return;
+  const long t_raw = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long t = t_raw < tokens_total ? t_raw : tokens_total - 1;   // (tail threads recompute the last row: all reach the barrier)
   unsigned rem = (tokens_total < (1L << 31))
                      ? static_cast<unsigned>(t) % static_cast<unsigned>(N) + static_cast<unsigned>(tok0)
                      : static_cast<unsigned>(t % N + tok0);
@@ -294,21 +294,48 @@ __global__ void __launch_bounds__(256) build_z_small32_fast_kernel(const T* __re
     q += d * d;
   }
   const float rstd = rsqrtf(q / C + LN_EPS);
-  uint4* dst = reinterpret_cast<uint4*>(z + t * (split ? 2 * ZW : ZW));
+  // the row as packed fp16 words: hi half, and (split) lo half = fp16(value - hi), with the merged tail (17 <= C <= 23:
+  // the hi parts of columns 16..C-1 again behind the lo half's zero column C, see xattn_small.cu)
+  uint32_t hw[ZW / 2], lw[ZW / 2];
 #pragma unroll
-  for (int g = 0; g < ZW / 8; ++g) {
-    float o[8];
+  for (int k = 0; k < ZW / 2; ++k) {
+    float o[2], l[2];
+    __half hh[2];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int i = g * 8 + j;
-      o[j] = i < C ? (v[i < C ? i : 0] - mean) * rstd : (i == C ? 1.f : 0.f);
+    for (int e = 0; e < 2; ++e) {
+      const int i = 2 * k + e;
+      o[e] = i < C ? (v[i < C ? i : 0] - mean) * rstd : (i == C ? 1.f : 0.f);
+      hh[e] = __float2half_rn(o[e]);
+      l[e] = o[e] - __half2float(hh[e]);
+      if (C >= 17 && C <= 23 && i > C && i <= 2 * C - 16) l[e] = (v[(i - C - 1 + 16) < C ? (i - C - 1 + 16) : 0] - mean) * rstd;
     }
-    store_hi_lo8(dst + g, split ? dst + ZW / 8 + g : nullptr, o);
+    const __half2 h2 = __halves2half2(hh[0], hh[1]);
+    const __half2 l2 = __floats2half2_rn(l[0], l[1]);
+    hw[k] = *reinterpret_cast<const uint32_t*>(&h2);
+    lw[k] = *reinterpret_cast<const uint32_t*>(&l2);
   }
-  if (split && C >= 17 && C <= 23) {  // merged tail (see build_z_small_kernel)
-    __half* lo = z + t * 2 * ZW + ZW;
+  // Coalesced stores: a thread's row is 64 (128) contiguous bytes, so direct 16-byte stores touch 32 different lines per
+  // warp instruction; the block's rows are contiguous in z, so they go through shared memory (16-byte chunks XOR-swizzled
+  // by the row index: the minimum of four wavefronts per 512-byte warp access on both sides) and leave as 512-byte warp stores.
+  constexpr int CH = ZW / 8;                       // 16-byte chunks per half
+  const int nch = split ? 2 * CH : CH;              // chunks per row
+  __shared__ uint4 stage[256 * 2 * CH];
+  {
+    const int r = threadIdx.x;
 #pragma unroll
-    for (int i = 16; i < C; ++i) lo[C + 1 + i - 16] = __float2half_rn((v[i < C ? i : 0] - mean) * rstd);
+    for (int c = 0; c < CH; ++c) {
+      stage[r * nch + (c ^ (r & (nch - 1)))] = make_uint4(hw[4 * c], hw[4 * c + 1], hw[4 * c + 2], hw[4 * c + 3]);
+      if (split)
+        stage[r * nch + ((CH + c) ^ (r & (nch - 1)))] = make_uint4(lw[4 * c], lw[4 * c + 1], lw[4 * c + 2], lw[4 * c + 3]);
+    }
+  }
+  __syncthreads();
+  const long row0 = static_cast<long>(blockIdx.x) * blockDim.x;
+  const long rows_here = tokens_total - row0 < 256 ? tokens_total - row0 : 256;
+  uint4* dst = reinterpret_cast<uint4*>(z) + row0 * nch;
+  for (int idx = threadIdx.x; idx < rows_here * nch; idx += 256) {
+    const int r = idx / nch, c = idx - r * nch;
+    dst[idx] = stage[r * nch + (c ^ (r & (nch - 1)))];
   }
 }
 
