@@ -259,15 +259,6 @@ int ln_backward(const float* x_in, const float* dxn, const float* gamma, float* 
   return 0;
 }
 
-// C[M][N] (+)= A[M][K] B[N][K]^T on tcgen05 from bf16 hi/lo rows packed by launch_pack_bf16 (three-term product)
-int tc_gemm(cudaStream_t st, const void* A, int segA, const void* B, int segB, int M, int N, int K, float* out, int ldo,
-            bool accumulate) {
-  GemmArgs g{static_cast<const __half*>(A), static_cast<const __half*>(B), M, N, K, 2 * segA, 2 * segB,
-             accumulate ? EPI_RES : EPI_F32, 0, nullptr, out, ldo, 3, segA, segB, 0};
-  g.bf16 = 1;
-  return launch_gemm(g, st);
-}
-
 // C[b1][b2][m][n] (+)= alpha * sum_k A(m, k) B(k, n) — the contraction of sg() above — on tcgen05: both operands are
 // packed to bf16 hi/lo rows with the contraction index contiguous (three-term products: 16 significant bits, fp32
 // range), batches stacked along the rows, one batched GEMM launch. Small products, operands that do not fit the
@@ -300,38 +291,26 @@ int mm(const hn_handle* h, BwdScratch& s, cudaStream_t st, int M, int N, int K, 
   return launch_gemm(g, st);
 }
 
-// Feed-forward backward with every contraction on tensor cores: gradient operands as bf16 hi/lo pairs (16 significant
-// bits, fp32 range; three-term products), the recomputed pre-activations through the forward's own fp16-split GEMM.
+// Feed-forward backward with every contraction on tensor cores (mm(): bf16 hi/lo operands, three-term products), the
+// recomputed pre-activations through the forward's own fp16-split GEMM.
 int ff_backward_tc(hn_handle* h, const BlockRec& rec, const std::vector<const float*>& wf, const std::vector<float*>& gf,
                    const FFPacked& fp, const char* tape, long rows, BwdScratch& s, cudaStream_t st) {
   const hn_desc& d = h->d;
   const int D = d.l_d, F = 4 * D, sD = h->segD, s4 = h->seg4D;
-  const int R = static_cast<int>(rows), sR = static_cast<int>(round_up_l(rows, 64)), s8 = round_up(2 * F, 64);
+  const int R = static_cast<int>(rows);
   const float* x_in = reinterpret_cast<const float*>(tape + rec.x_in);
   const __half* xn = reinterpret_cast<const __half*>(tape + rec.xn);
   const __half* hid = reinterpret_cast<const __half*>(tape + rec.o);
   BW(launch_colsum(0, s.dx, D, nullptr, 0, nullptr, rows, D, 1.f, gf[5], 1, s.colpart, st));
-  // dW2 += dx^T hid
-  BW(launch_pack_bf16(s.dx, 0, D, 0, rows, D, s.pA, sR, 1, st));
-  BW(launch_pack_bf16(hid, 1, 2 * s4, s4, rows, F, s.pB, sR, 1, st));
-  BW(tc_gemm(st, s.pA, sR, s.pB, sR, D, F, R, gf[4], F, true));
-  // dhid = dx W2
-  BW(launch_pack_bf16(s.dx, 0, D, 0, rows, D, s.pA, sD, 0, st));
-  BW(launch_pack_bf16(wf[4], 0, F, 0, D, F, s.pB, sD, 1, st));
-  BW(tc_gemm(st, s.pA, sD, s.pB, sD, R, F, D, s.dhid, F, false));
+  BW(mm(h, s, st, D, F, R, F32(s.dx, 1, D), H16(hid, s4, 2 * s4, 1), gf[4], F, 1.f, 1));            // dW2 += dx^T hid
+  BW(mm(h, s, st, R, F, D, F32(s.dx, D, 1), F32(wf[4], F, 1), s.dhid, F));                           // dhid = dx W2
   // [a | g] (interleaved, bias included) = LN(x) W1^T + b1 through the forward's GEMM
   GemmArgs g1{xn, fp.W1, R, 2 * F, D, 2 * sD, 2 * sD, EPI_F32, 0, fp.b1, s.hbuf, 2 * F, 3, sD, sD, 0};
   BW(launch_gemm(g1, st));
   BW(launch_gate_bwd_il(s.hbuf, s.dhid, s.dh2, rows, F, d.snn, st));
   BW(launch_colsum(0, s.dh2, 2 * F, nullptr, 0, nullptr, rows, 2 * F, 1.f, gf[3], 1, s.colpart, st));
-  // dW1 += dh^T xn
-  BW(launch_pack_bf16(s.dh2, 0, 2 * F, 0, rows, 2 * F, s.pA, sR, 1, st));
-  BW(launch_pack_bf16(xn, 1, 2 * sD, sD, rows, D, s.pB, sR, 1, st));
-  BW(tc_gemm(st, s.pA, sR, s.pB, sR, 2 * F, D, R, gf[2], D, true));
-  // dxn = dh W1
-  BW(launch_pack_bf16(s.dh2, 0, 2 * F, 0, rows, 2 * F, s.pA, s8, 0, st));
-  BW(launch_pack_bf16(wf[2], 0, D, 0, 2 * F, D, s.pB, s8, 1, st));
-  BW(tc_gemm(st, s.pA, s8, s.pB, s8, R, D, 2 * F, s.dxn, D, false));
+  BW(mm(h, s, st, 2 * F, D, R, F32(s.dh2, 1, 2 * F), H16(xn, sD, 2 * sD, 1), gf[2], D, 1.f, 1));    // dW1 += dh^T xn
+  BW(mm(h, s, st, R, D, 2 * F, F32(s.dh2, 2 * F, 1), F32(wf[2], D, 1), s.dxn, D));                   // dxn = dh W1
   return ln_backward(x_in, s.dxn, wf[0], gf[0], gf[1], rows, D, s, st);
 }
 

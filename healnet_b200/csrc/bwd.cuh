@@ -34,10 +34,8 @@ int launch_scale_cols(const float* in, const float* gamma, float scale, int C, l
 int launch_kv_fold_bwd(const float* dWp, const float* W, const float* gamma, const float* beta, const float* sv,
                        int rows2I, int I, int C, float* gW, float* ggamma, float* gbeta, cudaStream_t st);
 
-// bf16 hi/lo operand rows for the tensor-core GEMMs of the backward: dst [rows][2 seg] (transpose: [C][2 seg], seg >= R),
-// src fp32 (src_half = 0) or split fp16 (src_half = 1, lo at + lo_off)
-int launch_pack_bf16(const void* src, int src_half, long ld_src, int lo_off, long R, int C, void* dst, int seg,
-                     int transpose, cudaStream_t st);
+// bf16 hi/lo operand rows for the tensor-core GEMMs of the backward (hi = bf16(v), lo = bf16(v - hi): 16 significant
+// bits with fp32's exponent range)
 // general strided / batched form, both operands of one product in ONE launch: dst[(z R + r) 2 seg + c] = hi | lo of
 // p[b1 s_b1 + b2 s_b2 + r s_row + c s_col] (z = b1 nb2 + b2; type 0 = fp32, 1 = split fp16 with the lo part at
 // + lo_off), c < K, pad columns zero. The operands are given as (rows, contraction index) views.

@@ -515,8 +515,7 @@ __global__ void sum_splits_kernel(const float* __restrict__ part, int nsplit, lo
 
 // ------------------------------------------------------------------ bf16 hi/lo operand packing for the backward GEMMs
 // dst rows = [hi (seg cols) | lo (seg cols)], hi = bf16(v), lo = bf16(v - hi) (16 significant bits, fp32 range), pad
-// columns zero. src: fp32 (lo_off == 0) or the forward's split fp16 rows (value = hi + lo at + lo_off).
-// TRANSPOSE: dst[c][r] = src[r][c] (the weight-gradient products contract over the row axis).
+// columns zero. src: fp32 (type 0) or the forward's split fp16 rows (type 1: value = hi + lo at + lo_off).
 __device__ __forceinline__ float ld_src(const void* src, int src_half, long idx, int lo_off) {
   if (!src_half) return static_cast<const float*>(src)[idx];
   const __half* hp = static_cast<const __half*>(src);
@@ -527,40 +526,7 @@ __device__ __forceinline__ void st_bf16_split(__nv_bfloat16* dst, long idx, int 
   dst[idx] = hi;
   dst[idx + seg] = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
-__global__ void pack_bf16_kernel(const void* __restrict__ src, int src_half, long ld_src_, int lo_off, long R, int C,
-                                 __nv_bfloat16* __restrict__ dst, int seg) {
-  HN_PDL_LAUNCH();
-  HN_PDL_WAIT();
-  const long n = R * seg;
-  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) {
-    const long r = i / seg;
-    const int c = static_cast<int>(i - r * seg);
-    st_bf16_split(dst, r * 2 * seg + c, seg, c < C ? ld_src(src, src_half, r * ld_src_ + c, lo_off) : 0.f);
-  }
-}
-// 32 x 32 tiles through shared memory: coalesced reads along c, coalesced writes along r
-__global__ void __launch_bounds__(256) pack_bf16_t_kernel(const void* __restrict__ src, int src_half, long ld_src_,
-                                                          int lo_off, long R, int C, __nv_bfloat16* __restrict__ dst,
-                                                          int seg /* >= R */) {
-  HN_PDL_LAUNCH();
-  HN_PDL_WAIT();
-  __shared__ float tile[32][33];
-  const long r0 = static_cast<long>(blockIdx.x) * 32;
-  const int c0 = blockIdx.y * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int j = ty; j < 32; j += 8) {
-    const long r = r0 + j;
-    const int c = c0 + tx;
-    tile[j][tx] = (r < R && c < C) ? ld_src(src, src_half, r * ld_src_ + c, lo_off) : 0.f;
-  }
-  __syncthreads();
-  for (int j = ty; j < 32; j += 8) {
-    const int c = c0 + j;
-    const long r = r0 + tx;
-    if (c < C && r < seg) st_bf16_split(dst, static_cast<long>(c) * 2 * seg + r, seg, tile[tx][j]);
-  }
-}
-// General form for the strided, batched products of the attention blocks: dst[(z R + r) 2 seg + c] = hi, [+ seg] = lo
+// Strided, batched operands of every backward product: dst[(z R + r) 2 seg + c] = hi, [+ seg] = lo
 // of src(z, r, c) = p[b1 s_b1 + b2 s_b2 + r s_r + c s_c], z = b1 nb2 + b2; columns [C, seg) zero. 32 x 32 tiles:
 // read along whichever of (r, c) is contiguous in the source, always write along c.
 struct PackSrc {
@@ -805,21 +771,6 @@ int launch_kv_fold_bwd(const float* dWp, const float* W, const float* gamma, con
                        int rows2I, int I, int C, float* gW, float* ggamma, float* gbeta, cudaStream_t st) {
   HN_CHECK_CUDA(launch_k(kv_fold_bwd_kernel, dim3((C + 31) / 32), dim3(256), 0, st, dWp, W, gamma, beta, sv, rows2I, I, C, gW,
                          ggamma, gbeta));
-  HN_CHECK_CUDA(cudaGetLastError());
-  return 0;
-}
-int launch_pack_bf16(const void* src, int src_half, long ld_src, int lo_off, long R, int C, void* dst, int seg,
-                     int transpose, cudaStream_t st) {
-  __nv_bfloat16* d = static_cast<__nv_bfloat16*>(dst);
-  if (!transpose) {
-    HN_REQUIRE(seg >= C, "pack_bf16: segment narrower than the row");
-    HN_CHECK_CUDA(launch_k(pack_bf16_kernel, dim3(ew_grid(R * seg)), dim3(256), 0, st, src, src_half, ld_src, lo_off, R, C, d, seg));
-  } else {
-    HN_REQUIRE(seg >= R, "pack_bf16: segment shorter than the column");
-    // the pad columns [R, seg) of every output row must be zero: the tile loop writes them (r < seg) from zeros
-    const dim3 grid(static_cast<unsigned>((seg + 31) / 32), static_cast<unsigned>((C + 31) / 32));
-    HN_CHECK_CUDA(launch_k(pack_bf16_t_kernel, grid, dim3(256), 0, st, src, src_half, ld_src, lo_off, R, C, d, seg));
-  }
   HN_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
