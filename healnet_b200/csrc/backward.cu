@@ -572,6 +572,7 @@ int hn_backward(hn_handle* h, const float* grad_latents, const float* grad_logit
         ta.L = L;
         ta.nsplit = small_attention_pick_nsplit(batch, L, H, mp.Nl, zw);
         ta.N = mp.Nl;
+        ta.C = C;
         BW(launch_small_attention_bwd(ta, st));
         BW(launch_small_bwd_finish(s.dr_part, s.row_s, batch, ta.nsplit, H, L, C, zw, s.dr, st));
       } else {

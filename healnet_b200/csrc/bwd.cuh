@@ -74,6 +74,7 @@ struct SmallBwdTcArgs {
   float* part;
   int batch, H, L, nsplit;
   long N;
+  int C = 63;           // context width: products only run over the 16-column steps that hold context columns
 };
 int launch_small_attention_bwd(const SmallBwdTcArgs& a, cudaStream_t stream);
 // r / du / delta / stats -> the kernel's operands (R, DU split rows, per-row factors); scale[R] = the power of two DU was

@@ -916,6 +916,8 @@ attn_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 struct SmallBwdDev {
   int L, H, batch, nsplit, n_ltiles, n_rb, ctas_per_stream, tiles_total;
   int lo_off;           // column offset of the lo parts inside R / DU rows
+  int mode;             // KD 32: 0 = C <= 15 (every product fits one 16-column step), 1 = C == 16 (only R_hi.z_hi, which
+                        // carries the fold column, needs the second step), else all steps
   long N;
   const uint64_t* mask_bits;
   const float* row_a;   // [(b*L + l)*H + h]  2^-P_SHIFT / den
@@ -947,6 +949,9 @@ attn_small_bwd_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_cons
   __shared__ uint64_t q_full, z_full[NST], z_empty[NST];
   __shared__ uint64_t sg_full[MAXG], p_ready[MAXG], acc_done[MAXG];
   __shared__ uint32_t tmem_base_s;
+  // UMMA descriptors of the context-row ring (as in the forward kernel): [0..3] the dt.z operand of the four 16-token
+  // steps, [4..7] z_hi k0, z_hi k1, z_lo k0, z_lo k1; read with volatile loads before the issuer's wait for dt(i)
+  __shared__ __align__(16) uint64_t z_desc[NST][8];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int idx = blockIdx.x;
@@ -984,6 +989,16 @@ attn_small_bwd_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_cons
     }
     fence_mbar_init();
   }
+  if (KD == 32 && threadIdx.x >= 32 && threadIdx.x < 32 + NSB) {
+    const int st = threadIdx.x - 32;
+    const uint32_t z0 = smem_u32(sZ + st * Z_STAGE);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) z_desc[st][k] = smem_desc(z0 + k * V_KADV, 16, SBO, LAYOUT);
+    z_desc[st][4] = smem_desc(z0, 16, SBO, LAYOUT);
+    z_desc[st][5] = smem_desc(z0 + 32, 16, SBO, LAYOUT);
+    z_desc[st][6] = smem_desc(z0 + Z_BYTES, 16, SBO, LAYOUT);
+    z_desc[st][7] = smem_desc(z0 + Z_BYTES + 32, 16, SBO, LAYOUT);
+  }
   constexpr int PRODUCER_WARP = 5 * G;
   if (warp == PRODUCER_WARP) tmem_alloc<512>(&tmem_base_s);
   fence_before_sync();
@@ -1020,38 +1035,79 @@ attn_small_bwd_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_cons
     if (g < n_active && elect_one()) {
       const uint32_t tG = tmem + g * GCOLS;
       const uint32_t q0 = smem_u32(sQ + g * Q_GROUP);
-      mbar_wait(&q_full, 0);
-      for (int i = 0; i < n; ++i) {
+      // S' = R_hi.z_hi + R_lo.z_hi + R_hi.z_lo ; G = DU_hi.z_hi + DU_lo.z_hi over the 16-column steps that hold context
+      // columns (KH for the product that carries the fold column, KL for the others), compile-time per mode; dz = the
+      // tile's K-operand descriptors (KD 32: from the table)
+      auto issue_sg_c = [&](uint32_t z0, const uint64_t (&dz)[4], auto kh_c, auto kl_c) {
+        constexpr int KH = decltype(kh_c)::value, KL = decltype(kl_c)::value;
+        auto zh = [&](int k) { return KD == 32 ? dz[k] : smem_desc(z0 + k * 32, 16, SBO, LAYOUT); };
+        auto zl = [&](int k) { return KD == 32 ? dz[2 + k] : smem_desc(z0 + Z_BYTES + k * 32, 16, SBO, LAYOUT); };
+#pragma unroll
+        for (int k = 0; k < KH; ++k) umma_ss(tG, smem_desc(q0 + k * 32, 16, SBO, LAYOUT), zh(k), idesc_s, k != 0);
+#pragma unroll
+        for (int k = 0; k < KL; ++k) umma_ss(tG, smem_desc(q0 + Q_TILE + k * 32, 16, SBO, LAYOUT), zh(k), idesc_s, true);
+#pragma unroll
+        for (int k = 0; k < KL; ++k) umma_ss(tG, smem_desc(q0 + k * 32, 16, SBO, LAYOUT), zl(k), idesc_s, true);
+#pragma unroll
+        for (int k = 0; k < KL; ++k) umma_ss(tG + 64, smem_desc(q0 + 2 * Q_TILE + k * 32, 16, SBO, LAYOUT), zh(k), idesc_s, k != 0);
+#pragma unroll
+        for (int k = 0; k < KL; ++k) umma_ss(tG + 64, smem_desc(q0 + 3 * Q_TILE + k * 32, 16, SBO, LAYOUT), zh(k), idesc_s, true);
+        umma_commit(&sg_full[g]);
+      };
+      using std::integral_constant;
+      const int mode = p.mode;
+      auto issue_sg = [&](uint32_t z0, const uint64_t (&dz)[4]) {
+        constexpr int KF = KD / 16;
+        if (KD == 32) {
+          if (mode == 0) { issue_sg_c(z0, dz, integral_constant<int, 1>{}, integral_constant<int, 1>{}); return; }
+          if (mode == 1) { issue_sg_c(z0, dz, integral_constant<int, 2>{}, integral_constant<int, 1>{}); return; }
+        }
+        issue_sg_c(z0, dz, integral_constant<int, KF>{}, integral_constant<int, KF>{});
+      };
+      auto load_desc4 = [&](int stage, int first, uint64_t (&d)[4]) {
+        const uint32_t a = smem_u32(&z_desc[stage][first]);
+        asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];" : "=l"(d[0]), "=l"(d[1]) : "r"(a));
+        asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];" : "=l"(d[2]), "=l"(d[3]) : "r"(a + 16));
+      };
+      auto z_stage = [&](int i) {  // wait until tile i's context rows have landed; -> their shared address
         const int s = i % NSB;
         mbar_wait(&z_full[s], (i / NSB) & 1);
+        return smem_u32(sZ + s * Z_STAGE);
+      };
+      mbar_wait(&q_full, 0);
+      {
+        const uint32_t za = z_stage(0);
+        uint64_t dz[4] = {0, 0, 0, 0};
+        if (KD == 32) load_desc4(0, 4, dz);
         fence_after_sync();
+        issue_sg(za, dz);
+      }
+      for (int i = 0; i < n; ++i) {
+        // single-buffered S' / G: the softmax warps of this row block idle from the moment they publish dt(i) until
+        // S'(i+1) and G(i+1) are complete, so everything that does not depend on dt(i) happens BEFORE the wait for it
+        // (the dt.z descriptors, the arrival of tile i+1's context rows and their descriptors). The tensor pipe executes
+        // in issue order: dt(i).z has consumed S' columns 0..31 before S'(i+1) overwrites them.
+        const int s = i % NSB;
         const uint32_t z0 = smem_u32(sZ + s * Z_STAGE);
-        // S' = R_hi.z_hi + R_lo.z_hi + R_hi.z_lo ; G = DU_hi.z_hi + DU_lo.z_hi   (tensor pipe executes in issue order:
-        // the previous tile's dt . z has consumed S' columns 0..31 before these overwrite them)
+        uint64_t dv[4], dz[4] = {0, 0, 0, 0};
+        if (KD == 32) {
+          load_desc4(s, 0, dv);
+        } else {
 #pragma unroll
-        for (int k = 0; k < KD / 16; ++k)
-          umma_ss(tG, smem_desc(q0 + k * 32, 16, SBO, LAYOUT), smem_desc(z0 + k * 32, 16, SBO, LAYOUT), idesc_s, k != 0);
-#pragma unroll
-        for (int k = 0; k < KD / 16; ++k)
-          umma_ss(tG, smem_desc(q0 + Q_TILE + k * 32, 16, SBO, LAYOUT), smem_desc(z0 + k * 32, 16, SBO, LAYOUT), idesc_s, true);
-#pragma unroll
-        for (int k = 0; k < KD / 16; ++k)
-          umma_ss(tG, smem_desc(q0 + k * 32, 16, SBO, LAYOUT), smem_desc(z0 + Z_BYTES + k * 32, 16, SBO, LAYOUT), idesc_s, true);
-#pragma unroll
-        for (int k = 0; k < KD / 16; ++k)
-          umma_ss(tG + 64, smem_desc(q0 + 2 * Q_TILE + k * 32, 16, SBO, LAYOUT), smem_desc(z0 + k * 32, 16, SBO, LAYOUT),
-                  idesc_s, k != 0);
-#pragma unroll
-        for (int k = 0; k < KD / 16; ++k)
-          umma_ss(tG + 64, smem_desc(q0 + 3 * Q_TILE + k * 32, 16, SBO, LAYOUT), smem_desc(z0 + k * 32, 16, SBO, LAYOUT),
-                  idesc_s, true);
-        umma_commit(&sg_full[g]);
+          for (int k = 0; k < 4; ++k) dv[k] = smem_desc(z0 + k * V_KADV, 16, SBO, LAYOUT);
+        }
+        const bool more = i + 1 < n;
+        uint32_t z1 = 0;
+        if (more) {
+          z1 = z_stage(i + 1);
+          if (KD == 32) load_desc4((i + 1) % NSB, 4, dz);
+        }
         mbar_wait_sleepy(&p_ready[g], i & 1, 20000);
         fence_after_sync();
 #pragma unroll
-        for (int k = 0; k < BT / 16; ++k)
-          umma_ts(tG + 128, tG + k * 8, smem_desc(z0 + k * V_KADV, 16, SBO, LAYOUT), idesc_u, (i | k) != 0);
+        for (int k = 0; k < BT / 16; ++k) umma_ts(tG + 128, tG + k * 8, dv[k], idesc_u, (i | k) != 0);
         umma_commit(&z_empty[s]);
+        if (more) issue_sg(z1, dz);
         if (i + 1 == n) umma_commit(&acc_done[g]);
       }
     }
@@ -1159,6 +1215,7 @@ int launch_small_bwd_t(const SmallBwdTcArgs& a, cudaStream_t stream) {
   p.ctas_per_stream = (p.n_rb + G - 1) / G;
   p.tiles_total = static_cast<int>((a.N + BT - 1) / BT);
   p.lo_off = a.lo_off;
+  p.mode = a.C <= 15 ? 0 : a.C == 16 ? 1 : 3;
   p.N = a.N;
   p.mask_bits = a.mask_bits;
   p.row_a = a.row_a;
