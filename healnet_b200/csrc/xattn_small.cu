@@ -1132,37 +1132,42 @@ attn_small_bwd_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_cons
         fence_after_sync();
         uint64_t bits = ~0ull;
         if (has_mask) bits = p.mask_bits[static_cast<long>(b) * p.tiles_total + t_begin + i];
-        uint32_t pk[32];
+        // four 16-column chunks (16-register loads, 8-register stores: a 32-register store tuple costs ~30 MOVs per tile,
+        // see the forward kernel); x = S' <= P_SHIFT here (M is the true row max), so the lean polynomial needs no
+        // overflow test
+        uint32_t pk[4][8];
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t s[32], gq[32];
-          tmem_ld32(tL + c * 32, s);
-          tmem_ld32(tL + 64 + c * 32, gq);
+        for (int c = 0; c < 4; ++c) {
+          uint32_t s[16], gq[16];
+          tmem_ld16(tL + c * 16, s);
+          tmem_ld16(tL + 64 + c * 16, gq);
           tmem_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < 8; ++j) {
             const float x0 = __uint_as_float(s[2 * j]), x1 = __uint_as_float(s[2 * j + 1]);
             // w = a (G - delta)
             const float w0 = fmaf(__uint_as_float(gq[2 * j]), a_l, ad), w1 = fmaf(__uint_as_float(gq[2 * j + 1]), a_l, ad);
             if (j & 1) {  // half2 polynomial exponentials, product in half2
-              const uint32_t e = ex2_pair_h2(x0, x1);
+              uint32_t tb;
+              const uint32_t e = ex2_pair_h2_lean(x0, x1, tb);
               const __half2 wh = __floats2half2_rn(w0, w1);
               const __half2 r = __hmul2(*reinterpret_cast<const __half2*>(&e), wh);
-              pk[c * 16 + j] = *reinterpret_cast<const uint32_t*>(&r);
+              pk[c][j] = *reinterpret_cast<const uint32_t*>(&r);
             } else {
-              pk[c * 16 + j] = pack_half2(ex2_mufu(x0) * w0, ex2_mufu(x1) * w1);
+              pk[c][j] = pack_half2(ex2_mufu(x0) * w0, ex2_mufu(x1) * w1);
             }
           }
           if (has_mask) {
-            const uint32_t mb = static_cast<uint32_t>(bits >> (32 * c));
+            const uint32_t mb = static_cast<uint32_t>(bits >> (16 * c)) & 0xFFFFu;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int j = 0; j < 8; ++j) {
               const uint32_t keep = (((mb >> (2 * j)) & 1u) ? 0x0000FFFFu : 0u) | (((mb >> (2 * j + 1)) & 1u) ? 0xFFFF0000u : 0u);
-              pk[c * 16 + j] &= keep;
+              pk[c][j] &= keep;
             }
           }
         }
-        tmem_st32(tL, pk);  // dt(i) over S' columns 0..31 (all 64 columns of S' and G have been read)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_st8(tL + c * 8, pk[c]);  // dt(i) over S' columns 0..31 (all 64 columns of S' and G have been read)
         tmem_wait_st();
         fence_before_sync();
         __syncwarp();
