@@ -253,7 +253,7 @@ def run_reference_gpu_eager(args):
                 impl="reference", device="cuda-eager",
                 config=dict(workload=args.workload, batch_per_gpu=batch, shapes=[list(s) for s in shapes],
                             head_chunk=chunk, **{k: kwargs[k] for k in ("l_c", "l_d")}),
-                peak_mem_gb=torch.cuda.max_memory_allocated(dev) / 2 ** 30)
+                ms_per_step_runs=[round(r, 3) for r in runs], peak_mem_gb=torch.cuda.max_memory_allocated(dev) / 2 ** 30)
     print(json.dumps(line), flush=True)
     return 0
 
@@ -402,13 +402,16 @@ def run_train_step(args):
         for _ in range(args.steps):
             model(list(xs))
         fwd1.record()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        loss = step()
-    e1.record()
-    torch.cuda.synchronize(dev)
-    ms = e0.elapsed_time(e1) / args.steps
+    runs = []   # three K-step regions, the median is reported (the step is ~1100 launches: sensitive to a busy host)
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            loss = step()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        runs.append(e0.elapsed_time(e1) / args.steps)
+    ms = sorted(runs)[1]
     line = dict(metric="HealNet training step (forward + backward) samples/sec", value=batch / (ms * 1e-3),
                 unit="samples/s", n_gpus=1, steps=args.steps, warmup=args.warmup, ms_per_step=ms,
                 ms_forward_only=fwd0.elapsed_time(fwd1) / args.steps, higher_is_better=True, scaling="weak",

@@ -83,3 +83,33 @@ if os.path.exists(lst):
             f.write(f" (bench.py, same code: {ms_step:.2f} ms per step with launches overlapped)")
         f.write(".\n")
     print(open(os.path.join(P, f"{tag}_launches_summary.md")).read()[-1700:])
+
+tl = os.path.join(G, f"{tag}_train_launches.csv")
+if os.path.exists(tl):
+    # launch list of the training step: `ncu --metrics gpu__time_duration.sum ... python bench.py --mode train --steps 1 --warmup 1`
+    shutil.copy(tl, os.path.join(P, f"{tag}_train_launches.csv"))
+    lines = [l for l in open(tl) if not l.startswith("==")]
+    tot = collections.defaultdict(lambda: [0, 0.0])
+    n = 0
+    for row in csv.DictReader(lines):
+        if row.get("Metric Name") != "gpu__time_duration.sum":
+            continue
+        v = float(row["Metric Value"].replace(",", "")) * {"ns": 1e-6, "us": 1e-3, "ms": 1}[row["Metric Unit"]]
+        name = re.sub(r"\(.*", "", row["Kernel Name"])
+        for junk in ("void ", "hn::", "<unnamed>::", "unnamed>::"):
+            name = name.replace(junk, "")
+        tot[name][0] += 1
+        tot[name][1] += v
+        n += 1
+    T = sum(v[1] for v in tot.values())
+    with open(os.path.join(P, f"{tag}_train_launches_summary.md"), "w") as f:
+        f.write(f"# {tag} — launch list of the training step under ncu\n\n")
+        f.write("Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file "
+                f"gpurun_out/{tag}_train_launches.csv python bench.py --mode train --steps 1 --warmup 1 --no-cpu` "
+                f"({n} launches: weight packing, the bench's warm-up and timed training steps and its forward-only "
+                "passes). Per-launch times under ncu are cold-cache and serialised: compare SHARES.\n\n")
+        f.write("| kernel | launches | total ms | share |\n|---|---:|---:|---:|\n")
+        for k, v in sorted(tot.items(), key=lambda kv: -kv[1][1])[:30]:
+            f.write(f"| `{k[:70]}` | {v[0]} | {v[1]:.3f} | {100 * v[1] / T:.2f}% |\n")
+        f.write(f"| **total (all kernels)** | {n} | {T:.3f} | 100% |\n")
+    print("train launch summary written")
