@@ -80,3 +80,33 @@ def test_pinned_host_inputs_in_flight_match_device_inputs():
     for i, (a, b) in enumerate(zip(got, want)):
         assert torch.equal(a, b), f"call {i}: host-staged forward differs from the device-input forward"
     assert len(m._stage_ring) == m.host_staging_depth
+
+
+def test_forward_is_cuda_graph_capturable():
+    """hn_forward is a pure stream-ordered launch sequence (no host sync, no allocation, programmatic dependent launches):
+    a caller may capture it in a CUDA graph; the replay must reproduce the eager logits bit for bit (DESIGN.md 5c,
+    tools/graph_forward.py)."""
+    torch.manual_seed(0)
+    kw = dict(n_modalities=3, channel_dims=[200, 3, 3], num_spatial_axes=[1, 2, 3], out_dims=4, l_c=128, l_d=128, depth=2)
+    m = HealNet(**kw).eval().cuda()
+    xs = [torch.rand(2, 1, 200, device="cuda"), torch.rand(2, 64, 64, 3, device="cuda"),
+          torch.rand(2, 4, 48, 48, 3, device="cuda")]
+    with torch.no_grad():
+        want = m(list(xs)).clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            m(list(xs))
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            got = m(list(xs))
+        for t in xs:
+            t.mul_(0.5)                    # new data in the captured input buffers
+        want2 = None
+        g.replay()
+        torch.cuda.synchronize()
+        replayed = got.clone()
+        want2 = m(list(xs))
+    assert not torch.equal(want, want2)
+    assert torch.equal(replayed, want2), "graph replay differs from the eager forward on the same inputs"
