@@ -889,6 +889,46 @@ class HealNet(nn.Module):
         return out
 
     # ------------------------------------------------------------------------------------------- measurement
+    def capture_graph(self, tensors: Sequence[Optional[torch.Tensor]], return_embeddings: bool = False):
+        """Small-batch serving: captures THIS forward (shapes, dtypes and missing modalities of `tensors`; no mask) in a
+        CUDA graph and returns `run(tensors) -> output`. `run` copies the given tensors (host or device) into the
+        graph's static input buffers and replays it: one launch instead of ~110, bit-identical results (the forward is
+        a pure stream-ordered launch sequence; tests/test_gpu_properties.py, tools/graph_forward.py: -5 % latency at
+        batch 1 on cfg 1). The returned tensor is the graph's static output buffer: consume or clone it before the next
+        `run`. The graph holds the weights as they were packed at capture time: re-capture after changing them."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise RuntimeError("capture_graph() is for inference: call it under torch.no_grad()")
+        dev = next(self.parameters()).device
+        static = [None if t is None else t.detach().to(dev, copy=True).contiguous() for t in tensors]
+        call = lambda: self.forward(list(static), return_embeddings=return_embeddings)
+        keep = self.keep_output_on_device
+        self.keep_output_on_device = True
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                call()                                   # packs the weights / sizes the workspace outside the capture
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = call()
+        finally:
+            self.keep_output_on_device = keep
+        sig = self._weights_sig
+
+        def run(new_tensors):
+            if self._weights_sig != sig:
+                raise RuntimeError("the model's weights changed since capture_graph(): capture again")
+            for dst, src in zip(static, new_tensors):
+                if (dst is None) != (src is None) or (dst is not None and (dst.shape != src.shape or dst.dtype != src.dtype)):
+                    raise ValueError("capture_graph(): inputs must keep the shapes, dtypes and missing modalities of the capture")
+                if dst is not None:
+                    dst.copy_(src, non_blocking=True)
+            graph.replay()
+            return out
+
+        return run
+
     def enable_kernel_timing(self, on: bool = True) -> None:
         """Brackets every cross-attention kernel of subsequent forwards with CUDA events (hn_profile_enable)."""
         if self._handle is None:

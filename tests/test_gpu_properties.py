@@ -110,3 +110,22 @@ def test_forward_is_cuda_graph_capturable():
         want2 = m(list(xs))
     assert not torch.equal(want, want2)
     assert torch.equal(replayed, want2), "graph replay differs from the eager forward on the same inputs"
+
+
+def test_capture_graph_helper_matches_the_eager_forward():
+    """HealNet.capture_graph(): replay on new host / device inputs equals the eager forward; shape changes are refused."""
+    torch.manual_seed(0)
+    kw = dict(n_modalities=3, channel_dims=[200, 3, 3], num_spatial_axes=[1, 2, 3], out_dims=4, l_c=128, l_d=128, depth=2)
+    m = HealNet(**kw).eval().cuda()
+    g = torch.Generator().manual_seed(3)
+    mk = lambda: [torch.rand(1, 1, 200, generator=g), None, torch.rand(1, 4, 48, 48, 3, generator=g)]
+    with torch.no_grad():
+        run = m.capture_graph([t if t is None else t.cuda() for t in mk()])
+        for k in range(3):
+            xs = mk()
+            ins = xs if k % 2 else [t if t is None else t.cuda() for t in xs]       # host tensors and device tensors
+            got = run(ins).clone()
+            want = m([t if t is None else t.cuda() for t in xs])
+            assert torch.equal(got, want)
+        with pytest.raises(ValueError):
+            run([torch.rand(2, 1, 200), None, torch.rand(2, 4, 48, 48, 3)])
