@@ -85,6 +85,9 @@ SIGNATURES = {
     "hn_attention_forward": (c_int, [c_int, c_int, c_long, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_size_t, c_void_p]),
+    "hn_attention_forward_cached": (c_int, [c_int, c_int, c_long, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                            c_size_t, c_int, c_void_p]),
     "hn_op_gemm": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
                            c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "hn_op_layernorm_f16": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_long,

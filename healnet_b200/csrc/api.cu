@@ -1060,6 +1060,14 @@ int hn_attention_forward(int batch, int n_q, long n_ctx, int query_dim, int cont
                          const float* x, const float* context, const float* w_q, const float* w_kv,
                          const float* w_out, const float* b_out, const uint8_t* mask, float* out, void* workspace,
                          size_t workspace_bytes, void* cuda_stream) {
+  return hn_attention_forward_cached(batch, n_q, n_ctx, query_dim, context_dim, heads, dim_head, x, context, w_q, w_kv,
+                                     w_out, b_out, mask, out, workspace, workspace_bytes, 0, cuda_stream);
+}
+
+int hn_attention_forward_cached(int batch, int n_q, long n_ctx, int query_dim, int context_dim, int heads, int dim_head,
+                                const float* x, const float* context, const float* w_q, const float* w_kv,
+                                const float* w_out, const float* b_out, const uint8_t* mask, float* out,
+                                void* workspace, size_t workspace_bytes, int weights_packed, void* cuda_stream) {
   HN_REQUIRE(batch >= 1 && n_q >= 1 && query_dim >= 1 && heads >= 1, "hn_attention_forward: bad shape");
   HN_REQUIRE(dim_head >= 1 && dim_head <= MAX_DIM_HEAD, "hn_attention_forward: dim_head must be in 1..128");
   HN_REQUIRE(x && w_q && w_kv && w_out && b_out && out && workspace, "hn_attention_forward: null argument");
@@ -1091,13 +1099,15 @@ int hn_attention_forward(int batch, int n_q, long n_ctx, int query_dim, int cont
   if (!self)
     HN_TRY2(pack_plain(w.ch, ldc, context, context_dim, static_cast<int>(toks), context_dim, w.prec ? sc : ldc,
                        w.prec ? sc : 0, st));
-  HN_TRY2(pack_headpad_rows(w.wq, 2 * sq, 0, w_q, query_dim, 0, heads, dim_head, query_dim, scale, nullptr, sq, sq, hp,
-                            st));
-  HN_TRY2(pack_headpad_rows(w.wkv, 2 * sc, 0, w_kv, context_dim, 0, heads, dim_head, context_dim, 1.f, nullptr, sc, sc,
-                            hp, st));
-  HN_TRY2(pack_headpad_rows(w.wkv, 2 * sc, hw, w_kv, context_dim, inner, heads, dim_head, context_dim, 1.f, nullptr,
-                            sc, sc, hp, st));
-  HN_TRY2(pack_headpad_cols(w.wo, 2 * hw, w_out, inner, query_dim, heads, dim_head, hw, hw, hp, st));
+  if (!weights_packed) {  // (the packed weights of an earlier call with the same shapes still sit in this workspace)
+    HN_TRY2(pack_headpad_rows(w.wq, 2 * sq, 0, w_q, query_dim, 0, heads, dim_head, query_dim, scale, nullptr, sq, sq, hp,
+                              st));
+    HN_TRY2(pack_headpad_rows(w.wkv, 2 * sc, 0, w_kv, context_dim, 0, heads, dim_head, context_dim, 1.f, nullptr, sc, sc,
+                              hp, st));
+    HN_TRY2(pack_headpad_rows(w.wkv, 2 * sc, hw, w_kv, context_dim, inner, heads, dim_head, context_dim, 1.f, nullptr,
+                              sc, sc, hp, st));
+    HN_TRY2(pack_headpad_cols(w.wo, 2 * hw, w_out, inner, query_dim, heads, dim_head, hw, hw, hp, st));
+  }
   GemmArgs gq{w.xh, w.wq, static_cast<int>(rows), hw, query_dim, 2 * sq, 2 * sq, EPI_F16, 0, nullptr, w.q,
               w.prec ? 2 * hw : hw, 3, sq, sq, w.prec ? hw : 0};
   HN_TRY2(launch_gemm(gq, st));

@@ -212,6 +212,14 @@ HN_API int hn_attention_forward(int batch, int n_q, long n_ctx, int query_dim, i
                          const float* x, const float* context, const float* w_q, const float* w_kv,
                          const float* w_out, const float* b_out, const uint8_t* mask, float* out, void* workspace,
                          size_t workspace_bytes, void* cuda_stream);
+/* Same; weights_packed != 0 promises that `workspace` still holds the packed weights of an earlier call with the SAME
+ * shapes and the same (unchanged) weight tensors, so the four weight-packing launches are skipped (the module-level
+ * Attention keeps one workspace per module and tracks its parameters' versions). */
+HN_API int hn_attention_forward_cached(int batch, int n_q, long n_ctx, int query_dim, int context_dim, int heads,
+                                       int dim_head, const float* x, const float* context, const float* w_q,
+                                       const float* w_kv, const float* w_out, const float* b_out, const uint8_t* mask,
+                                       float* out, void* workspace, size_t workspace_bytes, int weights_packed,
+                                       void* cuda_stream);
 
 /* ---- kernel-level entry points (used by the parity tests and profiling scripts) ------------------ */
 /* C[M,N] = A[M,K] B[N,K]^T on tcgen05; A, B fp16 row-major; epi: 0 f16 out, 1 gated f16 out (N/2 cols),

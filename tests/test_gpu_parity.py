@@ -310,3 +310,24 @@ def test_attention_weight_export_long_axis_and_mask():
     m.export_attention_max_bytes = 1000
     with pytest.raises(MemoryError):
         m([x])
+
+
+def test_standalone_attention_reuses_its_packed_weights_until_they_change():
+    """Attention keeps the packed weights in its workspace (hn_attention_forward_cached): a second call with unchanged
+    parameters skips the packing launches and must give the same result; an in-place parameter update (optimizer step)
+    must be picked up."""
+    from healnet_b200 import Attention
+    torch.manual_seed(0)
+    att = Attention(query_dim=96, context_dim=40, heads=4, dim_head=24).cuda()
+    x, ctx = torch.randn(2, 50, 96, device="cuda"), torch.randn(2, 300, 40, device="cuda")
+    with torch.no_grad():
+        a = att(x, context=ctx)
+        b = att(x, context=ctx)              # cached weights
+        assert torch.equal(a, b)
+        att.to_q.weight.mul_(1.5)            # in-place update bumps the parameter's version
+        c = att(x, context=ctx)
+        fresh = Attention(query_dim=96, context_dim=40, heads=4, dim_head=24).cuda()
+        fresh.load_state_dict(att.state_dict())
+        want = fresh(x, context=ctx)
+    assert not torch.equal(a, c)
+    assert torch.equal(c, want)
