@@ -855,15 +855,12 @@ int hn::forward_impl(hn_handle* h, int batch, const void* const* modality_ptrs, 
           GemmArgs gkv{mp.z, ap.Wkv, static_cast<int>(tok), kvw, mp.C, mp.ldz, 2 * mp.segC, EPI_F16, 0, ap.bkv,
                        ws.kv, mp.precise ? 2 * kvw : kvw, mp.precise ? 3 : 2, mp.segC, mp.segC,
                        mp.precise ? kvw : 0};
-          // Long token axis: the attention contracts P with the hi parts of V only (v_hi_only below). Forming the V half
-          // of the projection from the hi parts of both operands as well (GemmArgs::hi_only_from = ow: one product
-          // instead of three, no lo store) was measured at +15 % on cfg 5 (668 -> 771 samples/s), +7 % on cfg 2 / 4 —
-          // and takes the latent error of the full-size PEAKED cfg 5 case from 4.5e-4 to 7.4e-4, past the 5e-4 that
-          // tests/test_gpu_fullsize.py allows (logits 2.8e-5, far inside theirs): with one dominant token nothing
-          // averages the 2^-12 operand rounding out. Parity first: off.
-          const bool v_hi = false;
-          if (v_hi) gkv.hi_only_from = ow;
-          rc = profile_begin_raw(h, 1, m, 2.0 * tok * (v_hi ? ow * (gkv.terms + 1.0) : kvw * static_cast<double>(gkv.terms)) * round_up(mp.C, 64),
+          // (Long token axis: the attention contracts P with the hi parts of V only, v_hi_only below. Forming the V half of
+          // this projection from single fp16 operands as well — one product instead of three, no lo store — was built and
+          // measured at +15 % on cfg 5, +7 % on cfg 2 / 4, and takes the latent error of the full-size PEAKED cfg 5 case
+          // from 4.5e-4 to 7.4e-4, past the 5e-4 tests/test_gpu_fullsize.py allows: with one dominant token nothing
+          // averages the 2^-12 operand rounding out. Parity first: removed again)
+          rc = profile_begin_raw(h, 1, m, 2.0 * tok * kvw * round_up(mp.C, 64) * gkv.terms,
                                  2.0 * tok * 2.0 * h->I * mp.C, 0.0, st);
           if (rc != 0) return rc;
           HN_TRY(launch_gemm(gkv, st));

@@ -125,10 +125,6 @@ struct GemmArgs {
   int nbatch = 1, nb2 = 1;
   long a_brows = 0, b_brows = 0, out_b1 = 0, out_b2 = 0;
   float alpha = 1.f;  // out (+)= alpha * A B^T (+ bias)
-  // EPI_F16 with split output: output columns >= hi_only_from (a multiple of the N tile) are formed from the hi parts of
-  // both operands only (one product instead of `terms`) and stored without their lo part — the V half of the K/V
-  // projection of a long token axis, which the attention contracts as fp16 hi anyway (AttnArgs::v_hi_only).
-  int hi_only_from = 0x7fffffff;
 };
 int launch_gemm(const GemmArgs& a, cudaStream_t stream);
 // can this residual GEMM also emit the next LayerNorm (GemmArgs::ln_*)? (shape / alignment rules, HN_GEMM_LN switch)

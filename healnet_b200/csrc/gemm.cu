@@ -66,7 +66,6 @@ struct GemmDev {
   int a_brows, b_brows;
   long out_b1, out_b2;
   float alpha;
-  int hi_only_from;      // tiles with n0 >= this run one product (hi.hi) and store no lo part
 };
 
 __device__ __forceinline__ void split_half(float v, __half& hi, __half& lo) {
@@ -112,7 +111,7 @@ __global__ void __launch_bounds__((2 + EPI_WARPS) * 32, 1) gemm_kernel(const __g
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_a = p.terms == 3 ? 2 : 1, n_b = p.terms >= 2 ? 2 : 1;  // distinct A / B tiles per k-tile
-  const int stage_bytes = n_a * A_BYTES + n_b * B_BYTES;               // (ring slot size; hi-only tiles fill less of it)
+  const int stage_bytes = n_a * A_BYTES + n_b * B_BYTES;
   const int stages = p.stages;
   // persistent loop over super-tiles (= tiles when CN == 1); every CTA of a cluster walks the same sequence
   const int crank = CN > 1 ? static_cast<int>(cluster_ctarank()) : 0;
@@ -154,12 +153,10 @@ __global__ void __launch_bounds__((2 + EPI_WARPS) * 32, 1) gemm_kernel(const __g
       for (int tile = first; tile < n_tiles; tile += stride) {
         const int z = tile / tiles_per;
         const int m0 = tile_m0(tile) + z * p.a_brows, n0 = tile_n0(tile) + z * p.b_brows;  // operand ROW coordinates
-        const bool hi_only = tile_n0(tile) >= p.hi_only_from;
-        const int n_a = hi_only ? 1 : (p.terms == 3 ? 2 : 1), n_b = hi_only ? 1 : (p.terms >= 2 ? 2 : 1);
         for (int kt = 0; kt < k_tiles; ++kt, ++it) {
           const int s = it % stages;
           mbar_wait(&empty_bar[s], ((it / stages) & 1) ^ 1);  // (clusters: released by every CTA that reads it)
-          mbar_arrive_expect_tx(&full_bar[s], n_a * A_BYTES + n_b * B_BYTES);
+          mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
           uint8_t* st = smem + s * stage_bytes;
           const int k0 = kt * BK;
           if (CN > 1 && SHARE_A) {  // my quarter (half) of the shared A tile, delivered to every CTA of the cluster
@@ -191,9 +188,6 @@ __global__ void __launch_bounds__((2 + EPI_WARPS) * 32, 1) gemm_kernel(const __g
         mbar_wait(&acc_empty[acc], ((j >> 1) & 1) ^ 1);  // epilogue of tile j-2 has drained this accumulator
         fence_after_sync();
         const uint32_t tD = tmem + acc * BN;
-        const bool hi_only = tile_n0(tile) >= p.hi_only_from;
-        const int terms = hi_only ? 1 : p.terms;
-        const int n_a = terms == 3 ? 2 : 1;
         for (int kt = 0; kt < k_tiles; ++kt, ++it) {
           const int s = it % stages;
           mbar_wait(&full_bar[s], (it / stages) & 1);
@@ -206,8 +200,8 @@ __global__ void __launch_bounds__((2 + EPI_WARPS) * 32, 1) gemm_kernel(const __g
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t dah = smem_desc(a_hi + k * 32, 16, SBO, LAYOUT), dbh = smem_desc(b_hi + k * 32, 16, SBO, LAYOUT);
             umma_ss(tD, dah, dbh, idesc, (kt | k) != 0);
-            if (terms == 3) umma_ss(tD, smem_desc(a_lo + k * 32, 16, SBO, LAYOUT), dbh, idesc, true);
-            if (terms >= 2) umma_ss(tD, dah, smem_desc(b_lo + k * 32, 16, SBO, LAYOUT), idesc, true);
+            if (p.terms == 3) umma_ss(tD, smem_desc(a_lo + k * 32, 16, SBO, LAYOUT), dbh, idesc, true);
+            if (p.terms >= 2) umma_ss(tD, dah, smem_desc(b_lo + k * 32, 16, SBO, LAYOUT), idesc, true);
           }
           if (CN > 1) umma_commit_mc(&empty_bar[s], CMASK); else umma_commit(&empty_bar[s]);
         }
@@ -260,7 +254,7 @@ __global__ void __launch_bounds__((2 + EPI_WARPS) * 32, 1) gemm_kernel(const __g
       if (row_ok) {
       if (p.epi == EPI_F16) {
         __half* o = reinterpret_cast<__half*>(p.out) + static_cast<size_t>(row) * p.ldo + nb;
-        const int out_seg = n0 >= p.hi_only_from ? 0 : p.out_seg;   // hi-only tiles store no lo part
+        const int out_seg = p.out_seg;
         if (full) {
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
@@ -438,8 +432,7 @@ int launch_t(const GemmArgs& a, cudaStream_t stream) {
             half_out ? a.out_seg : 0, stages,
             (a.bias != nullptr && (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0) ? 1 : 0,
             a.ln_gamma, a.ln_beta, a.ln_out, a.ln_ld, a.ln_seg, a.ln_counters, a.ln_epoch, tiles_m, tiles_n, a.bf16,
-            a.nbatch, a.nb2, static_cast<int>(a.a_brows), static_cast<int>(a.b_brows), a.out_b1, a.out_b2, a.alpha,
-            a.hi_only_from};
+            a.nbatch, a.nb2, static_cast<int>(a.a_brows), static_cast<int>(a.b_brows), a.out_b1, a.out_b2, a.alpha};
   const int smem = stages * stage_bytes + 1024;
   // per device, once: SM count and the kernel's shared-memory opt-in (the backward pass makes ~1000 GEMM launches per
   // step: three runtime calls per launch were a visible share of the host's enqueue time)
@@ -501,10 +494,6 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
                "gemm: batched operand rows out of range");
   }
   HN_REQUIRE(a.alpha == 1.f || a.epi == EPI_RES || a.epi == EPI_F32, "gemm: alpha goes with the plain fp32 epilogues");
-  const bool hi_tail = a.hi_only_from < a.N;
-  if (hi_tail)
-    HN_REQUIRE(a.epi == EPI_F16 && a.hi_only_from % 256 == 0 && a.nbatch == 1 && a.ln_out == nullptr,
-               "gemm: the hi-only column tail needs the split fp16 epilogue and a 256-aligned boundary");
   if (a.ln_out != nullptr) {
     const bool resid = a.epi == EPI_RES || a.epi == EPI_RES_LEAKY;
     const bool aligned = (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.ln_out) & 7) == 0 &&
@@ -541,8 +530,6 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   }
   const int tn = (a.N + bn - 1) / bn;
   const bool want_cluster = a.nbatch == 1 && (cl < 0 || (cl > 1 && a.M >= 16384));
-  // (clusters along N share the A tiles of CN consecutive n-tiles: with a hi-only tail every cluster must lie entirely on
-  // one side of the boundary — 256-aligned, and CN * BN <= 256 for all of them)
   if (bk == 64 && want_cluster) {
     if (bn == 64 && tn % 4 == 0) return launch_t<64, 64, 4, true>(a, stream);
     if (bn == 64 && tn % 2 == 0) return launch_t<64, 64, 2, true>(a, stream);
