@@ -75,10 +75,13 @@ struct SmallBwdTcArgs {
   int batch, H, L, nsplit;
   long N;
   int C = 63;           // context width: products only run over the 16-column steps that hold context columns
+  int merged_tail = 0;  // kd 32, 17 <= C <= 23: R_lo rows and z lo rows carry the merged tail (launch_small_bwd_prep)
 };
 int launch_small_attention_bwd(const SmallBwdTcArgs& a, cudaStream_t stream);
 // r / du / delta / stats -> the kernel's operands (R, DU split rows, per-row factors); scale[R] = the power of two DU was
 // multiplied with. Buffers rq / duq must hold rows * rq_ld halves.
+// kd 32 and 17 <= C <= 23: the lo half of an R row is written with the merged tail of the score product
+// ([R_lo 0..15 | R_hi 16..C-1, 0, R_lo 16..C-1, 0..], xattn_small.cu) — set SmallBwdTcArgs::merged_tail accordingly.
 int launch_small_bwd_prep(const float* r, const float* du, const float* delta, const float* stats, int batch, int H,
                           int L, int C, int kd, __half* rq, __half* duq, int rq_ld, int lo_off, float* row_a,
                           float* row_d, float* scale, cudaStream_t st);

@@ -640,10 +640,23 @@ __global__ void __launch_bounds__(256) small_bwd_prep_kernel(const float* __rest
       rv = dead ? 0.f : 10.f - M;   // P_SHIFT - M: exactly the fp16 value the forward folded into Q'
     }
     const __half rh = __float2half_rn(rv), dh = __float2half_rn(dv);
+    const __half rl = __float2half_rn(rv - __half2float(rh));
     rr[c] = rh;
-    rr[lo_off + c] = __float2half_rn(rv - __half2float(rh));
     dr[c] = dh;
     dr[lo_off + c] = __float2half_rn(dv - __half2float(dh));
+    if (kd == 32 && C >= 17 && C <= 23) {
+      // merged tail of the score product (xattn_small.cu): lo half = [R_lo 0..15 | R_hi 16..C-1 | 0 | R_lo 16..C-1 | 0..]
+      if (c < 16) {
+        rr[lo_off + c] = rl;
+      } else if (c < C) {
+        rr[lo_off + c] = rh;
+        rr[lo_off + C + 1 + (c - 16)] = rl;
+      } else if (c == C || c > 2 * C - 16) {
+        rr[lo_off + c] = __float2half_rn(0.f);
+      }
+    } else {
+      rr[lo_off + c] = rl;
+    }
   }
   if (lane == 0) {
     row_a[R] = dead ? 0.f : 0.0009765625f / den;

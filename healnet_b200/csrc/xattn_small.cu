@@ -917,7 +917,7 @@ struct SmallBwdDev {
   int L, H, batch, nsplit, n_ltiles, n_rb, ctas_per_stream, tiles_total;
   int lo_off;           // column offset of the lo parts inside R / DU rows
   int mode;             // KD 32: 0 = C <= 15 (every product fits one 16-column step), 1 = C == 16 (only R_hi.z_hi, which
-                        // carries the fold column, needs the second step), else all steps
+                        // carries the fold column, needs the second step), 2 = merged tail of S' (17 <= C <= 23), else all steps
   long N;
   const uint64_t* mask_bits;
   const float* row_a;   // [(b*L + l)*H + h]  2^-P_SHIFT / den
@@ -1038,8 +1038,9 @@ attn_small_bwd_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_cons
       // S' = R_hi.z_hi + R_lo.z_hi + R_hi.z_lo ; G = DU_hi.z_hi + DU_lo.z_hi over the 16-column steps that hold context
       // columns (KH for the product that carries the fold column, KL for the others), compile-time per mode; dz = the
       // tile's K-operand descriptors (KD 32: from the table)
-      auto issue_sg_c = [&](uint32_t z0, const uint64_t (&dz)[4], auto kh_c, auto kl_c) {
-        constexpr int KH = decltype(kh_c)::value, KL = decltype(kl_c)::value;
+      auto issue_sg_c = [&](uint32_t z0, const uint64_t (&dz)[4], auto kh_c, auto kl_c, auto kg_c, auto mg_c) {
+        constexpr int KH = decltype(kh_c)::value, KL = decltype(kl_c)::value, KG = decltype(kg_c)::value;
+        constexpr bool MG = decltype(mg_c)::value;
         auto zh = [&](int k) { return KD == 32 ? dz[k] : smem_desc(z0 + k * 32, 16, SBO, LAYOUT); };
         auto zl = [&](int k) { return KD == 32 ? dz[2 + k] : smem_desc(z0 + Z_BYTES + k * 32, 16, SBO, LAYOUT); };
 #pragma unroll
@@ -1048,21 +1049,28 @@ attn_small_bwd_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_cons
         for (int k = 0; k < KL; ++k) umma_ss(tG, smem_desc(q0 + Q_TILE + k * 32, 16, SBO, LAYOUT), zh(k), idesc_s, true);
 #pragma unroll
         for (int k = 0; k < KL; ++k) umma_ss(tG, smem_desc(q0 + k * 32, 16, SBO, LAYOUT), zl(k), idesc_s, true);
+        if (MG)  // merged tail (as in the forward): [R_hi tail | 0 | R_lo tail] . [z_lo tail | 0 | z_hi tail], R_lo rows
+                 // arrive re-arranged from launch_small_bwd_prep, the z rows from the context-row builder
+          umma_ss(tG, smem_desc(q0 + Q_TILE + 32, 16, SBO, LAYOUT), zl(1), idesc_s, true);
 #pragma unroll
-        for (int k = 0; k < KL; ++k) umma_ss(tG + 64, smem_desc(q0 + 2 * Q_TILE + k * 32, 16, SBO, LAYOUT), zh(k), idesc_s, k != 0);
+        for (int k = 0; k < KG; ++k) umma_ss(tG + 64, smem_desc(q0 + 2 * Q_TILE + k * 32, 16, SBO, LAYOUT), zh(k), idesc_s, k != 0);
 #pragma unroll
-        for (int k = 0; k < KL; ++k) umma_ss(tG + 64, smem_desc(q0 + 3 * Q_TILE + k * 32, 16, SBO, LAYOUT), zh(k), idesc_s, true);
+        for (int k = 0; k < KG; ++k) umma_ss(tG + 64, smem_desc(q0 + 3 * Q_TILE + k * 32, 16, SBO, LAYOUT), zh(k), idesc_s, true);
         umma_commit(&sg_full[g]);
       };
       using std::integral_constant;
       const int mode = p.mode;
       auto issue_sg = [&](uint32_t z0, const uint64_t (&dz)[4]) {
         constexpr int KF = KD / 16;
+        using I1 = integral_constant<int, 1>;
+        using I2 = integral_constant<int, 2>;
         if (KD == 32) {
-          if (mode == 0) { issue_sg_c(z0, dz, integral_constant<int, 1>{}, integral_constant<int, 1>{}); return; }
-          if (mode == 1) { issue_sg_c(z0, dz, integral_constant<int, 2>{}, integral_constant<int, 1>{}); return; }
+          if (mode == 2) { issue_sg_c(z0, dz, I2{}, I1{}, I2{}, std::true_type{}); return; }
+          if (mode == 0) { issue_sg_c(z0, dz, I1{}, I1{}, I1{}, std::false_type{}); return; }
+          if (mode == 1) { issue_sg_c(z0, dz, I2{}, I1{}, I1{}, std::false_type{}); return; }
         }
-        issue_sg_c(z0, dz, integral_constant<int, KF>{}, integral_constant<int, KF>{});
+        issue_sg_c(z0, dz, integral_constant<int, KF>{}, integral_constant<int, KF>{}, integral_constant<int, KF>{},
+                   std::false_type{});
       };
       auto load_desc4 = [&](int stage, int first, uint64_t (&d)[4]) {
         const uint32_t a = smem_u32(&z_desc[stage][first]);
@@ -1220,7 +1228,7 @@ int launch_small_bwd_t(const SmallBwdTcArgs& a, cudaStream_t stream) {
   p.ctas_per_stream = (p.n_rb + G - 1) / G;
   p.tiles_total = static_cast<int>((a.N + BT - 1) / BT);
   p.lo_off = a.lo_off;
-  p.mode = a.C <= 15 ? 0 : a.C == 16 ? 1 : 3;
+  p.mode = a.C <= 15 ? 0 : a.C == 16 ? 1 : (KD == 32 && a.merged_tail && a.C >= 17 && a.C <= 23) ? 2 : 3;
   p.N = a.N;
   p.mask_bits = a.mask_bits;
   p.row_a = a.row_a;
